@@ -1,0 +1,635 @@
+// Fused attention for sm_100a on tcgen05: S = Q K^T and O += P V run on the 5th-gen tensor cores
+// with S / O accumulators in TMEM; softmax is done one-thread-per-query-row straight out of TMEM
+// (no shuffles), P goes back through SWIZZLE_128B shared memory as the A operand of the PV MMA.
+//
+//   forward : causal, d=128 (Llama; HF llama/modeling_llama.py:199-222, attention_mask=None =>
+//             pure causal, pads attended — muffin/train/trainers.py:199) and non-causal, d=64
+//             (CLIP; HF clip/modeling_clip.py:261-279). Softmax in fp32, P rounded to bf16 before PV.
+//   backward: causal d=128; recomputes S^T / dP^T per (kv tile, q tile), five MMAs per pair;
+//             dK/dV accumulate in TMEM, dQ is reduced with fp32 red.global.add.
+//
+// Layouts: q/k/v/o are [nseq*S rows][ld] bf16 with head h at columns [h*D, h*D+D); q, k, v may be
+// column blocks of one fused qkv buffer. LSE is fp32 [nseq][n_heads][S] (natural log).
+#include "common.cuh"
+#include "host_util.h"
+
+namespace b200 {
+
+constexpr int ATT_BQ = 128;
+constexpr int ATT_BKV = 128;
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+
+// ================================================================================================
+// forward
+// ================================================================================================
+template <int D>
+struct AttFwdCfg {
+  static constexpr uint32_t Q_BYTES = ATT_BQ * D * 2;
+  static constexpr uint32_t KV_BYTES = ATT_BKV * D * 2;   // one of K or V
+  static constexpr uint32_t P_BYTES = ATT_BQ * ATT_BKV * 2;
+  static constexpr uint32_t OFF_Q = 0;
+  static constexpr uint32_t OFF_K = Q_BYTES;                  // 2 stages
+  static constexpr uint32_t OFF_V = OFF_K + 2 * KV_BYTES;     // 2 stages
+  static constexpr uint32_t OFF_P = OFF_V + 2 * KV_BYTES;
+  static constexpr uint32_t OFF_BAR = OFF_P + P_BYTES;
+  static constexpr uint32_t SMEM_BYTES = OFF_BAR + 128 + 1024;
+  static constexpr uint32_t TMEM_COLS = 256;  // S: [0,128), O: [128,128+D)
+};
+
+template <int D, bool CAUSAL>
+__global__ void __launch_bounds__(160, 1)
+attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ out, long long ld_out,
+                     float* __restrict__ lse_out, int S, int n_heads, float scale) {
+  using Cfg = AttFwdCfg<D>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* o_done = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_q_tiles = (S + ATT_BQ - 1) / ATT_BQ;
+  const int q_tile = num_q_tiles - 1 - blockIdx.x;  // heavy (late) tiles first
+  const int head = blockIdx.y, seq = blockIdx.z;
+  const int q0 = q_tile * ATT_BQ;
+  const int n_kv = CAUSAL ? (q_tile + 1) : (S + ATT_BKV - 1) / ATT_BKV;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmK);
+      tma_prefetch_desc(&tmV);
+      mbar_init(q_full, 1);
+      for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+      mbar_init(s_full, 1);
+      mbar_init(p_full, 128);
+      mbar_init(o_done, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+
+  if (warp == 4) {
+    // ------------------------------ control: TMA + MMA issue ------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, ATT_BKV, false, false);
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, D, false, true);
+      const uint32_t q_addr = smem_u32(smem + Cfg::OFF_Q);
+      const uint32_t p_addr = smem_u32(smem + Cfg::OFF_P);
+      auto load_kv = [&](int j) {
+        const int s = j & 1;
+        mbar_arrive_expect_tx(&kv_full[s], 2 * Cfg::KV_BYTES);
+#pragma unroll
+        for (int a = 0; a < D / 64; ++a) {
+          tma_load_3d(smem + Cfg::OFF_K + s * Cfg::KV_BYTES + a * (ATT_BKV * 128), &tmK, &kv_full[s],
+                      head * D + a * 64, j * ATT_BKV, seq);
+          tma_load_3d(smem + Cfg::OFF_V + s * Cfg::KV_BYTES + a * (ATT_BKV * 128), &tmV, &kv_full[s],
+                      head * D + a * 64, j * ATT_BKV, seq);
+        }
+      };
+      auto issue_s = [&](int j) {
+        const int s = j & 1;
+        mbar_wait(&kv_full[s], (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(smem + Cfg::OFF_K + s * Cfg::KV_BYTES);
+#pragma unroll
+        for (int k16 = 0; k16 < D / 16; ++k16) {
+          const uint64_t ad = desc_kmajor(q_addr + (k16 >> 2) * (ATT_BQ * 128), k16 & 3);
+          const uint64_t bd = desc_kmajor(k_addr + (k16 >> 2) * (ATT_BKV * 128), k16 & 3);
+          umma_ss(tmem_S, ad, bd, idesc_s, k16 > 0 ? 1u : 0u);
+        }
+        umma_commit(s_full);
+      };
+      mbar_arrive_expect_tx(q_full, Cfg::Q_BYTES);
+#pragma unroll
+      for (int a = 0; a < D / 64; ++a)
+        tma_load_3d(smem + Cfg::OFF_Q + a * (ATT_BQ * 128), &tmQ, q_full, head * D + a * 64, q0, seq);
+      load_kv(0);
+      if (n_kv > 1) load_kv(1);
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j & 1;
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(smem + Cfg::OFF_V + s * Cfg::KV_BYTES);
+#pragma unroll
+        for (int k16 = 0; k16 < ATT_BKV / 16; ++k16) {
+          const uint64_t ad = desc_kmajor(p_addr + (k16 >> 2) * (ATT_BQ * 128), k16 & 3);
+          const uint64_t bd = desc_mnmajor(v_addr, k16, ATT_BKV);
+          umma_ss(tmem_O, ad, bd, idesc_o, (j > 0 || k16 > 0) ? 1u : 0u);
+        }
+        umma_commit(&kv_empty[s]);
+        umma_commit(o_done);
+        if (j + 1 < n_kv) {
+          issue_s(j + 1);
+          if (j + 2 < n_kv) {
+            mbar_wait(&kv_empty[s], (j >> 1) & 1);
+            load_kv(j + 2);
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------ softmax / epilogue: one thread per query row ------------------------------
+    const int r = warp * 32 + lane;          // row in tile == TMEM lane
+    const int q_idx = q0 + r;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const float c = scale * LOG2E;
+    float m_used = -INFINITY, l = 0.f;
+    uint8_t* p_row = smem + Cfg::OFF_P + r * 128;
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      const int kv0 = j * ATT_BKV;
+      const bool need_mask = (kv0 + ATT_BKV > S) || (CAUSAL && j == q_tile);
+      // pass 1: row max
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_S + lane_off + ch * 32, v);
+        tmem_wait_ld();
+        if (need_mask) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int kv = kv0 + ch * 32 + i;
+            const bool masked = (kv >= S) || (CAUSAL && kv > q_idx);
+            mx = fmaxf(mx, masked ? -INFINITY : __uint_as_float(v[i]));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+      }
+      float m_new = fmaxf(m_used, mx * c);
+      if (m_new == -INFINITY) m_new = 0.f;
+      if (j == 0) {
+        m_used = m_new;
+      } else {
+        const bool need = (m_new - m_used) > 8.0f;
+        mbar_wait(o_done, (j - 1) & 1);  // PV_{j-1} finished: O readable, P smem reusable
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, need)) {
+          const float alpha = need ? exp2f(m_used - m_new) : 1.f;
+          if (need) { m_used = m_new; l *= alpha; }
+#pragma unroll 1
+          for (int ch = 0; ch < D / 32; ++ch) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tmem_O + lane_off + ch * 32, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st_32x32b_x32(tmem_O + lane_off + ch * 32, v);
+          }
+          tmem_wait_st();
+        }
+      }
+      // pass 2: P = exp2(s*c - m) -> bf16 -> swizzled smem; row sum in fp32
+      float rs = 0.f;
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_S + lane_off + ch * 32, v);
+        tmem_wait_ld();
+        float p[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int kv = kv0 + ch * 32 + i;
+          const bool masked = need_mask && ((kv >= S) || (CAUSAL && kv > q_idx));
+          p[i] = masked ? 0.f : exp2f(__uint_as_float(v[i]) * c - m_used);
+          rs += p[i];
+        }
+        uint8_t* base = p_row + (ch >> 1) * (ATT_BQ * 128);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int chunk = ((ch & 1) * 4 + g) ^ (r & 7);
+          uint4 u;
+          u.x = pack_bf16(p[g * 8 + 0], p[g * 8 + 1]);
+          u.y = pack_bf16(p[g * 8 + 2], p[g * 8 + 3]);
+          u.z = pack_bf16(p[g * 8 + 4], p[g * 8 + 5]);
+          u.w = pack_bf16(p[g * 8 + 6], p[g * 8 + 7]);
+          *reinterpret_cast<uint4*>(base + chunk * 16) = u;
+        }
+      }
+      l += rs;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    // epilogue
+    mbar_wait(o_done, (n_kv - 1) & 1);
+    tc_fence_after();
+    const float inv = 1.f / l;
+    const bool row_ok = q_idx < S;
+    bf16* o_row = out + ((long long)seq * S + q_idx) * ld_out + head * D;
+#pragma unroll 1
+    for (int ch = 0; ch < D / 32; ++ch) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem_O + lane_off + ch * 32, v);
+      tmem_wait_ld();
+      if (row_ok) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(v[g * 8 + 0]) * inv, __uint_as_float(v[g * 8 + 1]) * inv);
+          u.y = pack_bf16(__uint_as_float(v[g * 8 + 2]) * inv, __uint_as_float(v[g * 8 + 3]) * inv);
+          u.z = pack_bf16(__uint_as_float(v[g * 8 + 4]) * inv, __uint_as_float(v[g * 8 + 5]) * inv);
+          u.w = pack_bf16(__uint_as_float(v[g * 8 + 6]) * inv, __uint_as_float(v[g * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(o_row + ch * 32 + g * 8) = u;
+        }
+      }
+    }
+    if (row_ok && lse_out)
+      lse_out[((long long)seq * n_heads + head) * S + q_idx] = (m_used + log2f(l)) * LN2;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ================================================================================================
+// backward (causal, D = 128)
+// ================================================================================================
+// delta[seq][head][q] = sum_d dO * O   (fp32)
+__global__ void attention_delta_kernel(const bf16* __restrict__ o, long long ld_o,
+                                       const bf16* __restrict__ d_o, long long ld_do,
+                                       float* __restrict__ delta, int nseq, int S, int n_heads, int D) {
+  const long long total = (long long)nseq * S * n_heads;
+  const int wpb = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  for (long long w = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); w < total;
+       w += (long long)gridDim.x * wpb) {
+    const int head = (int)(w % n_heads);
+    const long long row = w / n_heads;
+    float acc = 0.f;
+    for (int c = lane * 4; c < D; c += 128) {
+      uint2 a = *reinterpret_cast<const uint2*>(o + row * ld_o + head * D + c);
+      uint2 b = *reinterpret_cast<const uint2*>(d_o + row * ld_do + head * D + c);
+      float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), b0 = unpack_bf16(b.x), b1 = unpack_bf16(b.y);
+      acc += a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      const long long seq = row / S;
+      const int q = (int)(row % S);
+      delta[(seq * n_heads + head) * S + q] = acc;
+    }
+  }
+}
+
+struct AttBwdCfg {
+  static constexpr int D = 128;
+  static constexpr uint32_t TILE_BYTES = 128 * 128 * 2;  // 32 KB: any [128 x 128] bf16 tile
+  static constexpr uint32_t OFF_K = 0;
+  static constexpr uint32_t OFF_V = TILE_BYTES;
+  static constexpr uint32_t OFF_Q = 2 * TILE_BYTES;
+  static constexpr uint32_t OFF_DO = 3 * TILE_BYTES;
+  static constexpr uint32_t OFF_PT = 4 * TILE_BYTES;
+  static constexpr uint32_t OFF_DST = 5 * TILE_BYTES;
+  static constexpr uint32_t OFF_LSE = 6 * TILE_BYTES;         // 128 floats
+  static constexpr uint32_t OFF_DELTA = OFF_LSE + 512;        // 128 floats
+  static constexpr uint32_t OFF_BAR = OFF_DELTA + 512;
+  static constexpr uint32_t SMEM_BYTES = OFF_BAR + 128 + 1024;
+  static constexpr uint32_t TMEM_COLS = 512;  // S^T/dQ [0,128) dP^T [128,256) dV [256,384) dK [384,512)
+};
+
+// One CTA per (kv tile, head, seq). Thread r of warps 0..3 owns kv row r of the tile (TMEM lane r).
+__global__ void __launch_bounds__(160, 1)
+attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                     const float* __restrict__ lse, const float* __restrict__ delta,
+                     float* __restrict__ dq_f32, bf16* __restrict__ dk, bf16* __restrict__ dv,
+                     long long ld_dkv, int S, int n_heads, float scale) {
+  using Cfg = AttBwdCfg;
+  constexpr int D = Cfg::D;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* q_full = bars + 1;    // Q_i, dO_i landed
+  uint64_t* st_full = bars + 2;   // S^T and dP^T MMAs done
+  uint64_t* pt_full = bars + 3;   // P^T, dS^T written to smem (128 arrivals)
+  uint64_t* acc_done = bars + 4;  // dV, dK, dQ MMAs of this iteration done
+  uint64_t* dq_read = bars + 5;   // dQ tile drained from TMEM (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  float* s_lse = reinterpret_cast<float*>(smem + Cfg::OFF_LSE);
+  float* s_delta = reinterpret_cast<float*>(smem + Cfg::OFF_DELTA);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = (S + 127) / 128;
+  const int kv_tile = blockIdx.x;
+  const int head = blockIdx.y, seq = blockIdx.z;
+  const int kv0 = kv_tile * 128;
+  const int n_q = num_tiles - kv_tile;  // q tiles kv_tile .. num_tiles-1
+
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
+      mbar_init(kv_full, 1);
+      mbar_init(q_full, 1);
+      mbar_init(st_full, 1);
+      mbar_init(pt_full, 128);
+      mbar_init(acc_done, 1);
+      mbar_init(dq_read, 128);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_ST = tmem_base, tmem_DPT = tmem_base + 128, tmem_DV = tmem_base + 256,
+                 tmem_DK = tmem_base + 384, tmem_DQ = tmem_base;  // dQ reuses the S^T columns
+
+  const uint32_t k_addr = smem_u32(smem + Cfg::OFF_K), v_addr = smem_u32(smem + Cfg::OFF_V);
+  const uint32_t q_addr = smem_u32(smem + Cfg::OFF_Q), do_addr = smem_u32(smem + Cfg::OFF_DO);
+  const uint32_t pt_addr = smem_u32(smem + Cfg::OFF_PT), dst_addr = smem_u32(smem + Cfg::OFF_DST);
+
+  if (warp == 4) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_kk = make_idesc_bf16(128, 128, false, false);  // both K-major
+      constexpr uint32_t idesc_kmn = make_idesc_bf16(128, 128, false, true);  // A K-major, B MN-major
+      constexpr uint32_t idesc_mnmn = make_idesc_bf16(128, 128, true, true);  // both MN-major
+      mbar_arrive_expect_tx(kv_full, 2 * Cfg::TILE_BYTES);
+      for (int a = 0; a < 2; ++a) {
+        tma_load_3d(smem + Cfg::OFF_K + a * 16384, &tmK, kv_full, head * D + a * 64, kv0, seq);
+        tma_load_3d(smem + Cfg::OFF_V + a * 16384, &tmV, kv_full, head * D + a * 64, kv0, seq);
+      }
+      auto load_q = [&](int it) {
+        const int q0 = (kv_tile + it) * 128;
+        mbar_arrive_expect_tx(q_full, 2 * Cfg::TILE_BYTES);
+        for (int a = 0; a < 2; ++a) {
+          tma_load_3d(smem + Cfg::OFF_Q + a * 16384, &tmQ, q_full, head * D + a * 64, q0, seq);
+          tma_load_3d(smem + Cfg::OFF_DO + a * 16384, &tmDO, q_full, head * D + a * 64, q0, seq);
+        }
+      };
+      load_q(0);
+      mbar_wait(kv_full, 0);
+      for (int it = 0; it < n_q; ++it) {
+        mbar_wait(q_full, it & 1);
+        if (it > 0) mbar_wait(dq_read, (it - 1) & 1);  // dQ columns (== S^T columns) drained
+        tc_fence_after();
+        // S^T[kv][q] = K Q^T ; dP^T[kv][q] = V dO^T   (contraction over d, all K-major)
+#pragma unroll
+        for (int k16 = 0; k16 < 8; ++k16) {
+          umma_ss(tmem_ST, desc_kmajor(k_addr + (k16 >> 2) * 16384, k16 & 3),
+                  desc_kmajor(q_addr + (k16 >> 2) * 16384, k16 & 3), idesc_kk, k16 > 0);
+        }
+#pragma unroll
+        for (int k16 = 0; k16 < 8; ++k16) {
+          umma_ss(tmem_DPT, desc_kmajor(v_addr + (k16 >> 2) * 16384, k16 & 3),
+                  desc_kmajor(do_addr + (k16 >> 2) * 16384, k16 & 3), idesc_kk, k16 > 0);
+        }
+        umma_commit(st_full);
+        mbar_wait(pt_full, it & 1);
+        tc_fence_after();
+        // dV[kv][d] += P^T[kv][q] dO[q][d]   (A = P^T K-major over q, B = dO tile read MN-major)
+        // dK[kv][d] += dS^T[kv][q] Q[q][d]
+#pragma unroll
+        for (int k16 = 0; k16 < 8; ++k16) {
+          umma_ss(tmem_DV, desc_kmajor(pt_addr + (k16 >> 2) * 16384, k16 & 3),
+                  desc_mnmajor(do_addr, k16, 128), idesc_kmn, (it > 0 || k16 > 0));
+        }
+#pragma unroll
+        for (int k16 = 0; k16 < 8; ++k16) {
+          umma_ss(tmem_DK, desc_kmajor(dst_addr + (k16 >> 2) * 16384, k16 & 3),
+                  desc_mnmajor(q_addr, k16, 128), idesc_kmn, (it > 0 || k16 > 0));
+        }
+        // dQ[q][d] = dS[q][kv] K[kv][d]  (A = dS^T tile read MN-major: M=q contiguous; B = K tile MN-major)
+#pragma unroll
+        for (int k16 = 0; k16 < 8; ++k16) {
+          umma_ss(tmem_DQ, desc_mnmajor(dst_addr, k16, 128), desc_mnmajor(k_addr, k16, 128), idesc_mnmn,
+                  k16 > 0);
+        }
+        umma_commit(acc_done);
+        if (it + 1 < n_q) {
+          mbar_wait(acc_done, it & 1);  // Q/dO smem free again
+          load_q(it + 1);
+        }
+      }
+    }
+  } else {
+    const int r = warp * 32 + lane;  // kv row within tile, TMEM lane; also q row for the dQ drain
+    const int kv_idx = kv0 + r;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const float c = scale * LOG2E;
+    for (int it = 0; it < n_q; ++it) {
+      const int q_tile = kv_tile + it;
+      const int q0 = q_tile * 128;
+      // stage LSE / delta of this q tile (previous readers finished before last pt_full arrive;
+      // named barrier among the 128 compute threads keeps it simple)
+      asm volatile("bar.sync 1, 128;");
+      {
+        const int q = q0 + r;
+        const long long base = ((long long)seq * n_heads + head) * S;
+        s_lse[r] = q < S ? lse[base + q] * LOG2E : INFINITY;   // exp2(x - inf) = 0 for padded q
+        s_delta[r] = q < S ? delta[base + q] : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;");
+      mbar_wait(st_full, it & 1);
+      tc_fence_after();
+      const bool diag = (q_tile == kv_tile);
+      uint8_t* pt_row = smem + Cfg::OFF_PT + r * 128;
+      uint8_t* dst_row = smem + Cfg::OFF_DST + r * 128;
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t sv[32], dpv[32];
+        tmem_ld_32x32b_x32(tmem_ST + lane_off + ch * 32, sv);
+        tmem_ld_32x32b_x32(tmem_DPT + lane_off + ch * 32, dpv);
+        tmem_wait_ld();
+        float p[32], ds[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int qi = ch * 32 + i;
+          const bool masked = (kv_idx >= S) || (diag && kv_idx > q0 + qi);
+          const float pv = masked ? 0.f : exp2f(__uint_as_float(sv[i]) * c - s_lse[qi]);
+          p[i] = pv;
+          ds[i] = pv * (__uint_as_float(dpv[i]) - s_delta[qi]) * scale;
+        }
+        uint8_t* pb = pt_row + (ch >> 1) * 16384;
+        uint8_t* db = dst_row + (ch >> 1) * 16384;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int chunk = ((ch & 1) * 4 + g) ^ (r & 7);
+          uint4 u, w;
+          u.x = pack_bf16(p[g * 8 + 0], p[g * 8 + 1]); u.y = pack_bf16(p[g * 8 + 2], p[g * 8 + 3]);
+          u.z = pack_bf16(p[g * 8 + 4], p[g * 8 + 5]); u.w = pack_bf16(p[g * 8 + 6], p[g * 8 + 7]);
+          w.x = pack_bf16(ds[g * 8 + 0], ds[g * 8 + 1]); w.y = pack_bf16(ds[g * 8 + 2], ds[g * 8 + 3]);
+          w.z = pack_bf16(ds[g * 8 + 4], ds[g * 8 + 5]); w.w = pack_bf16(ds[g * 8 + 6], ds[g * 8 + 7]);
+          *reinterpret_cast<uint4*>(pb + chunk * 16) = u;
+          *reinterpret_cast<uint4*>(db + chunk * 16) = w;
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(pt_full);
+      // drain dQ tile: TMEM lane r = q row q0 + r
+      mbar_wait(acc_done, it & 1);
+      tc_fence_after();
+      {
+        const int q = q0 + r;
+        float* dq_row = dq_f32 + ((long long)seq * S + q) * ((long long)n_heads * D) + head * D;
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_DQ + lane_off + ch * 32, v);
+          tmem_wait_ld();
+          if (q < S) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) atomicAdd(dq_row + ch * 32 + i, __uint_as_float(v[i]));
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(dq_read);
+    }
+    // epilogue: dV, dK rows (kv row r) -> bf16 global
+    // acc_done for the last iteration was already waited above
+    tc_fence_after();
+    if (kv_idx < S) {
+      bf16* dv_row = dv + ((long long)seq * S + kv_idx) * ld_dkv + head * D;
+      bf16* dk_row = dk + ((long long)seq * S + kv_idx) * ld_dkv + head * D;
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t a[32], b[32];
+        tmem_ld_32x32b_x32(tmem_DV + lane_off + ch * 32, a);
+        tmem_ld_32x32b_x32(tmem_DK + lane_off + ch * 32, b);
+        tmem_wait_ld();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 u, w;
+          u.x = pack_bf16(__uint_as_float(a[g * 8 + 0]), __uint_as_float(a[g * 8 + 1]));
+          u.y = pack_bf16(__uint_as_float(a[g * 8 + 2]), __uint_as_float(a[g * 8 + 3]));
+          u.z = pack_bf16(__uint_as_float(a[g * 8 + 4]), __uint_as_float(a[g * 8 + 5]));
+          u.w = pack_bf16(__uint_as_float(a[g * 8 + 6]), __uint_as_float(a[g * 8 + 7]));
+          w.x = pack_bf16(__uint_as_float(b[g * 8 + 0]), __uint_as_float(b[g * 8 + 1]));
+          w.y = pack_bf16(__uint_as_float(b[g * 8 + 2]), __uint_as_float(b[g * 8 + 3]));
+          w.z = pack_bf16(__uint_as_float(b[g * 8 + 4]), __uint_as_float(b[g * 8 + 5]));
+          w.w = pack_bf16(__uint_as_float(b[g * 8 + 6]), __uint_as_float(b[g * 8 + 7]));
+          *reinterpret_cast<uint4*>(dv_row + ch * 32 + g * 8) = u;
+          *reinterpret_cast<uint4*>(dk_row + ch * 32 + g * 8) = w;
+        }
+      }
+    } else {
+      // keep the warp-collective tcgen05.ld convergent even for rows past S
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t a[32], b[32];
+        tmem_ld_32x32b_x32(tmem_DV + lane_off + ch * 32, a);
+        tmem_ld_32x32b_x32(tmem_DK + lane_off + ch * 32, b);
+        tmem_wait_ld();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+static int make_qkv_tmap(CUtensorMap* tm, const void* ptr, long long ld, int nseq, int S, int cols) {
+  uint64_t dims[3] = {(uint64_t)cols, (uint64_t)S, (uint64_t)nseq};
+  uint64_t str[2] = {(uint64_t)ld * 2, (uint64_t)S * ld * 2};
+  uint32_t box[3] = {64, 128, 1};
+  return make_tmap_bf16(tm, ptr, 3, dims, str, box);
+}
+
+template <int D, bool CAUSAL>
+static int launch_att_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, bf16* out,
+                          long long ld_out, float* lse, int nseq, int S, int n_heads, float scale,
+                          cudaStream_t st) {
+  using Cfg = AttFwdCfg<D>;
+  auto kern = attention_fwd_kernel<D, CAUSAL>;
+  static bool configured = false;
+  if (!configured) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  dim3 grid((S + ATT_BQ - 1) / ATT_BQ, n_heads, nseq);
+  kern<<<grid, 160, Cfg::SMEM_BYTES, st>>>(tq, tk, tv, out, ld_out, lse, S, n_heads, scale);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int rlaifv_attention_fwd(const void* q, const void* k, const void* v, long long ld_qkv, void* out,
+                                    long long ld_out, float* lse, int nseq, int S, int n_heads, int head_dim,
+                                    int causal, float scale, void* stream) {
+  B200_REQUIRE(head_dim == 128 || head_dim == 64, "attention_fwd: head_dim %d not in {64,128}", head_dim);
+  B200_REQUIRE(ld_qkv % 8 == 0 && ld_out % 8 == 0, "attention_fwd: ld must be a multiple of 8");
+  CUtensorMap tq, tk, tv;
+  const int cols = n_heads * head_dim;
+  int rc;
+  if ((rc = make_qkv_tmap(&tq, q, ld_qkv, nseq, S, cols))) return rc;
+  if ((rc = make_qkv_tmap(&tk, k, ld_qkv, nseq, S, cols))) return rc;
+  if ((rc = make_qkv_tmap(&tv, v, ld_qkv, nseq, S, cols))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (head_dim == 128) {
+    return causal ? launch_att_fwd<128, true>(tq, tk, tv, (bf16*)out, ld_out, lse, nseq, S, n_heads, scale, st)
+                  : launch_att_fwd<128, false>(tq, tk, tv, (bf16*)out, ld_out, lse, nseq, S, n_heads, scale, st);
+  }
+  return causal ? launch_att_fwd<64, true>(tq, tk, tv, (bf16*)out, ld_out, lse, nseq, S, n_heads, scale, st)
+                : launch_att_fwd<64, false>(tq, tk, tv, (bf16*)out, ld_out, lse, nseq, S, n_heads, scale, st);
+}
+
+// dq_f32 [nseq*S][n_heads*128] must be zeroed by the caller; delta_ws fp32 [nseq*n_heads*S].
+extern "C" int rlaifv_attention_bwd(const void* q, const void* k, const void* v, long long ld_qkv,
+                                    const void* out, long long ld_out, const void* d_out, long long ld_dout,
+                                    const float* lse, float* dq_f32, void* dk, void* dv, long long ld_dkv,
+                                    float* delta_ws, int nseq, int S, int n_heads, int head_dim, float scale,
+                                    void* stream) {
+  B200_REQUIRE(head_dim == 128, "attention_bwd: head_dim must be 128 (got %d)", head_dim);
+  cudaStream_t st = (cudaStream_t)stream;
+  {
+    const long long total = (long long)nseq * S * n_heads;
+    long long blocks = (total + 7) / 8;
+    if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
+    attention_delta_kernel<<<(int)blocks, 256, 0, st>>>((const bf16*)out, ld_out, (const bf16*)d_out, ld_dout,
+                                                        delta_ws, nseq, S, n_heads, head_dim);
+    B200_CHECK_CUDA(cudaGetLastError());
+  }
+  CUtensorMap tq, tk, tv, tdo;
+  const int cols = n_heads * head_dim;
+  int rc;
+  if ((rc = make_qkv_tmap(&tq, q, ld_qkv, nseq, S, cols))) return rc;
+  if ((rc = make_qkv_tmap(&tk, k, ld_qkv, nseq, S, cols))) return rc;
+  if ((rc = make_qkv_tmap(&tv, v, ld_qkv, nseq, S, cols))) return rc;
+  if ((rc = make_qkv_tmap(&tdo, d_out, ld_dout, nseq, S, cols))) return rc;
+  static bool configured = false;
+  if (!configured) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)AttBwdCfg::SMEM_BYTES));
+    configured = true;
+  }
+  dim3 grid((S + 127) / 128, n_heads, nseq);
+  attention_bwd_kernel<<<grid, 160, AttBwdCfg::SMEM_BYTES, st>>>(tq, tk, tv, tdo, lse, delta_ws, dq_f32,
+                                                                 (bf16*)dk, (bf16*)dv, ld_dkv, S, n_heads, scale);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

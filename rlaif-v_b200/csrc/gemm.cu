@@ -1,0 +1,332 @@
+// bf16 x bf16 -> fp32(TMEM) -> bf16 GEMM for sm_100a: TMA-staged SWIZZLE_128B shared-memory tiles
+// feeding tcgen05.mma (UMMA 128 x BN x 16), persistent warp-specialised CTAs, double-buffered
+// TMEM accumulators so the epilogue of tile i overlaps the main loop of tile i+1.
+//
+// One kernel covers the three operand forms a linear layer needs (reference call sites: every
+// nn.Linear inside HF LlamaDecoderLayer / CLIPEncoderLayer / mm_projector —
+// llava/model/language_model/llava_llama.py:91-102, llava/model/multimodal_projector/builder.py:39-46):
+//   forward  Y[M,N]  = X[M,K]  * W[N,K]^T      A K-major,  B K-major
+//   dgrad    dX[M,K] = dY[M,N] * W[N,K]        A K-major,  B MN-major
+//   wgrad    dW[N,K] = dY[M,N]^T * X[M,K]      A MN-major, B MN-major
+// "K-major" = contraction index contiguous in memory; "MN-major" = the tensor is stored
+// [contraction][M or N] row-major. No transposes are ever materialised.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc),
+// warps 2..5 = epilogue (TMEM lane quadrant = warp % 4).
+#include "common.cuh"
+#include "host_util.h"
+
+namespace b200 {
+
+struct GemmEpilogue {
+  bf16* C;
+  long long ldc;
+  const bf16* bias;      // [N] or nullptr
+  const bf16* residual;  // [M, ldr] or nullptr
+  long long ldr;
+  int act;         // 0 none, 1 GELU(erf), 2 quick_gelu (x*sigmoid(1.702x))
+  int accumulate;  // C = C + result (fp32 add of the old bf16 value)
+};
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 192;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr uint32_t B_BYTES = BN * GEMM_BK * 2;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr uint32_t TMEM_COLS = 2 * BN;
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;  // + barriers + align
+};
+
+__device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& m_blk, int& n_blk) {
+  constexpr int GROUP_M = 16;
+  int per_group = GROUP_M * num_n;
+  int g = t / per_group;
+  int first_m = g * GROUP_M;
+  int gsz = min(num_m - first_m, GROUP_M);
+  int r = t - g * per_group;
+  m_blk = first_m + r % gsz;
+  n_blk = r / gsz;
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == 1) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+  if (act == 2) return v / (1.0f + __expf(-1.702f * v));
+  return v;
+}
+
+template <bool A_MN, bool B_MN, int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 int M, int N, int K, GemmEpilogue epi) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_m = (M + GEMM_BM - 1) / GEMM_BM;
+  const int num_n = (N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_k = (K + GEMM_BK - 1) / GEMM_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < STAGES; ++i) {
+        mbar_init(&full[i], 1);
+        mbar_init(&empty[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&tfull[i], 1);
+        mbar_init(&tempty[i], 4);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int m_blk, n_blk;
+        tile_coords(t, num_m, num_n, m_blk, n_blk);
+        const int m0 = m_blk * GEMM_BM, n0 = n_blk * BN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
+          uint8_t* b_dst = a_dst + Cfg::A_BYTES;
+          mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
+          const int k0 = kb * GEMM_BK;
+          if (A_MN) {
+#pragma unroll
+            for (int a = 0; a < GEMM_BM / 64; ++a)
+              tma_load_2d(a_dst + a * (GEMM_BK * 128), &tmA, &full[s], m0 + a * 64, k0);
+          } else {
+            tma_load_2d(a_dst, &tmA, &full[s], k0, m0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int a = 0; a < BN / 64; ++a)
+              tma_load_2d(b_dst + a * (GEMM_BK * 128), &tmB, &full[s], n0 + a * 64, k0);
+          } else {
+            tma_load_2d(b_dst, &tmB, &full[s], k0, n0);
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, A_MN, B_MN);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_ph = (it >> 1) & 1;
+        mbar_wait(&tempty[acc], acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+#pragma unroll
+          for (int k16 = 0; k16 < GEMM_BK / 16; ++k16) {
+            const uint64_t adesc = A_MN ? desc_mnmajor(a_addr, k16, GEMM_BK) : desc_kmajor(a_addr, k16);
+            const uint64_t bdesc = B_MN ? desc_mnmajor(b_addr, k16, GEMM_BK) : desc_kmajor(b_addr, k16);
+            umma_ss(d_tmem, adesc, bdesc, idesc, (kb > 0 || k16 > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);  // smem slot is free once these MMAs have read it
+          if (kb == num_k - 1) umma_commit(&tfull[acc]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ------------------------------ epilogue ------------------------------
+    const int quad = warp & 3;
+    const int row_in_tile = quad * 32 + lane;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      int m_blk, n_blk;
+      tile_coords(t, num_m, num_n, m_blk, n_blk);
+      const int acc = it & 1;
+      const uint32_t acc_ph = (it >> 1) & 1;
+      mbar_wait(&tfull[acc], acc_ph);
+      tc_fence_after();
+      const long long row = (long long)m_blk * GEMM_BM + row_in_tile;
+      const bool row_ok = row < M;
+      const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
+      bf16* c_row = epi.C + row * epi.ldc;
+      const bf16* r_row = epi.residual ? epi.residual + row * epi.ldr : nullptr;
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_addr + ch * 32, r);
+        tmem_wait_ld();
+        const int col0 = n_blk * BN + ch * 32;
+        if (row_ok && col0 < N) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = col0 + g * 8;
+            if (col < N) {
+              float v[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+              if (epi.bias) {
+                uint4 b4 = __ldg(reinterpret_cast<const uint4*>(epi.bias + col));
+                float2 b0 = unpack_bf16(b4.x), b1 = unpack_bf16(b4.y), b2 = unpack_bf16(b4.z),
+                       b3 = unpack_bf16(b4.w);
+                v[0] += b0.x; v[1] += b0.y; v[2] += b1.x; v[3] += b1.y;
+                v[4] += b2.x; v[5] += b2.y; v[6] += b3.x; v[7] += b3.y;
+              }
+              if (epi.act) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = apply_act(bf16_round(v[j]), epi.act);
+              }
+              if (r_row) {
+                uint4 q4 = *reinterpret_cast<const uint4*>(r_row + col);
+                float2 q0 = unpack_bf16(q4.x), q1 = unpack_bf16(q4.y), q2 = unpack_bf16(q4.z),
+                       q3 = unpack_bf16(q4.w);
+                // reference adds two bf16 tensors: round the linear output first
+                v[0] = bf16_round(v[0]) + q0.x; v[1] = bf16_round(v[1]) + q0.y;
+                v[2] = bf16_round(v[2]) + q1.x; v[3] = bf16_round(v[3]) + q1.y;
+                v[4] = bf16_round(v[4]) + q2.x; v[5] = bf16_round(v[5]) + q2.y;
+                v[6] = bf16_round(v[6]) + q3.x; v[7] = bf16_round(v[7]) + q3.y;
+              }
+              if (epi.accumulate) {
+                uint4 o4 = *reinterpret_cast<const uint4*>(c_row + col);
+                float2 o0 = unpack_bf16(o4.x), o1 = unpack_bf16(o4.y), o2 = unpack_bf16(o4.z),
+                       o3 = unpack_bf16(o4.w);
+                v[0] += o0.x; v[1] += o0.y; v[2] += o1.x; v[3] += o1.y;
+                v[4] += o2.x; v[5] += o2.y; v[6] += o3.x; v[7] += o3.y;
+              }
+              uint4 o;
+              o.x = pack_bf16(v[0], v[1]);
+              o.y = pack_bf16(v[2], v[3]);
+              o.z = pack_bf16(v[4], v[5]);
+              o.w = pack_bf16(v[6], v[7]);
+              *reinterpret_cast<uint4*>(c_row + col) = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <bool A_MN, bool B_MN, int BN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K,
+                       const GemmEpilogue& epi, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_bf16_kernel<A_MN, B_MN, BN>;
+  static bool configured = false;
+  if (!configured) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int num_tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
+  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, epi);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Build the tensor map of one operand. K-major: tensor [rows][kdim] (ld elements per row),
+// box {64, box_rows}. MN-major: tensor [kdim][rows] (ld per k-row), box {64, 64}.
+static int operand_tmap(CUtensorMap* tm, const void* ptr, long long ld, bool mn_major, int rows,
+                        int kdim, int box_rows) {
+  if (!mn_major) {
+    uint64_t dims[2] = {(uint64_t)kdim, (uint64_t)rows};
+    uint64_t str[1] = {(uint64_t)ld * 2};
+    uint32_t box[2] = {64, (uint32_t)box_rows};
+    return make_tmap_bf16(tm, ptr, 2, dims, str, box);
+  } else {
+    uint64_t dims[2] = {(uint64_t)rows, (uint64_t)kdim};
+    uint64_t str[1] = {(uint64_t)ld * 2};
+    uint32_t box[2] = {64, 64};
+    return make_tmap_bf16(tm, ptr, 2, dims, str, box);
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+// C ABI — see include/rlaifv_b200.h for the contract.
+extern "C" int rlaifv_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B,
+                                long long ldb, int b_mn_major, void* C, long long ldc, int M, int N,
+                                int K, const void* bias, const void* residual, long long ldr,
+                                int act, int accumulate, int tile_n, void* stream) {
+  B200_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  B200_REQUIRE(N % 8 == 0 && ldc % 8 == 0, "gemm: N (%d) and ldc (%lld) must be multiples of 8", N,
+               ldc);
+  B200_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8");
+  B200_REQUIRE(!(a_mn_major && !b_mn_major), "gemm: A MN-major with B K-major is not instantiated");
+  B200_REQUIRE(((uintptr_t)C & 15) == 0, "gemm: C not 16-byte aligned");
+  int bn = tile_n;
+  if (bn == 0) {
+    const long long tiles256 = (long long)((M + 127) / 128) * ((N + 255) / 256);
+    bn = (N >= 256 && tiles256 >= 120) ? 256 : 128;
+  }
+  B200_REQUIRE(bn == 128 || bn == 256, "gemm: tile_n must be 0, 128 or 256");
+  CUtensorMap tmA, tmB;
+  int rc = operand_tmap(&tmA, A, lda, a_mn_major != 0, M, K, GEMM_BM);
+  if (rc) return rc;
+  rc = operand_tmap(&tmB, B, ldb, b_mn_major != 0, N, K, bn);
+  if (rc) return rc;
+  GemmEpilogue epi;
+  epi.C = (bf16*)C;
+  epi.ldc = ldc;
+  epi.bias = (const bf16*)bias;
+  epi.residual = (const bf16*)residual;
+  epi.ldr = ldr;
+  epi.act = act;
+  epi.accumulate = accumulate;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!a_mn_major && !b_mn_major)
+    return bn == 256 ? launch_gemm<false, false, 256>(tmA, tmB, M, N, K, epi, st)
+                     : launch_gemm<false, false, 128>(tmA, tmB, M, N, K, epi, st);
+  if (!a_mn_major && b_mn_major)
+    return bn == 256 ? launch_gemm<false, true, 256>(tmA, tmB, M, N, K, epi, st)
+                     : launch_gemm<false, true, 128>(tmA, tmB, M, N, K, epi, st);
+  return bn == 256 ? launch_gemm<true, true, 256>(tmA, tmB, M, N, K, epi, st)
+                   : launch_gemm<true, true, 128>(tmA, tmB, M, N, K, epi, st);
+}
