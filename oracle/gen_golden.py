@@ -1,0 +1,208 @@
+"""ORACLE TOOLING — generates tests/golden/*.npz by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU box):
+
+    PYTHONDONTWRITEBYTECODE=1 python oracle/gen_golden.py
+
+For every case it (1) builds a random-init tiny LlavaLlamaForCausalLM + CLIPVisionTower +
+mlp2x_gelu projector exactly as SURVEY.md Appendix A describes, with weights from
+oracle.llava_dpo_oracle.make_params (deterministic, so no weight file is committed),
+(2) runs the reference's own DataCollatorForDPODataset -> get_beta_and_logps(is_llava15=True) ->
+dpo_loss -> loss.backward() on torch-CPU fp32, (3) checks the restated oracle against those
+outputs (<= 2e-5 relative; index work bit-exact) and (4) writes inputs + reference outputs as a
+small fixture.  The fixture therefore pins BOTH the oracle and (through the oracle-independent
+reference outputs it stores) the CUDA path.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+REF = "/root/reference"
+
+
+def import_reference():
+    if not os.path.isdir(REF):
+        raise SystemExit("reference tree %s not present (golden generation runs in the build container only)" % REF)
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, REF)
+    for name in ("matplotlib", "matplotlib.pyplot"):   # utils/utils.py:19 imports it at module top
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    from llava.model import LlavaLlamaForCausalLM, LlavaConfig                      # noqa
+    from llava.model.multimodal_encoder.clip_encoder import CLIPVisionTower        # noqa
+    from llava.model.multimodal_projector.builder import build_vision_projector    # noqa
+    from muffin.train.trainers import get_beta_and_logps, dpo_loss                 # noqa
+    from muffin.train.train_muffin import DataCollatorForDPODataset                # noqa
+    from muffin.eval.muffin_inference_logp import get_batch_logps                  # noqa
+    from transformers import CLIPVisionModel, CLIPVisionConfig                     # noqa
+    return dict(LlavaLlamaForCausalLM=LlavaLlamaForCausalLM, LlavaConfig=LlavaConfig,
+                CLIPVisionTower=CLIPVisionTower, build_vision_projector=build_vision_projector,
+                get_beta_and_logps=get_beta_and_logps, dpo_loss=dpo_loss,
+                DataCollatorForDPODataset=DataCollatorForDPODataset, get_batch_logps=get_batch_logps,
+                CLIPVisionModel=CLIPVisionModel, CLIPVisionConfig=CLIPVisionConfig)
+
+
+def build_reference_model(R, cfg, params):
+    """SURVEY.md Appendix A recipe: random-init model, CLIP tower attached without network."""
+    lc = R["LlavaConfig"](vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size,
+                          intermediate_size=cfg.intermediate_size, num_hidden_layers=cfg.num_layers,
+                          num_attention_heads=cfg.num_heads, num_key_value_heads=cfg.num_heads,
+                          rms_norm_eps=cfg.rms_eps, rope_theta=cfg.rope_theta, max_position_embeddings=4096,
+                          attn_implementation="eager", tie_word_embeddings=False, pad_token_id=0,
+                          bos_token_id=1, eos_token_id=2)
+    lc.pretraining_tp = 1
+    model = R["LlavaLlamaForCausalLM"](lc)
+    vt = R["CLIPVisionTower"].__new__(R["CLIPVisionTower"])
+    torch.nn.Module.__init__(vt)
+    vt.is_loaded = True
+    vt.vision_tower_name = "synthetic"
+    vt.select_layer = cfg.select_layer
+    vt.select_feature = "patch"
+    vc = R["CLIPVisionConfig"](hidden_size=cfg.clip_hidden, intermediate_size=cfg.clip_intermediate,
+                               num_hidden_layers=cfg.clip_layers, num_attention_heads=cfg.clip_heads,
+                               image_size=cfg.image_size, patch_size=cfg.patch_size, hidden_act="quick_gelu",
+                               layer_norm_eps=cfg.clip_eps, attn_implementation="eager")
+    vt.vision_tower = R["CLIPVisionModel"](vc)
+    vt.vision_tower.requires_grad_(False)
+    model.model.vision_tower = vt
+    model.config.mm_projector_type = "mlp2x_gelu"
+    model.config.mm_hidden_size = cfg.clip_hidden
+    model.model.mm_projector = R["build_vision_projector"](model.config)
+    model.config.tokenizer_model_max_length = cfg.max_len
+    model.config.tokenizer_padding_side = "right"
+    model.float()
+    missing, unexpected = model.load_state_dict({k: v.clone() for k, v in params.items()}, strict=False)
+    missing = [m for m in missing if "rotary" not in m and "position_ids" not in m]
+    assert not missing and not unexpected, (missing, unexpected)
+    return model
+
+
+def make_instances(batch, ref, B):
+    """(rej_dict, win_dict) tuples as DPODataset.__getitem__ yields them
+    (muffin/train/train_llava15.py:140-145, muffin/train/train_utils.py:256-262)."""
+    ids, labs = batch["concatenated_input_ids"], batch["concatenated_labels"]
+    inst = []
+    for i in range(B):
+        def one(row, kind):
+            n = int((ids[row] != 0).sum())     # strip collator padding (pad id 0 never occurs inside)
+            d = {"input_ids": ids[row, :n].clone(), "labels": labs[row, :n].clone(), "image": batch["images"][i]}
+            d[f"ref_{kind}_logp"] = float(ref[f"ref_{kind}_logp"][i])
+            d[f"ref_{kind}_avg_logp"] = float(ref[f"ref_{kind}_avg_logp"][i])
+            d[f"ref_{kind}_per_token_logp"] = [0.0] * (n + 600)
+            return d
+        inst.append((one(B + i, "rej"), one(i, "win")))
+    return inst
+
+
+CASES = {
+    # name: (B, prompt_len, resp_len, seed, image_pos, ragged)
+    "tiny_equal": (1, 20, 16, 11, None, False),
+    "tiny_ragged_b2": (2, 24, 20, 12, 5, True),
+    "tiny_image_first": (2, 16, 12, 13, 1, True),
+}
+
+
+def main():
+    from oracle import llava_dpo_oracle as O
+    R = import_reference()
+    cfg = O.TINY
+    params = O.make_params(cfg, seed=0)
+    model = build_reference_model(R, cfg, params)
+    model.train()
+    out_dir = os.path.join(REPO, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+
+    class Tok:
+        pad_token_id = 0
+
+    class Args:
+        dpo_use_average = False
+        dpo_token_weighted = False
+        task = "DPO"
+
+    for name, (B, P, Rl, seed, ipos, ragged) in CASES.items():
+        batch = O.synthetic_pair_batch(cfg, B, P, Rl, seed, image_pos=ipos, ragged=ragged)
+        g = torch.Generator().manual_seed(seed + 100)
+        ref = {k: (-40.0 + 3.0 * torch.randn(B, generator=g)) for k in ("ref_win_logp", "ref_rej_logp")}
+        ref["ref_win_avg_logp"] = ref["ref_win_logp"] / Rl
+        ref["ref_rej_avg_logp"] = ref["ref_rej_logp"] / Rl
+        collator = R["DataCollatorForDPODataset"](tokenizer=Tok(), beta=0.1, mod_token_weight=1.0)
+        data = collator(make_instances(batch, ref, B))
+        assert torch.equal(data["concatenated_input_ids"], batch["concatenated_input_ids"])
+        assert torch.equal(data["concatenated_labels"], batch["concatenated_labels"])
+        # --- reference forward/backward (unmodified functions) ---
+        model.zero_grad(set_to_none=True)
+        keep_ids = data["concatenated_input_ids"].clone()
+        keep_labels = data["concatenated_labels"].clone()
+        # also capture the spliced embeds/labels the reference builds
+        with torch.no_grad():
+            _, _, _, _, ref_embeds, ref_new_labels = model.prepare_inputs_labels_for_multimodal(
+                input_ids=keep_ids, position_ids=None, attention_mask=None, past_key_values=None,
+                labels=keep_labels, images=torch.cat([data["images"], data["images"]], 0))
+            ref_logits = model.forward(inputs_embeds=ref_embeds, labels=None).logits.float()
+            ref_per_tok, _, _ = R["get_batch_logps"](ref_logits, ref_new_labels, return_all=True)
+        pw, pr, rw, rr, beta = R["get_beta_and_logps"](dict(data), model, Args(), is_llava15=True)
+        losses, cr, rj = R["dpo_loss"](pw, pr, rw, rr, beta=beta)
+        loss = losses.mean()
+        loss.backward()
+        ref_grads = {k: v.grad.detach().clone() for k, v in model.named_parameters() if v.grad is not None}
+        assert all("vision_tower" not in k for k in ref_grads), "CLIP must stay frozen"
+        # --- oracle ---
+        op = {k: v.clone().requires_grad_(k.startswith(O.TRAINABLE_PREFIXES)) for k, v in params.items()}
+        ob = dict(batch, ref_win_logp=ref["ref_win_logp"], ref_rej_logp=ref["ref_rej_logp"])
+        oo = O.dpo_step(op, cfg, ob, beta=0.1)
+        oo["loss"].backward()
+
+        def rel(a, b):
+            return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+        assert torch.equal(oo["labels"], ref_new_labels), "splice labels not bit-exact"
+        assert torch.equal(oo["inputs_embeds"].detach(), ref_embeds), "splice rows not bit-exact"
+        checks = {
+            "per_token_logps": rel(oo["per_token_logps"].detach(), ref_per_tok),
+            "policy_win_logp": rel(oo["policy_win_logp"].detach(), pw.detach()),
+            "policy_rej_logp": rel(oo["policy_rej_logp"].detach(), pr.detach()),
+            "losses": rel(oo["losses"].detach(), losses.detach()),
+            "chosen_rewards": rel(oo["chosen_rewards"], cr),
+        }
+        gsel = ["model.embed_tokens.weight", "lm_head.weight", "model.mm_projector.0.weight",
+                "model.mm_projector.2.bias", "model.layers.0.self_attn.q_proj.weight",
+                "model.layers.1.mlp.down_proj.weight", "model.layers.0.input_layernorm.weight",
+                "model.norm.weight"]
+        for k in ref_grads:
+            checks["grad:" + k] = rel(op[k].grad, ref_grads[k])
+        worst = max(checks.values())
+        print(f"[{name}] oracle vs reference: worst rel err {worst:.3e} over {len(checks)} quantities; "
+              f"loss={float(loss):.6f} T={ref_new_labels.shape[1]}")
+        assert worst < 2e-5, {k: v for k, v in checks.items() if v >= 2e-5}
+        fx = dict(
+            B=np.int64(B), prompt_len=np.int64(P), resp_len=np.int64(Rl), seed=np.int64(seed),
+            image_pos=np.int64(-1 if ipos is None else ipos), ragged=np.int64(int(ragged)),
+            params_checksum=np.float64(O.params_checksum(params)),
+            concatenated_input_ids=keep_ids.numpy(), concatenated_labels=keep_labels.numpy(),
+            images=data["images"].numpy().astype(np.float32),
+            ref_win_logp=ref["ref_win_logp"].numpy(), ref_rej_logp=ref["ref_rej_logp"].numpy(),
+            beta=np.float64(0.1),
+            spliced_labels=ref_new_labels.numpy(),
+            spliced_embeds_rowsum=ref_embeds.double().sum(-1).numpy(),
+            per_token_logps=ref_per_tok.numpy(), policy_win_logp=pw.detach().numpy(),
+            policy_rej_logp=pr.detach().numpy(), losses=losses.detach().numpy(),
+            chosen_rewards=cr.numpy(), rejected_rewards=rj.numpy(), loss=np.float64(float(loss)),
+        )
+        for k in gsel:
+            gk = ref_grads[k]
+            fx["gradnorm:" + k] = np.float64(float(gk.double().norm()))
+            flat = gk.flatten()
+            idx = torch.linspace(0, flat.numel() - 1, 64).long()
+            fx["gradsample:" + k] = flat[idx].numpy()
+        np.savez_compressed(os.path.join(out_dir, name + ".npz"), **fx)
+    print("golden fixtures written to", out_dir)
+
+
+if __name__ == "__main__":
+    main()

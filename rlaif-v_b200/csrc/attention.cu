@@ -507,7 +507,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     // epilogue: dV, dK rows (kv row r) -> bf16 global
     // acc_done for the last iteration was already waited above
     tc_fence_after();
-    if (kv_idx < S) {
+    {
+      const bool row_ok = kv_idx < S;  // loads stay warp-convergent; only the stores are predicated
       bf16* dv_row = dv + ((long long)seq * S + kv_idx) * ld_dkv + head * D;
       bf16* dk_row = dk + ((long long)seq * S + kv_idx) * ld_dkv + head * D;
 #pragma unroll 1
@@ -516,29 +517,22 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tmem_ld_32x32b_x32(tmem_DV + lane_off + ch * 32, a);
         tmem_ld_32x32b_x32(tmem_DK + lane_off + ch * 32, b);
         tmem_wait_ld();
+        if (row_ok) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 u, w;
-          u.x = pack_bf16(__uint_as_float(a[g * 8 + 0]), __uint_as_float(a[g * 8 + 1]));
-          u.y = pack_bf16(__uint_as_float(a[g * 8 + 2]), __uint_as_float(a[g * 8 + 3]));
-          u.z = pack_bf16(__uint_as_float(a[g * 8 + 4]), __uint_as_float(a[g * 8 + 5]));
-          u.w = pack_bf16(__uint_as_float(a[g * 8 + 6]), __uint_as_float(a[g * 8 + 7]));
-          w.x = pack_bf16(__uint_as_float(b[g * 8 + 0]), __uint_as_float(b[g * 8 + 1]));
-          w.y = pack_bf16(__uint_as_float(b[g * 8 + 2]), __uint_as_float(b[g * 8 + 3]));
-          w.z = pack_bf16(__uint_as_float(b[g * 8 + 4]), __uint_as_float(b[g * 8 + 5]));
-          w.w = pack_bf16(__uint_as_float(b[g * 8 + 6]), __uint_as_float(b[g * 8 + 7]));
-          *reinterpret_cast<uint4*>(dv_row + ch * 32 + g * 8) = u;
-          *reinterpret_cast<uint4*>(dk_row + ch * 32 + g * 8) = w;
+          for (int g = 0; g < 4; ++g) {
+            uint4 u, w;
+            u.x = pack_bf16(__uint_as_float(a[g * 8 + 0]), __uint_as_float(a[g * 8 + 1]));
+            u.y = pack_bf16(__uint_as_float(a[g * 8 + 2]), __uint_as_float(a[g * 8 + 3]));
+            u.z = pack_bf16(__uint_as_float(a[g * 8 + 4]), __uint_as_float(a[g * 8 + 5]));
+            u.w = pack_bf16(__uint_as_float(a[g * 8 + 6]), __uint_as_float(a[g * 8 + 7]));
+            w.x = pack_bf16(__uint_as_float(b[g * 8 + 0]), __uint_as_float(b[g * 8 + 1]));
+            w.y = pack_bf16(__uint_as_float(b[g * 8 + 2]), __uint_as_float(b[g * 8 + 3]));
+            w.z = pack_bf16(__uint_as_float(b[g * 8 + 4]), __uint_as_float(b[g * 8 + 5]));
+            w.w = pack_bf16(__uint_as_float(b[g * 8 + 6]), __uint_as_float(b[g * 8 + 7]));
+            *reinterpret_cast<uint4*>(dv_row + ch * 32 + g * 8) = u;
+            *reinterpret_cast<uint4*>(dk_row + ch * 32 + g * 8) = w;
+          }
         }
-      }
-    } else {
-      // keep the warp-collective tcgen05.ld convergent even for rows past S
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t a[32], b[32];
-        tmem_ld_32x32b_x32(tmem_DV + lane_off + ch * 32, a);
-        tmem_ld_32x32b_x32(tmem_DK + lane_off + ch * 32, b);
-        tmem_wait_ld();
       }
     }
   }

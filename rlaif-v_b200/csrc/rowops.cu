@@ -367,6 +367,18 @@ __global__ void gelu_bwd_kernel(const bf16* __restrict__ pre, const bf16* __rest
   }
 }
 
+// GELU(erf) forward on a bf16 tensor (nn.GELU() between the two projector linears)
+__global__ void gelu_fwd_kernel(const bf16* __restrict__ pre, bf16* __restrict__ post, long long n8) {
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n8;
+       idx += (long long)gridDim.x * blockDim.x) {
+    float x[8];
+    load8(pre + idx * 8, x);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = 0.5f * x[j] * (1.f + erff(x[j] * 0.70710678118654752f));
+    store8(post + idx * 8, x);
+  }
+}
+
 // column sums of a bf16 matrix [M][N] -> bias grad (fp32 accumulate, bf16 out, optional +=)
 __global__ void colsum_kernel(const bf16* __restrict__ x, long long M, int N, float* __restrict__ part) {
   // grid (ceil(N/256), P); each block sums rows blockIdx.y, +P, ... for 256 columns (2 per thread)
@@ -859,6 +871,12 @@ extern "C" int rlaifv_swiglu_fwd(const void* gu, void* act, long long M, int F, 
 extern "C" int rlaifv_swiglu_bwd(const void* gu, const void* dact, void* dgu, long long M, int F, void* stream) {
   B200_REQUIRE(F % 8 == 0, "swiglu: F %% 8 != 0");
   swiglu_bwd_kernel<<<grid_for(M * (F / 8), 256), 256, 0, ST>>>((const bf16*)gu, (const bf16*)dact, (bf16*)dgu, M, F);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int rlaifv_gelu_fwd(const void* pre, void* post, long long n, void* stream) {
+  B200_REQUIRE(n % 8 == 0, "gelu_fwd: n %% 8 != 0");
+  gelu_fwd_kernel<<<grid_for(n / 8, 256), 256, 0, ST>>>((const bf16*)pre, (bf16*)post, n / 8);
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -29,6 +29,7 @@ _SIGNATURES = {
     "rlaifv_rope_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_ll, c_void_p],
     "rlaifv_swiglu_fwd": [c_void_p, c_void_p, c_ll, c_int, c_void_p],
     "rlaifv_swiglu_bwd": [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p],
+    "rlaifv_gelu_fwd": [c_void_p, c_void_p, c_ll, c_void_p],
     "rlaifv_gelu_bwd": [c_void_p, c_void_p, c_void_p, c_ll, c_void_p],
     "rlaifv_colsum": [c_void_p, c_ll, c_int, c_void_p, c_int, c_void_p, c_void_p],
     "rlaifv_clip_im2col": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],

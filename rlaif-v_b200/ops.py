@@ -51,3 +51,260 @@ def gemm(a, b, out=None, *, a_mn=False, b_mn=False, bias=None, residual=None, ac
             residual.stride(0) if residual is not None else 0, int(act), int(accumulate), int(tile_n),
             _l.stream_ptr())
     return out
+
+
+def attention_fwd(q, k, v, nseq, S, n_heads, head_dim, causal, scale, out=None, lse=None):
+    """q/k/v: [nseq*S, ld] views (column blocks allowed) sharing one row stride."""
+    _chk(q), _chk(k), _chk(v)
+    assert q.stride(0) == k.stride(0) == v.stride(0) and q.stride(1) == 1
+    M = nseq * S
+    if out is None:
+        out = torch.empty((M, n_heads * head_dim), dtype=torch.bfloat16, device=q.device)
+    if lse is None:
+        lse = torch.empty((nseq, n_heads, S), dtype=torch.float32, device=q.device)
+    _l.call("rlaifv_attention_fwd", _l.ptr(q), _l.ptr(k), _l.ptr(v), q.stride(0), _l.ptr(out), out.stride(0),
+            _l.ptr(lse), nseq, S, n_heads, head_dim, int(causal), float(scale), _l.stream_ptr())
+    return out, lse
+
+
+def attention_bwd(q, k, v, out, d_out, lse, nseq, S, n_heads, head_dim, scale, dq_f32, dk, dv, delta_ws=None):
+    """dq_f32 [M, n_heads*head_dim] fp32 must be zeroed; dk/dv bf16 views with a shared row stride."""
+    _chk(q), _chk(k), _chk(v), _chk(out), _chk(d_out), _chk(dk), _chk(dv)
+    _chk(dq_f32, torch.float32), _chk(lse, torch.float32)
+    assert dk.stride(0) == dv.stride(0)
+    if delta_ws is None:
+        delta_ws = torch.empty((nseq, n_heads, S), dtype=torch.float32, device=q.device)
+    _l.call("rlaifv_attention_bwd", _l.ptr(q), _l.ptr(k), _l.ptr(v), q.stride(0), _l.ptr(out), out.stride(0),
+            _l.ptr(d_out), d_out.stride(0), _l.ptr(lse), _l.ptr(dq_f32), _l.ptr(dk), _l.ptr(dv), dk.stride(0),
+            _l.ptr(delta_ws), nseq, S, n_heads, head_dim, float(scale), _l.stream_ptr())
+    return dq_f32, dk, dv
+
+
+# --------------------------------------------------------------------------------------------
+# row kernels
+# --------------------------------------------------------------------------------------------
+_f32 = torch.float32
+
+
+def rmsnorm_fwd(x, w, eps, out=None, rstd=None):
+    _chk(x), _chk(w)
+    M, H = x.shape
+    assert x.is_contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    _l.call("rlaifv_rmsnorm_fwd", _l.ptr(x), _l.ptr(w), _l.ptr(out), _l.ptr(rstd), M, H, float(eps),
+            _l.stream_ptr())
+    return out
+
+
+_norm_ws = {}
+
+
+def _norm_workspace(H, device):
+    n = _l.load().rlaifv_rmsnorm_bwd_partials()
+    key = (H, device)
+    if key not in _norm_ws:
+        _norm_ws[key] = torch.empty((n, H), dtype=_f32, device=device)
+    return _norm_ws[key]
+
+
+def rmsnorm_bwd(dy, x, w, rstd, dx, dw, dres=None, dw_accumulate=True):
+    """dx = rmsnorm'(dy) (+ dres); dw (+)= sum_rows dy * xhat."""
+    _chk(dy), _chk(x), _chk(w), _chk(dx), _chk(dw), _chk(rstd, _f32)
+    M, H = x.shape
+    ws = _norm_workspace(H, x.device)
+    _l.call("rlaifv_rmsnorm_bwd", _l.ptr(dy), _l.ptr(x), _l.ptr(w), _l.ptr(rstd), _l.ptr(dres), _l.ptr(dx),
+            _l.ptr(dw), int(dw_accumulate), _l.ptr(ws), M, H, _l.stream_ptr())
+    return dx
+
+
+def layernorm_fwd(x, w, b, eps, out=None):
+    _chk(x), _chk(w), _chk(b)
+    M, H = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    _l.call("rlaifv_layernorm_fwd", _l.ptr(x), _l.ptr(w), _l.ptr(b), _l.ptr(out), M, H, float(eps),
+            _l.stream_ptr())
+    return out
+
+
+def rope_fwd(qkv, cos, sin, T, n_heads, head_dim):
+    _chk(qkv), _chk(cos), _chk(sin)
+    _l.call("rlaifv_rope_fwd", _l.ptr(qkv), _l.ptr(cos), _l.ptr(sin), qkv.shape[0], T, n_heads, head_dim,
+            qkv.stride(0), _l.stream_ptr())
+    return qkv
+
+
+def rope_bwd(dqkv, dq_f32, cos, sin, T, n_heads, head_dim):
+    _chk(dqkv), _chk(dq_f32, _f32)
+    _l.call("rlaifv_rope_bwd", _l.ptr(dqkv), _l.ptr(dq_f32), _l.ptr(cos), _l.ptr(sin), dqkv.shape[0], T,
+            n_heads, head_dim, dqkv.stride(0), _l.stream_ptr())
+    return dqkv
+
+
+def swiglu_fwd(gu, out=None):
+    _chk(gu)
+    M, F2 = gu.shape
+    if out is None:
+        out = torch.empty((M, F2 // 2), dtype=torch.bfloat16, device=gu.device)
+    _l.call("rlaifv_swiglu_fwd", _l.ptr(gu), _l.ptr(out), M, F2 // 2, _l.stream_ptr())
+    return out
+
+
+def swiglu_bwd(gu, dact, dgu=None):
+    _chk(gu), _chk(dact)
+    M, F2 = gu.shape
+    if dgu is None:
+        dgu = torch.empty_like(gu)
+    _l.call("rlaifv_swiglu_bwd", _l.ptr(gu), _l.ptr(dact), _l.ptr(dgu), M, F2 // 2, _l.stream_ptr())
+    return dgu
+
+
+def gelu_fwd(pre, post=None):
+    _chk(pre)
+    if post is None:
+        post = torch.empty_like(pre)
+    _l.call("rlaifv_gelu_fwd", _l.ptr(pre), _l.ptr(post), pre.numel(), _l.stream_ptr())
+    return post
+
+
+def gelu_bwd(pre, dpost, dpre=None):
+    _chk(pre), _chk(dpost)
+    if dpre is None:
+        dpre = torch.empty_like(pre)
+    _l.call("rlaifv_gelu_bwd", _l.ptr(pre), _l.ptr(dpost), _l.ptr(dpre), pre.numel(), _l.stream_ptr())
+    return dpre
+
+
+def colsum(x, db, accumulate=True):
+    _chk(x), _chk(db)
+    M, N = x.shape
+    ws = torch.empty((64, N), dtype=_f32, device=x.device)
+    _l.call("rlaifv_colsum", _l.ptr(x), M, N, _l.ptr(db), int(accumulate), _l.ptr(ws), _l.stream_ptr())
+    return db
+
+
+def clip_im2col(images, patch, k_pad):
+    _chk(images)
+    N, C, S, _ = images.shape
+    G = S // patch
+    out = torch.empty((N * G * G, k_pad), dtype=torch.bfloat16, device=images.device)
+    _l.call("rlaifv_clip_im2col", _l.ptr(images), _l.ptr(out), N, C, S, patch, k_pad, _l.stream_ptr())
+    return out
+
+
+def clip_embed(patch_out, cls, pos, n_img, n_patch):
+    _chk(patch_out), _chk(cls), _chk(pos)
+    H = patch_out.shape[1]
+    x = torch.empty((n_img * (n_patch + 1), H), dtype=torch.bfloat16, device=patch_out.device)
+    _l.call("rlaifv_clip_embed", _l.ptr(patch_out), _l.ptr(cls), _l.ptr(pos), _l.ptr(x), n_img, n_patch, H,
+            _l.stream_ptr())
+    return x
+
+
+def clip_drop_cls(x, n_img, n_patch):
+    _chk(x)
+    H = x.shape[1]
+    out = torch.empty((n_img * n_patch, H), dtype=torch.bfloat16, device=x.device)
+    _l.call("rlaifv_clip_drop_cls", _l.ptr(x), _l.ptr(out), n_img, n_patch, H, _l.stream_ptr())
+    return out
+
+
+def splice_count(ids, n_feat_tokens, max_len):
+    assert ids.dtype == torch.int64 and ids.is_cuda and ids.is_contiguous()
+    nseq, L = ids.shape
+    n_img = torch.empty(nseq, dtype=torch.int32, device=ids.device)
+    lens = torch.empty(nseq, dtype=torch.int32, device=ids.device)
+    _l.call("rlaifv_splice_count", _l.ptr(ids), nseq, L, n_feat_tokens, max_len, _l.ptr(n_img), _l.ptr(lens),
+            _l.stream_ptr())
+    return n_img, lens
+
+
+def splice_map(ids, labels, n_img, img_index, n_feat_tokens, T, max_len):
+    nseq, L = ids.shape
+    src = torch.empty((nseq, T), dtype=torch.int32, device=ids.device)
+    new_labels = torch.empty((nseq, T), dtype=torch.int64, device=ids.device)
+    assert img_index.dtype == torch.int32 and (labels is None or labels.is_contiguous())
+    _l.call("rlaifv_splice_map", _l.ptr(ids), _l.ptr(labels), _l.ptr(n_img), _l.ptr(img_index), nseq, L,
+            n_feat_tokens, T, max_len, _l.ptr(src), _l.ptr(new_labels), _l.stream_ptr())
+    return src, new_labels
+
+
+def splice_gather(src, ids, embed, feat, out=None):
+    _chk(embed), _chk(feat)
+    nseq, T = src.shape
+    H = embed.shape[1]
+    if out is None:
+        out = torch.empty((nseq * T, H), dtype=torch.bfloat16, device=embed.device)
+    _l.call("rlaifv_splice_gather", _l.ptr(src), _l.ptr(ids), _l.ptr(embed), _l.ptr(feat), _l.ptr(out), nseq,
+            ids.shape[1], T, H, _l.stream_ptr())
+    return out
+
+
+def splice_scatter(src, ids, dx, d_embed_f32, d_feat_f32):
+    _chk(dx)
+    nseq, T = src.shape
+    H = dx.shape[1]
+    _l.call("rlaifv_splice_scatter", _l.ptr(src), _l.ptr(ids), _l.ptr(dx), _l.ptr(d_embed_f32),
+            _l.ptr(d_feat_f32), nseq, ids.shape[1], T, H, _l.stream_ptr())
+
+
+def f32_to_bf16(src, dst, accumulate=False):
+    _chk(src, _f32), _chk(dst)
+    assert src.numel() == dst.numel()
+    _l.call("rlaifv_f32_to_bf16", _l.ptr(src), _l.ptr(dst), src.numel(), int(accumulate), _l.stream_ptr())
+    return dst
+
+
+def logp_fwd(logits, labels, nseq, T):
+    """logits [nseq*T, V] bf16 (row stride may exceed V); labels [nseq, T] int64 (spliced).
+    Returns per_tok [nseq, T-1], lse [nseq, T], logp_sum, logp_avg, count [nseq] (all fp32)."""
+    _chk(logits)
+    assert labels.dtype == torch.int64 and labels.is_contiguous()
+    V = logits.shape[1]
+    dev = logits.device
+    per_tok = torch.empty((nseq, T - 1), dtype=_f32, device=dev)
+    lse = torch.zeros((nseq, T), dtype=_f32, device=dev)
+    s = torch.empty(nseq, dtype=_f32, device=dev)
+    a = torch.empty(nseq, dtype=_f32, device=dev)
+    c = torch.empty(nseq, dtype=_f32, device=dev)
+    _l.call("rlaifv_logp_fwd", _l.ptr(logits), logits.stride(0), _l.ptr(labels), nseq, T, V, _l.ptr(per_tok),
+            _l.ptr(lse), _l.ptr(s), _l.ptr(a), _l.ptr(c), _l.stream_ptr())
+    return per_tok, lse, s, a, c
+
+
+def logp_bwd(logits, labels, lse, d_logp, nseq, T, count=None):
+    """In place: logits <- d loss / d logits."""
+    _chk(logits), _chk(lse, _f32), _chk(d_logp, _f32)
+    _l.call("rlaifv_logp_bwd", _l.ptr(logits), logits.stride(0), _l.ptr(labels), _l.ptr(lse), _l.ptr(d_logp),
+            _l.ptr(count), nseq, T, logits.shape[1], _l.stream_ptr())
+    return logits
+
+
+def dpo_loss(policy_win, policy_rej, ref_win, ref_rej, beta, dpo_weight=1.0, sft_weight=0.0, grad_scale=1.0,
+             want_grad=True):
+    for t in (policy_win, policy_rej, ref_win, ref_rej):
+        _chk(t, _f32)
+    B = policy_win.numel()
+    dev = policy_win.device
+    losses = torch.empty(B, dtype=_f32, device=dev)
+    cr = torch.empty(B, dtype=_f32, device=dev)
+    rr = torch.empty(B, dtype=_f32, device=dev)
+    dpw = torch.empty(B, dtype=_f32, device=dev) if want_grad else None
+    dpr = torch.empty(B, dtype=_f32, device=dev) if want_grad else None
+    out9 = torch.empty(9, dtype=_f32, device=dev)
+    _l.call("rlaifv_dpo_loss", _l.ptr(policy_win), _l.ptr(policy_rej), _l.ptr(ref_win), _l.ptr(ref_rej), B,
+            float(beta), float(dpo_weight), float(sft_weight), float(grad_scale), _l.ptr(losses), _l.ptr(cr),
+            _l.ptr(rr), _l.ptr(dpw), _l.ptr(dpr), _l.ptr(out9), _l.stream_ptr())
+    return losses, cr, rr, dpw, dpr, out9
+
+
+def adamw_step(master, exp_avg, exp_avg_sq, grad, param_bf16, lr, beta1, beta2, eps, weight_decay, step,
+               grad_scale=1.0):
+    _chk(master, _f32), _chk(exp_avg, _f32), _chk(exp_avg_sq, _f32), _chk(param_bf16)
+    assert grad.dtype in (torch.bfloat16, torch.float32)
+    n = master.numel()
+    assert grad.numel() == n and param_bf16.numel() == n
+    _l.call("rlaifv_adamw_step", _l.ptr(master), _l.ptr(exp_avg), _l.ptr(exp_avg_sq), _l.ptr(grad),
+            int(grad.dtype == torch.float32), _l.ptr(param_bf16), n, float(lr), float(beta1), float(beta2),
+            float(eps), float(weight_decay), int(step), float(grad_scale), _l.stream_ptr())
