@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py — preference-pairs/sec of one full LLaVA-1.5-7B DPO optimisation step on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            (N=1)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" = policy forward on chosen+rejected (CLIP -> projector -> splice -> 32 decoder layers ->
+lm_head -> log-prob gather), DPO loss + gradient, full backward, ZeRO-2 gradient reduction and the
+fused fp32 AdamW, on BASELINE.json configs[1]: 8 synthetic pairs per GPU, 336x336 images,
+48-token prompt + 512-token responses (T = 1135), bf16, random-init weights at true dimensions.
+
+`value`  : whole-job pairs/s with the step's inputs already resident in HBM.
+`e2e`    : same metric through the public call DPOStepEngine.train_step() with HOST (pinned) buffers:
+           H2D of ids/labels/images/ref-logps and a D2H read of the loss inside the timed region.
+`roofline`: dominant kernel = the tcgen05 GEMM; achieved = sum(2MNK) / sum(CUDA-event durations) of
+           every GEMM launch of one instrumented step, against MEASURED_PEAKS.json.
+`cpu_baseline` / `--impl reference`: the oracle port of the reference path (oracle/llava_dpo_oracle.py)
+           on the host cores, on a bounded sample (see cpu_reference_pairs_per_sec).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+PAIRS_PER_GPU = 8
+PROMPT_LEN, RESP_LEN, IMAGE_POS = 48, 512, 35
+
+
+def flops_per_pair(T):
+    """F_pair = 3*2*F_seq(T) + F_clip + 3*F_proj (algorithmic, no recompute)."""
+    n_dec = 32 * (4 * 4096 ** 2 + 3 * 4096 * 11008)
+    n_head = 4096 * 32000
+    f_seq = 2 * (n_dec + n_head) * T + 32 * 4 * T * T * 4096 * 0.5
+    f_clip = 2 * 23 * (4 * 1024 ** 2 + 2 * 1024 * 4096) * 577 + 23 * 4 * 577 ** 2 * 1024 + 2 * 588 * 1024 * 576
+    f_proj = 2 * (1024 * 4096 + 4096 ** 2) * 576
+    return 3 * 2 * f_seq + f_clip + 3 * f_proj
+
+
+def measured_peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("bf16_tflops_sustained", 1400.0), d.get("bf16_tflops", 1590.0), "measured"
+    return 1400.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def synthetic_batch(rank, step, B):
+    """SURVEY.md §8d canonical inputs (seed 1234 + 1000*rank + step), host tensors (pinned)."""
+    g = torch.Generator().manual_seed(1234 + 1000 * rank + step)
+    L = PROMPT_LEN + RESP_LEN
+    ids = torch.empty((2 * B, L), dtype=torch.int64)
+    labels = torch.full((2 * B, L), -100, dtype=torch.int64)
+    for i in range(B):
+        prompt = torch.randint(3, 32000, (PROMPT_LEN,), generator=g)
+        prompt[0] = 1
+        prompt[IMAGE_POS] = -200
+        for row in (i, B + i):
+            resp = torch.randint(3, 32000, (RESP_LEN,), generator=g)
+            resp[-1] = 2
+            ids[row] = torch.cat([prompt, resp])
+            labels[row, PROMPT_LEN:] = resp
+    images = torch.randn(B, 3, 336, 336, generator=g)
+    return {"concatenated_input_ids": ids.pin_memory(), "concatenated_labels": labels.pin_memory(),
+            "images": images.pin_memory(), "beta": 0.1}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: oracle port of the reference path on the host cores, bounded sample
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_pairs_per_sec(dtype_name="float32"):
+    """Times oracle.dpo_step fwd + bwd + AdamW at FULL WIDTH (h=4096, ffn=11008, vocab=32000,
+    CLIP-L 23 layers, 336 px) on config (a) shape (1 pair, 64-token responses, T=687) with 1 and 2
+    decoder layers, and extrapolates linearly to 32 layers."""
+    from oracle import llava_dpo_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    dt = getattr(torch, dtype_name)
+    times = {}
+    for nl in (1, 2):
+        cfg = O.OracleConfig(num_layers=nl)
+        p = O.make_params(cfg, seed=0, dtype=dt)
+        for k in p:
+            if k.startswith(O.TRAINABLE_PREFIXES):
+                p[k].requires_grad_(True)
+        batch = O.synthetic_pair_batch(cfg, 1, 48, 64, seed=1234, image_pos=35)
+        batch["images"] = batch["images"].to(dt)
+        batch["ref_win_logp"] = torch.tensor([-660.0])
+        batch["ref_rej_logp"] = torch.tensor([-661.0])
+        names = O.trainable_names(p)
+        state = {k: (torch.zeros_like(p[k], dtype=torch.float32), torch.zeros_like(p[k], dtype=torch.float32))
+                 for k in names}
+        t0 = time.perf_counter()
+        out = O.dpo_step(p, cfg, batch, beta=0.1)
+        out["loss"].backward()
+        with torch.no_grad():
+            for k in names:
+                new_p, m, v = O.adamw_update(p[k].float(), p[k].grad.float(), state[k][0], state[k][1], 1, 5e-7)
+                p[k].copy_(new_p.to(dt))
+        times[nl] = time.perf_counter() - t0
+        del p, state, out
+    t_layer = max(times[2] - times[1], 1e-9)
+    t_full = times[1] + 31 * t_layer
+    sample = ("oracle port, torch-CPU %s, full width, 1 pair, R=64 (T=687): fwd+bwd+AdamW timed with 1 and 2 "
+              "decoder layers (%.1fs, %.1fs) and extrapolated linearly to 32 layers" % (dtype_name, times[1], times[2]))
+    return 1.0 / t_full, os.cpu_count() or 1, sample
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    vals = []
+    for _ in range(max(1, min(args.steps, 1))):
+        v, cores, sample = cpu_reference_pairs_per_sec()
+        vals.append(v)
+    value = sum(vals) / len(vals)
+    line = {"impl": "reference", "metric": "preference-pairs/sec LLaVA-1.5-7B DPO step", "value": value,
+            "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "LLaVA-1.5-7B DPO step (reference CPU path via oracle port; config (a) shape, "
+                                   "extrapolated to 32 layers)"},
+            "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--micro-pairs", type=int, default=0, help="pairs per micro-batch (0 = auto)")
+    ap.add_argument("--layers", type=int, default=32, help="debug only; anything but 32 is not the benchmark")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from rlaifv_b200 import lib, ops
+    from rlaifv_b200.engine import DPOStepEngine
+    from rlaifv_b200.model import LlavaDims, LlavaDPOPolicy
+
+    dims = LlavaDims(num_layers=args.layers)
+    B = PAIRS_PER_GPU
+    micro = args.micro_pairs or (4 if world == 1 else B)   # 1 GPU holds the unsharded 81 GB optimizer state
+    policy = LlavaDPOPolicy(dims, torch.device("cuda", local_rank), seed=0)
+    engine = DPOStepEngine(policy, lr=5e-7, weight_decay=0.01, total_steps=2672, micro_pairs=micro,
+                           rank=rank, world=world)
+    T = PROMPT_LEN + RESP_LEN - 1 + dims.num_patches
+
+    # frozen-reference log-probs = initial policy log-probs (step-0 loss = ln 2 known answer)
+    host_batches = [synthetic_batch(rank, s, B) for s in range(2)]
+    for hb in host_batches:
+        rw, rr = [], []
+        for lo in range(0, B, micro):
+            hi = min(B, lo + micro)
+            ids = torch.cat([hb["concatenated_input_ids"][lo:hi], hb["concatenated_input_ids"][B + lo:B + hi]])
+            lab = torch.cat([hb["concatenated_labels"][lo:hi], hb["concatenated_labels"][B + lo:B + hi]])
+            out = policy.forward_logps(ids, lab, hb["images"][lo:hi], keep_stash=False)
+            rw.append(out["logp"][: hi - lo].float().cpu())
+            rr.append(out["logp"][hi - lo:].float().cpu())
+        hb["ref_win_logp"] = torch.cat(rw).pin_memory()
+        hb["ref_rej_logp"] = torch.cat(rr).pin_memory()
+    dev_batches = [{k: (v.cuda(local_rank) if torch.is_tensor(v) else v) for k, v in hb.items()} for hb in host_batches]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    loss_host = torch.zeros(9, dtype=torch.float32).pin_memory()
+
+    def run_steps(batches, n, read_back):
+        for s in range(n):
+            m = engine.train_step(batches[s % len(batches)])
+            if read_back:
+                loss_host.copy_(m, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+
+    step0 = engine.train_step(dev_batches[0], optimizer_step=False)   # known-answer check (no update)
+    loss0 = float(step0[0].item())
+
+    # ---- device-resident timing (value) ----
+    run_steps(dev_batches, args.warmup, False)
+    sampler = ClockSampler(local_rank)
+    launches0 = lib.launch_count()
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run_steps(dev_batches, args.steps, False)
+    e1.record()
+    barrier()
+    ms_dev = e0.elapsed_time(e1) / args.steps
+    launches = (lib.launch_count() - launches0) // max(1, args.steps)
+    # ---- end-to-end timing through the public call with host buffers (e2e) ----
+    run_steps(host_batches, 1, True)
+    barrier()
+    e0.record()
+    run_steps(host_batches, args.steps, True)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1) / args.steps
+    clocks = sampler.stop()
+    t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = t.tolist()
+
+    # ---- roofline of the dominant kernel: every GEMM launch of one instrumented step ----
+    gemm_events = []
+    orig_gemm = ops.gemm
+
+    def timed_gemm(a, b, out=None, **kw):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        r = orig_gemm(a, b, out, **kw)
+        e.record()
+        K = a.shape[0] if kw.get("a_mn") else a.shape[1]
+        gemm_events.append((s, e, 2.0 * r.shape[0] * r.shape[1] * K))
+        return r
+
+    ops.gemm = timed_gemm
+    try:
+        import rlaifv_b200.model as _m
+        _m.ops.gemm = timed_gemm
+        engine.train_step(dev_batches[0])
+        torch.cuda.synchronize()
+    finally:
+        ops.gemm = orig_gemm
+        _m.ops.gemm = orig_gemm
+    gemm_ms = sum(s.elapsed_time(e) for s, e, _ in gemm_events)
+    gemm_flops = sum(f for _, _, f in gemm_events)
+    peak_sus, peak_burst, peak_kind = measured_peaks()
+    achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
+
+    total_pairs = B * world
+    value = total_pairs / (ms_dev * 1e-3)
+    e2e_value = total_pairs / (ms_e2e * 1e-3)
+    hb = host_batches[0]
+    h2d = sum(v.numel() * v.element_size() for v in hb.values() if torch.is_tensor(v))
+    f_pair = flops_per_pair(T)
+    line = {
+        "metric": "preference-pairs/sec LLaVA-1.5-7B DPO step", "value": value, "unit": "pairs/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "LLaVA-1.5-7B DPO bf16, %d pairs/GPU, 336px, 512-tok responses (T=%d), ZeRO-2 AdamW"
+                               % (B, T),
+                   "layers": args.layers, "pairs_per_gpu": B, "micro_pairs": micro, "parallelism": "dp%d" % world,
+                   "l2": "per-step working set (>100 GB of weights/activations) is far larger than the 126 MB L2",
+                   "step0_loss": loss0, "step0_loss_expected": math.log(2.0)},
+        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 36,
+                "ms_per_step": ms_e2e},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "model_flops_per_pair": f_pair,
+        "step_tflops_per_gpu": value / world * f_pair / 1e12,
+        "step_frac_of_peak": {"measured_sustained_%g" % peak_sus: value / world * f_pair / 1e12 / peak_sus,
+                              "measured_burst_%g" % peak_burst: value / world * f_pair / 1e12 / peak_burst,
+                              "datasheet_2250": value / world * f_pair / 1e12 / 2250.0},
+        "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05)", "achieved": achieved,
+                     "peak": peak_sus, "unit": "TFLOP/s", "frac": achieved / peak_sus, "traffic": None,
+                     "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step); burst %g"
+                                    % (peak_kind, peak_burst),
+                     "gemm_launches": len(gemm_events), "gemm_ms_per_step": gemm_ms,
+                     "gemm_share_of_step": gemm_ms / ms_dev},
+    }
+    if rank == 0:
+        if not args.no_cpu_baseline and world == 1:
+            v, cores, sample = cpu_reference_pairs_per_sec()
+            line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,131 @@
+/* rlaifv_b200.h — C ABI of librlaifv_b200.so: the B200 (sm_100a) kernels of the LLaVA-1.5 DPO
+ * training step that replaces the reference's HF/torch hot path.
+ *
+ * Conventions
+ *  - Every function returns 0 on success, <0 on error (-1 bad argument, -2 CUDA error, -3 driver /
+ *    tensor-map error); the message is available from rlaifv_last_error() (thread-local).
+ *    Nothing throws or aborts.
+ *  - All pointers are raw DEVICE pointers owned by the caller (PyTorch storage in this repo);
+ *    the library borrows them for the duration of the enqueued work and allocates nothing.
+ *  - `stream` is a cudaStream_t (the caller's current stream); all work is enqueued asynchronously,
+ *    no host synchronisation happens inside.
+ *  - "bf16" = __nv_bfloat16 storage. Row-major everywhere; `ld*` = elements between rows.
+ *  - The reference has no FFI of its own (pure Python): each entry point names the reference code
+ *    whose arithmetic it replaces. "HF:" = transformers/models/ (pinned 4.35.0, pyproject.toml:22).
+ */
+#ifndef RLAIFV_B200_H_
+#define RLAIFV_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* rlaifv_last_error(void);
+
+/* ---- dense contractions (tcgen05 / TMA) -------------------------------------------------------
+ * C[M,N] (+)= op(A) * op(B)^T (+ bias[N]) -> act -> (+ residual[M,N]).
+ *   a_mn_major = 0: A is [M][K] (K contiguous)      1: A is stored [K][M]
+ *   b_mn_major = 0: B is [N][K] (K contiguous)      1: B is stored [K][N]
+ *   act: 0 none, 1 GELU(erf), 2 quick_gelu.  accumulate: C += result.  tile_n: 0 auto, 128, 256.
+ * Replaces every nn.Linear forward / dgrad / wgrad of HF LlamaDecoderLayer (HF:llama/modeling_llama.py
+ * :182-184,:262-264,:289), lm_head (llava/model/language_model/llava_llama.py:91-102), CLIP layers
+ * (HF:clip/modeling_clip.py:300-351), the patch-embedding conv as im2col GEMM (:148-154) and the
+ * mm_projector (llava/model/multimodal_projector/builder.py:39-46). */
+int rlaifv_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb,
+                     int b_mn_major, void* C, long long ldc, int M, int N, int K, const void* bias,
+                     const void* residual, long long ldr, int act, int accumulate, int tile_n,
+                     void* stream);
+
+/* ---- attention (tcgen05, S/O accumulators in TMEM) ---------------------------------------------
+ * q/k/v/out: [nseq*S][ld] bf16, head h at columns [h*head_dim, (h+1)*head_dim); lse fp32
+ * [nseq][n_heads][S]. head_dim 128 (Llama, causal) or 64 (CLIP, non-causal).
+ * Replaces HF:llama/modeling_llama.py:199-222 (eager causal attention; attention_mask=None as set at
+ * muffin/train/trainers.py:199) and HF:clip/modeling_clip.py:261-279. */
+int rlaifv_attention_fwd(const void* q, const void* k, const void* v, long long ld_qkv, void* out,
+                         long long ld_out, float* lse, int nseq, int S, int n_heads, int head_dim,
+                         int causal, float scale, void* stream);
+/* causal, head_dim 128. dq_f32 [nseq*S][n_heads*128] fp32 must be zeroed by the caller (reduced with
+ * atomics); dk/dv bf16 [nseq*S][ld_dkv]; delta_ws fp32 [nseq*n_heads*S] scratch. */
+int rlaifv_attention_bwd(const void* q, const void* k, const void* v, long long ld_qkv, const void* out,
+                         long long ld_out, const void* d_out, long long ld_dout, const float* lse,
+                         float* dq_f32, void* dk, void* dv, long long ld_dkv, float* delta_ws, int nseq,
+                         int S, int n_heads, int head_dim, float scale, void* stream);
+
+/* ---- norms (HF:llama/modeling_llama.py:62-67; HF:clip LayerNorm) -------------------------------- */
+int rlaifv_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd_or_null, int M, int H, float eps,
+                       void* stream);
+int rlaifv_rmsnorm_bwd_partials(void); /* rows of the fp32 [partials][H] workspace rmsnorm_bwd needs */
+int rlaifv_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd,
+                       const void* dres_or_null, void* dx, void* dw, int dw_accumulate, float* workspace,
+                       int M, int H, void* stream);
+int rlaifv_layernorm_fwd(const void* x, const void* w, const void* b, void* y, int M, int H, float eps,
+                         void* stream);
+
+/* ---- RoPE on the fused qkv buffer (HF:llama/modeling_llama.py:124-168; positions 0..T-1 because
+ * position_ids are not forwarded, llava_llama.py:94). cos/sin: bf16 [T][head_dim]. In place. */
+int rlaifv_rope_fwd(void* qkv, const void* cos_tab, const void* sin_tab, long long M, int T, int n_heads,
+                    int head_dim, long long ld, void* stream);
+int rlaifv_rope_bwd(void* dqkv, const float* dq_f32, const void* cos_tab, const void* sin_tab, long long M,
+                    int T, int n_heads, int head_dim, long long ld, void* stream);
+
+/* ---- SwiGLU on the fused [gate | up] buffer (HF:llama/modeling_llama.py:182-184), GELU of the projector */
+int rlaifv_swiglu_fwd(const void* gu, void* act, long long M, int F, void* stream);
+int rlaifv_swiglu_bwd(const void* gu, const void* dact, void* dgu, long long M, int F, void* stream);
+int rlaifv_gelu_fwd(const void* pre, void* post, long long n, void* stream);
+int rlaifv_gelu_bwd(const void* pre, const void* dpost, void* dpre, long long n, void* stream);
+int rlaifv_colsum(const void* x, long long M, int N, void* db, int accumulate, float* workspace_64xN,
+                  void* stream);
+
+/* ---- CLIP embedding helpers (HF:clip/modeling_clip.py:202-219; clip_encoder.py:36-44) ----------- */
+int rlaifv_clip_im2col(const void* images, void* out, int n_img, int channels, int size, int patch,
+                       int k_pad, void* stream);
+int rlaifv_clip_embed(const void* patch, const void* cls, const void* pos, void* x, int n_img, int n_patch,
+                      int H, void* stream);
+int rlaifv_clip_drop_cls(const void* x, void* out, int n_img, int n_patch, int H, void* stream);
+
+/* ---- image-token splice (llava/model/llava_arch.py:150-330, attention_mask=None path) -----------
+ * ids/labels int64 [nseq][L]; IMAGE_TOKEN_INDEX = -200, IGNORE_INDEX = -100. Integer outputs are
+ * bit-exact w.r.t. the reference; row gathers are pure copies.
+ *   splice_count : n_img[b], len[b] = min(L - n_img + n_img*P, max_len)
+ *   splice_map   : src[b][t] (>=0 token position, -1-r feature row r, INT_MIN pad), new_labels[b][t]
+ *   splice_gather: out[b][t][:] = embed[ids[b][src]] | feat[r] | 0
+ *   splice_scatter: backward (fp32 atomics into d_embed [V][H] / d_feat [rows][H]) */
+int rlaifv_splice_count(const long long* ids, int nseq, int L, int P, int max_len, int* n_img, int* len,
+                        void* stream);
+int rlaifv_splice_map(const long long* ids, const long long* labels, const int* n_img, const int* img_index,
+                      int nseq, int L, int P, int T, int max_len, int* src, long long* new_labels,
+                      void* stream);
+int rlaifv_splice_gather(const int* src, const long long* ids, const void* embed, const void* feat, void* out,
+                         int nseq, int L, int T, int H, void* stream);
+int rlaifv_splice_scatter(const int* src, const long long* ids, const void* dx, float* d_embed, float* d_feat,
+                          int nseq, int L, int T, int H, void* stream);
+int rlaifv_f32_to_bf16(const float* in, void* out, long long n, int accumulate, void* stream);
+
+/* ---- per-token log-prob gather (muffin/eval/muffin_inference_logp.py:82-115) ---------------------
+ * logits bf16 [nseq*T][ld] (upcast to fp32 inside, as pinned transformers 4.35 does), labels = spliced
+ * labels [nseq][T]. per_tok [nseq][T-1], lse [nseq][T], logp_sum/logp_avg/count [nseq].
+ * logp_bwd overwrites logits with d loss / d logits given d loss / d logp_sum (count != NULL:
+ * average mode). */
+int rlaifv_logp_fwd(const void* logits, long long ld, const long long* labels, int nseq, int T, int V,
+                    float* per_tok, float* lse, float* logp_sum, float* logp_avg, float* count, void* stream);
+int rlaifv_logp_bwd(void* logits, long long ld, const long long* labels, const float* lse, const float* d_logp,
+                    const float* count_or_null, int nseq, int T, int V, void* stream);
+
+/* ---- DPO loss + gradient (muffin/train/trainers.py:91-126, :279-311) ---------------------------
+ * out9: [0] loss = DPO_w*mean(losses) - SFT_w*mean(pw); [1..8] local means of chosen_reward,
+ * rejected_reward, accuracy, margin, logp_rejected, logp_chosen, ref_rejected, ref_chosen. */
+int rlaifv_dpo_loss(const float* policy_win, const float* policy_rej, const float* ref_win,
+                    const float* ref_rej, int B, float beta, float dpo_weight, float sft_weight,
+                    float grad_scale, float* losses, float* chosen_rewards, float* rejected_rewards,
+                    float* d_policy_win, float* d_policy_rej, float* out9, void* stream);
+
+/* ---- fused AdamW on a flat shard (torch.optim.AdamW; optim=adamw_torch, muffin/train/train_llava15.py:75;
+ * fp32 master/moments as under DeepSpeed bf16 + ZeRO-2, script/zero2.json). */
+int rlaifv_adamw_step(float* master, float* exp_avg, float* exp_avg_sq, const void* grad, int grad_is_f32,
+                      void* param_bf16, long long n, float lr, float beta1, float beta2, float eps,
+                      float weight_decay, int step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RLAIFV_B200_H_ */

@@ -1,0 +1,108 @@
+"""DPO training-step engine: the public call a user makes for one optimisation step.
+
+`DPOStepEngine.train_step(batch)` takes the reference collator's batch dict
+(DataCollatorForDPODataset.__call__, muffin/train/train_muffin.py:43-112 — host tensors), copies
+the step's inputs host->device, runs policy forward on chosen+rejected, the DPO loss + gradient
+kernel, the hand-written backward, the (ZeRO-2) gradient reduction and the fused AdamW, and
+returns the metrics of LLaVA15DPOTrainer.compute_loss (muffin/train/trainers.py:279-311).
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .model import LlavaDPOPolicy
+from .zero2 import Zero2AdamW, cosine_lr
+
+_F32 = torch.float32
+
+METRIC_NAMES = ("loss", "rewards_train/chosen", "rewards_train/rejected", "rewards_train/accuracies",
+                "rewards_train/margins", "logps_train/rejected", "logps_train/chosen",
+                "logps_train/ref_rejected", "logps_train/ref_chosen")
+
+
+class DPOStepEngine:
+    def __init__(self, policy: LlavaDPOPolicy, lr=5e-7, weight_decay=0.01, betas=(0.9, 0.999), eps=1e-8,
+                 total_steps=2672, warmup_ratio=0.05, dpo_use_average=False, micro_pairs=None,
+                 rank=0, world=1, group=None, constant_lr=False):
+        self.policy = policy
+        self.rank, self.world, self.group = rank, world, group
+        self.opt = Zero2AdamW(policy.store, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
+                              rank=rank, world=world, group=group)
+        self.base_lr, self.total_steps, self.warmup_ratio = lr, total_steps, warmup_ratio
+        self.constant_lr = constant_lr
+        self.dpo_use_average = dpo_use_average
+        self.micro_pairs = micro_pairs
+        self.global_step = 0
+        self._metrics = torch.zeros(9, dtype=_F32, device=policy.device)
+        self._last_micro = False
+        # ZeRO-2 overlap: reduce a layer's bucket as soon as its backward finished (last micro-batch only)
+        policy.on_layer_grads_ready = self._layer_ready
+
+    def _layer_ready(self, layer):
+        if self._last_micro:
+            self.opt.reduce_bucket(1 + layer)      # bucket order: embed, layer0.., head, projector
+
+    def _h2d(self, t, dtype=None):
+        if not t.is_cuda:
+            if not t.is_pinned():
+                t = t.pin_memory()
+            t = t.to(self.policy.device, non_blocking=True)
+        return t if dtype is None else t.to(dtype)
+
+    def train_step(self, batch, optimizer_step=True):
+        """batch: dict with concatenated_input_ids/labels [2B,L] (win rows first), images [B,3,S,S],
+        ref_win_logp / ref_rej_logp [B] (or the *_avg_* variants when dpo_use_average), beta."""
+        pol = self.policy
+        ids = self._h2d(batch["concatenated_input_ids"])
+        labels = self._h2d(batch["concatenated_labels"])
+        images = self._h2d(batch["images"])
+        key = "avg_logp" if self.dpo_use_average else "logp"
+        rw = self._h2d(batch["ref_win_" + key]).to(_F32)
+        rr = self._h2d(batch["ref_rej_" + key]).to(_F32)
+        # HF Trainer._prepare_inputs casts float inputs to bf16 under DeepSpeed bf16:
+        # the reference logps are therefore bf16-rounded before dpo_loss.
+        rw = rw.to(torch.bfloat16).to(_F32)
+        rr = rr.to(torch.bfloat16).to(_F32)
+        beta = float(batch["beta"])
+        B = images.shape[0]
+        mp = self.micro_pairs or B
+        sft_w = float(os.environ.get("SFT_weight", 0.0))     # muffin/train/trainers.py:299-300
+        dpo_w = float(os.environ.get("DPO_weight", 1.0))
+        self._metrics.zero_()
+        n_micro = (B + mp - 1) // mp
+        for mi in range(n_micro):
+            lo, hi = mi * mp, min(B, (mi + 1) * mp)
+            b = hi - lo
+            self._last_micro = mi == n_micro - 1
+            mids = torch.cat([ids[lo:hi], ids[B + lo:B + hi]], 0)
+            mlab = torch.cat([labels[lo:hi], labels[B + lo:B + hi]], 0)
+            out = pol.forward_logps(mids, mlab, images[lo:hi], keep_stash=True)
+            lp = out["avg_logp"] if self.dpo_use_average else out["logp"]
+            _, _, _, dpw, dpr, out9 = ops.dpo_loss(lp[:b].contiguous(), lp[b:].contiguous(), rw[lo:hi].contiguous(),
+                                                   rr[lo:hi].contiguous(), beta, dpo_w, sft_w,
+                                                   grad_scale=(b / B) / self.world)
+            self._metrics.add_(out9, alpha=b / B)
+            pol.backward_logps(torch.cat([dpw, dpr]).contiguous(), use_average=self.dpo_use_average,
+                               accumulate=mi > 0)
+        pol.finalize_embed_grad()
+        if self.world > 1:
+            self.opt.reduce_bucket(0)                         # embed
+            self.opt.reduce_bucket(len(self.opt.slices) - 2)  # head
+            self.opt.reduce_bucket(len(self.opt.slices) - 1)  # projector
+        if optimizer_step:
+            lr = self.base_lr if self.constant_lr else cosine_lr(self.global_step, self.total_steps, self.base_lr,
+                                                                 self.warmup_ratio)
+            self.opt.step(lr)
+            self.global_step += 1
+        return self._metrics
+
+    def metrics_dict(self, metrics=None):
+        """One small all-reduce + one D2H for the 9 scalars (the reference does 7 gathers + 7 syncs)."""
+        m = (self._metrics if metrics is None else metrics).clone()
+        if self.world > 1:
+            dist.all_reduce(m, op=dist.ReduceOp.SUM, group=self.group)
+            m /= self.world
+        vals = m.tolist()
+        return dict(zip(METRIC_NAMES, vals))

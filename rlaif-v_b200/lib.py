@@ -106,8 +106,18 @@ def last_error():
     return load().rlaifv_last_error().decode("utf-8", "replace")
 
 
+_launches = 0
+
+
+def launch_count():
+    """Number of C-ABI kernel-launching calls made so far (each launches >= 1 CUDA kernel)."""
+    return _launches
+
+
 def call(name, *args):
+    global _launches
     lib = load()
+    _launches += 1
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise B200Error("%s failed (rc=%d): %s" % (name, rc, last_error()))

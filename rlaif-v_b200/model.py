@@ -1,0 +1,485 @@
+"""LLaVA-1.5 DPO policy on the B200 kernels: parameter storage + hand-written forward / backward.
+
+Mirrors what the reference executes in `get_beta_and_logps(..., is_llava15=True)`
+(muffin/train/trainers.py:205-231): CLIP tower (frozen, llava/model/multimodal_encoder/clip_encoder.py:46-58)
+-> mm_projector (llava/model/multimodal_projector/builder.py:39-46) -> image-token splice
+(llava/model/llava_arch.py:150-330) -> Llama decoder (llava/model/language_model/llava_llama.py:57-102)
+-> per-token log-prob gather (muffin/eval/muffin_inference_logp.py:82-115) — and the backward of
+all trainable parts.  There is no autograd here: the backward is an explicit sequence of kernel
+launches over an activation stash.
+
+All arithmetic runs in the C-ABI library (ops.*); torch supplies device memory, streams and
+zero-fills.  Parameters live in ONE flat bf16 buffer cut into buckets (embed | layer i | head |
+projector); gradients in a same-layout flat buffer, so the ZeRO-2 optimizer (zero2.py) can
+reduce-scatter / update / all-gather bucket slices in place.
+"""
+import math
+from dataclasses import dataclass, field
+
+import torch
+
+from . import ops
+
+IGNORE_INDEX = -100
+IMAGE_TOKEN_INDEX = -200
+_BF = torch.bfloat16
+_F32 = torch.float32
+
+
+@dataclass
+class LlavaDims:
+    """Dimensions (defaults = LLaVA-1.5-7B + CLIP-ViT-L/14-336; script/train/llava15_train.sh:8,11)."""
+    vocab_size: int = 32000
+    hidden_size: int = 4096
+    intermediate_size: int = 11008
+    num_layers: int = 32
+    num_heads: int = 32
+    rms_eps: float = 1e-5
+    rope_theta: float = 10000.0
+    max_len: int = 2048
+    clip_hidden: int = 1024
+    clip_intermediate: int = 4096
+    clip_layers: int = 24
+    clip_heads: int = 16
+    image_size: int = 336
+    patch_size: int = 14
+    clip_eps: float = 1e-5
+    select_layer: int = -2
+
+    @property
+    def head_dim(self):
+        return self.hidden_size // self.num_heads
+
+    @property
+    def num_patches(self):
+        return (self.image_size // self.patch_size) ** 2
+
+    @property
+    def clip_layers_used(self):
+        return self.clip_layers + 1 + self.select_layer if self.select_layer < 0 else self.select_layer
+
+    @property
+    def patch_k(self):
+        return 3 * self.patch_size * self.patch_size
+
+    @property
+    def patch_k_pad(self):
+        return (self.patch_k + 63) // 64 * 64
+
+
+def _round_up(n, m):
+    return (n + m - 1) // m * m
+
+
+@dataclass
+class Segment:
+    name: str           # storage name (fused tensors have their own names)
+    shape: tuple
+    offset: int         # element offset in the flat buffer
+    decay: bool
+
+
+@dataclass
+class Bucket:
+    name: str
+    start: int
+    size: int            # padded to a multiple of PAD
+    decay_size: int      # leading part that gets weight decay; the rest (norm weights, biases) does not
+    segments: list = field(default_factory=list)
+
+
+class ParamStore:
+    """Flat bf16 parameter / gradient storage with named views.
+
+    Storage tensors: embed, per layer {qkv [3H,H], o [H,H], gu [2F,H], down [H,F], ln1 [H], ln2 [H]},
+    norm [H], lm_head [V,H], projector {w0 [H,C], w2 [H,H], b0 [H], b2 [H]}.
+    HF state-dict names map onto (views of) these — see hf_views().
+    """
+    PAD = 1024  # bucket sizes are multiples of this (divisible by any world size <= 8 with 128-elem slices)
+
+    def __init__(self, dims: LlavaDims, device):
+        self.dims = dims
+        d = dims
+        H, F, V, C = d.hidden_size, d.intermediate_size, d.vocab_size, d.clip_hidden
+        self.buckets = []
+        off = 0
+
+        def add_bucket(name, decay_list, nodecay_list):
+            nonlocal off
+            b = Bucket(name=name, start=off, size=0, decay_size=0)
+            o = off
+            for nm, shape in decay_list:
+                b.segments.append(Segment(nm, shape, o, True))
+                o += math.prod(shape)
+            b.decay_size = o - off
+            for nm, shape in nodecay_list:
+                b.segments.append(Segment(nm, shape, o, False))
+                o += math.prod(shape)
+            b.size = _round_up(o - off, self.PAD)
+            off += b.size
+            self.buckets.append(b)
+
+        add_bucket("embed", [("embed", (V, H))], [])
+        for i in range(d.num_layers):
+            add_bucket(f"layer{i}",
+                       [(f"l{i}.qkv", (3 * H, H)), (f"l{i}.o", (H, H)), (f"l{i}.gu", (2 * F, H)),
+                        (f"l{i}.down", (H, F))],
+                       [(f"l{i}.ln1", (H,)), (f"l{i}.ln2", (H,))])
+        add_bucket("head", [("lm_head", (V, H))], [("norm", (H,))])
+        add_bucket("projector", [("proj.w0", (H, C)), ("proj.w2", (H, H))], [("proj.b0", (H,)), ("proj.b2", (H,))])
+        self.numel = off
+        self.flat = torch.zeros(off, dtype=_BF, device=device)
+        self.grad = torch.zeros(off, dtype=_BF, device=device)
+        self.p = {}
+        self.g = {}
+        for b in self.buckets:
+            for s in b.segments:
+                n = math.prod(s.shape)
+                self.p[s.name] = self.flat[s.offset:s.offset + n].view(*s.shape)
+                self.g[s.name] = self.grad[s.offset:s.offset + n].view(*s.shape)
+
+    def hf_views(self):
+        """HF state-dict name -> view into the fused storage (LlavaLlamaForCausalLM naming)."""
+        d = self.dims
+        H, F = d.hidden_size, d.intermediate_size
+        out = {"model.embed_tokens.weight": self.p["embed"], "model.norm.weight": self.p["norm"],
+               "lm_head.weight": self.p["lm_head"],
+               "model.mm_projector.0.weight": self.p["proj.w0"], "model.mm_projector.0.bias": self.p["proj.b0"],
+               "model.mm_projector.2.weight": self.p["proj.w2"], "model.mm_projector.2.bias": self.p["proj.b2"]}
+        for i in range(d.num_layers):
+            pre = f"model.layers.{i}."
+            qkv, gu = self.p[f"l{i}.qkv"], self.p[f"l{i}.gu"]
+            out[pre + "self_attn.q_proj.weight"] = qkv[0:H]
+            out[pre + "self_attn.k_proj.weight"] = qkv[H:2 * H]
+            out[pre + "self_attn.v_proj.weight"] = qkv[2 * H:3 * H]
+            out[pre + "self_attn.o_proj.weight"] = self.p[f"l{i}.o"]
+            out[pre + "mlp.gate_proj.weight"] = gu[0:F]
+            out[pre + "mlp.up_proj.weight"] = gu[F:2 * F]
+            out[pre + "mlp.down_proj.weight"] = self.p[f"l{i}.down"]
+            out[pre + "input_layernorm.weight"] = self.p[f"l{i}.ln1"]
+            out[pre + "post_attention_layernorm.weight"] = self.p[f"l{i}.ln2"]
+        return out
+
+    def hf_grad_views(self):
+        saved = self.p
+        self.p = self.g
+        try:
+            return self.hf_views()
+        finally:
+            self.p = saved
+
+    def load_hf(self, state):
+        """Copy a (possibly fp32, CPU) HF-named state dict into the flat storage."""
+        views = self.hf_views()
+        for k, v in views.items():
+            v.copy_(state[k].to(device=v.device, dtype=_BF))
+
+
+class ClipWeights:
+    """Frozen CLIP-ViT weights in kernel-friendly form (fused qkv, padded patch-embedding matrix)."""
+
+    def __init__(self, dims: LlavaDims, device, state=None, seed=1):
+        d = dims
+        C, I = d.clip_hidden, d.clip_intermediate
+        vp = "model.vision_tower.vision_tower.vision_model."
+        if state is None:
+            g = torch.Generator().manual_seed(seed)
+            state = {}
+
+            def rnd(name, *shape, s=0.02):
+                state[name] = torch.randn(*shape, generator=g) * s
+
+            rnd(vp + "embeddings.class_embedding", C)
+            rnd(vp + "embeddings.patch_embedding.weight", C, 3, d.patch_size, d.patch_size)
+            rnd(vp + "embeddings.position_embedding.weight", d.num_patches + 1, C)
+            state[vp + "pre_layrnorm.weight"] = torch.ones(C)
+            state[vp + "pre_layrnorm.bias"] = torch.zeros(C)
+            for i in range(d.clip_layers_used):
+                pre = vp + f"encoder.layers.{i}."
+                for nm in ("q_proj", "k_proj", "v_proj", "out_proj"):
+                    rnd(pre + f"self_attn.{nm}.weight", C, C)
+                    state[pre + f"self_attn.{nm}.bias"] = torch.zeros(C)
+                rnd(pre + "mlp.fc1.weight", I, C)
+                state[pre + "mlp.fc1.bias"] = torch.zeros(I)
+                rnd(pre + "mlp.fc2.weight", C, I)
+                state[pre + "mlp.fc2.bias"] = torch.zeros(C)
+                for ln in ("layer_norm1", "layer_norm2"):
+                    state[pre + ln + ".weight"] = torch.ones(C)
+                    state[pre + ln + ".bias"] = torch.zeros(C)
+
+        def dev(t):
+            return t.to(device=device, dtype=_BF).contiguous()
+
+        self.cls = dev(state[vp + "embeddings.class_embedding"])
+        w = state[vp + "embeddings.patch_embedding.weight"].reshape(C, -1).to(_BF)
+        wp = torch.zeros(C, d.patch_k_pad, dtype=_BF)
+        wp[:, : d.patch_k] = w
+        self.patch_w = wp.to(device)
+        self.pos = dev(state[vp + "embeddings.position_embedding.weight"])
+        self.pre_ln_w = dev(state[vp + "pre_layrnorm.weight"])
+        self.pre_ln_b = dev(state[vp + "pre_layrnorm.bias"])
+        self.layers = []
+        for i in range(d.clip_layers_used):
+            pre = vp + f"encoder.layers.{i}."
+            L = {}
+            L["qkv_w"] = dev(torch.cat([state[pre + f"self_attn.{n}.weight"] for n in ("q_proj", "k_proj", "v_proj")], 0))
+            L["qkv_b"] = dev(torch.cat([state[pre + f"self_attn.{n}.bias"] for n in ("q_proj", "k_proj", "v_proj")], 0))
+            L["o_w"] = dev(state[pre + "self_attn.out_proj.weight"])
+            L["o_b"] = dev(state[pre + "self_attn.out_proj.bias"])
+            L["fc1_w"] = dev(state[pre + "mlp.fc1.weight"])
+            L["fc1_b"] = dev(state[pre + "mlp.fc1.bias"])
+            L["fc2_w"] = dev(state[pre + "mlp.fc2.weight"])
+            L["fc2_b"] = dev(state[pre + "mlp.fc2.bias"])
+            for ln in ("layer_norm1", "layer_norm2"):
+                L[ln + "_w"] = dev(state[pre + ln + ".weight"])
+                L[ln + "_b"] = dev(state[pre + ln + ".bias"])
+            self.layers.append(L)
+
+
+class LlavaDPOPolicy:
+    """Forward (policy log-probs) and backward (gradients into ParamStore.grad) of one micro-batch."""
+
+    def __init__(self, dims: LlavaDims, device="cuda", hf_state=None, seed=0, init_std=0.02):
+        self.dims = dims
+        self.device = torch.device(device)
+        self.store = ParamStore(dims, self.device)
+        if hf_state is not None:
+            self.store.load_hf(hf_state)
+            self.clip = ClipWeights(dims, self.device, hf_state)
+        else:
+            self._random_init(seed, init_std)
+            self.clip = ClipWeights(dims, self.device, None, seed + 1)
+        self._rope = {}
+        self._bufs = {}
+        self.embed_grad_f32 = None   # fp32 scatter target for embedding rows (allocated lazily)
+        self._stash = None
+
+    # ------------------------------------------------------------------ init / buffers
+    def _random_init(self, seed, std):
+        g = torch.Generator(device=self.device).manual_seed(seed)
+        for b in self.store.buckets:
+            for s in b.segments:
+                v = self.store.p[s.name]
+                if len(s.shape) == 1 and (s.name.endswith("ln1") or s.name.endswith("ln2") or s.name == "norm"):
+                    v.fill_(1.0)
+                elif len(s.shape) == 1:
+                    v.zero_()
+                else:
+                    # chunked normal_ to bound the fp32 temporary
+                    flat = v.view(-1)
+                    step = 1 << 26
+                    for o in range(0, flat.numel(), step):
+                        n = min(step, flat.numel() - o)
+                        flat[o:o + n].copy_(torch.randn(n, generator=g, device=self.device, dtype=_F32) * std)
+
+    def buf(self, key, shape, dtype=_BF):
+        t = self._bufs.get(key)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            self._bufs[key] = t
+        return t
+
+    def rope_tables(self, T):
+        if T not in self._rope:
+            d = self.dims
+            hd = d.head_dim
+            inv_freq = 1.0 / (d.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))
+            pos = torch.arange(T, dtype=_F32)
+            emb = torch.cat([pos[:, None] * inv_freq[None, :]] * 2, dim=-1)
+            self._rope[T] = (emb.cos().to(_BF).to(self.device).contiguous(),
+                             emb.sin().to(_BF).to(self.device).contiguous())
+        return self._rope[T]
+
+    # ------------------------------------------------------------------ CLIP (frozen, forward only)
+    def encode_images(self, images):
+        """images [b,3,S,S] (any float dtype) -> CLIP patch features [b*P, C] (bf16)."""
+        d, cw = self.dims, self.clip
+        b = images.shape[0]
+        P, C = d.num_patches, d.clip_hidden
+        T = P + 1
+        img = images.to(device=self.device, dtype=_BF).contiguous()
+        cols = ops.clip_im2col(img, d.patch_size, d.patch_k_pad)
+        patch = ops.gemm(cols, cw.patch_w)
+        x = ops.clip_embed(patch, cw.cls, cw.pos, b, P)
+        x = ops.layernorm_fwd(x, cw.pre_ln_w, cw.pre_ln_b, d.clip_eps)
+        nh = d.clip_heads
+        hd = C // nh
+        scale = hd ** -0.5
+        for L in cw.layers:
+            h = ops.layernorm_fwd(x, L["layer_norm1_w"], L["layer_norm1_b"], d.clip_eps, out=self.buf("clip_h", x.shape))
+            qkv = ops.gemm(h, L["qkv_w"], self.buf("clip_qkv", (b * T, 3 * C)), bias=L["qkv_b"])
+            att, _ = ops.attention_fwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], b, T, nh, hd, False, scale,
+                                       out=self.buf("clip_att", (b * T, C)), lse=self.buf("clip_lse", (b, nh, T), _F32))
+            x2 = ops.gemm(att, L["o_w"], self.buf("clip_x2", x.shape), bias=L["o_b"], residual=x)
+            h = ops.layernorm_fwd(x2, L["layer_norm2_w"], L["layer_norm2_b"], d.clip_eps, out=self.buf("clip_h", x.shape))
+            f = ops.gemm(h, L["fc1_w"], self.buf("clip_f", (b * T, d.clip_intermediate)), bias=L["fc1_b"],
+                         act=ops.ACT_QUICK_GELU)
+            x = ops.gemm(f, L["fc2_w"], self.buf("clip_x", x.shape), bias=L["fc2_b"], residual=x2)
+        return ops.clip_drop_cls(x, b, P)
+
+    # ------------------------------------------------------------------ splice
+    def splice(self, input_ids, labels, image_rows, n_blocks, img_index=None, T_hint=None):
+        """llava_arch.prepare_inputs_labels_for_multimodal (attention_mask=None path).
+
+        image_rows: [n_blocks*P, H] projected features; img_index[i] = feature block used by the
+        i-th image slot (default: identity).  Returns (embeds [nseq*T,H], new_labels [nseq,T], src, T)."""
+        d = self.dims
+        nseq, L = input_ids.shape
+        n_img, lens = ops.splice_count(input_ids, d.num_patches, d.max_len)
+        if T_hint is None:
+            T = int(lens.max().item())       # one tiny D2H per step (the reference syncs ~4x per sample)
+            n_slots = int(torch.clamp(n_img, min=1).sum().item())
+        else:
+            T, n_slots = T_hint
+        if img_index is None:
+            img_index = torch.arange(n_slots, dtype=torch.int32, device=self.device)
+        src, new_labels = ops.splice_map(input_ids, labels, n_img, img_index, d.num_patches, T, d.max_len)
+        embeds = ops.splice_gather(src, input_ids, self.store.p["embed"], image_rows,
+                                   out=self.buf("x0", (nseq * T, d.hidden_size)))
+        return embeds, new_labels, src, T
+
+    # ------------------------------------------------------------------ forward
+    def forward_logps(self, input_ids, labels, images, keep_stash=True, return_per_token=True, T_hint=None):
+        """input_ids/labels [2b, L] int64 (win rows first, then rej — preference_collator_fn order),
+        images [b,3,S,S].  Returns dict(per_token_logps [2b,T-1], logp [2b], avg_logp [2b], labels [2b,T])."""
+        d, P = self.dims, self.store.p
+        dev = self.device
+        input_ids = input_ids.to(dev).contiguous()
+        labels = labels.to(dev).contiguous()
+        nseq = input_ids.shape[0]
+        b = images.shape[0]
+        H, F, V = d.hidden_size, d.intermediate_size, d.vocab_size
+        nh, hd = d.num_heads, d.head_dim
+        st = {"layers": []} if keep_stash else None
+
+        feats = self.encode_images(images)                                   # [b*Pn, C]
+        pre = ops.gemm(feats, P["proj.w0"], self.buf("proj_pre", (feats.shape[0], H)), bias=P["proj.b0"])
+        post = ops.gelu_fwd(pre, self.buf("proj_post", pre.shape))
+        proj = ops.gemm(post, P["proj.w2"], self.buf("proj_out", pre.shape), bias=P["proj.b2"])
+        # images are shared by the win and rej copy of a pair (trainers.py:190 cat([images, images]))
+        n_slots = nseq
+        img_index = (torch.arange(n_slots, dtype=torch.int32, device=dev) % b).contiguous() if nseq == 2 * b \
+            else torch.arange(n_slots, dtype=torch.int32, device=dev)
+        x, new_labels, src, T = self.splice(input_ids, labels, proj, b, img_index,
+                                            T_hint=(T_hint, n_slots) if T_hint is not None else None)
+        M = nseq * T
+        cos, sin = self.rope_tables(T)
+        scale = hd ** -0.5
+        if keep_stash:
+            st.update(feats=feats, proj_pre=pre, proj_post=post, src=src, input_ids=input_ids, labels=new_labels,
+                      T=T, nseq=nseq, b=b)
+        for i in range(d.num_layers):
+            if keep_stash:
+                ls = {"x": x}
+                qkv = torch.empty((M, 3 * H), dtype=_BF, device=dev)
+                att = torch.empty((M, H), dtype=_BF, device=dev)
+                x2 = torch.empty((M, H), dtype=_BF, device=dev)
+                gu = torch.empty((M, 2 * F), dtype=_BF, device=dev)
+                x3 = torch.empty((M, H), dtype=_BF, device=dev)
+                rstd1 = torch.empty(M, dtype=_F32, device=dev)
+                rstd2 = torch.empty(M, dtype=_F32, device=dev)
+                lse = torch.empty((nseq, nh, T), dtype=_F32, device=dev)
+            else:
+                qkv, att = self.buf("qkv", (M, 3 * H)), self.buf("att", (M, H))
+                x2, gu = self.buf("x2", (M, H)), self.buf("gu", (M, 2 * F))
+                x3 = self.buf("x3_%d" % (i & 1), (M, H))
+                rstd1 = rstd2 = None
+                lse = self.buf("lse", (nseq, nh, T), _F32)
+            n1 = ops.rmsnorm_fwd(x, P[f"l{i}.ln1"], d.rms_eps, out=self.buf("n", (M, H)), rstd=rstd1)
+            ops.gemm(n1, P[f"l{i}.qkv"], qkv)
+            ops.rope_fwd(qkv, cos, sin, T, nh, hd)
+            ops.attention_fwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], nseq, T, nh, hd, True, scale, out=att, lse=lse)
+            ops.gemm(att, P[f"l{i}.o"], x2, residual=x)
+            n2 = ops.rmsnorm_fwd(x2, P[f"l{i}.ln2"], d.rms_eps, out=self.buf("n", (M, H)), rstd=rstd2)
+            ops.gemm(n2, P[f"l{i}.gu"], gu)
+            act = ops.swiglu_fwd(gu, self.buf("act", (M, F)))
+            ops.gemm(act, P[f"l{i}.down"], x3, residual=x2)
+            if keep_stash:
+                ls.update(qkv=qkv, att=att, x2=x2, gu=gu, rstd1=rstd1, rstd2=rstd2, lse=lse)
+                st["layers"].append(ls)
+            x = x3
+        rstd_f = torch.empty(M, dtype=_F32, device=dev) if keep_stash else None
+        hn = ops.rmsnorm_fwd(x, P["norm"], d.rms_eps, out=self.buf("hn", (M, H)), rstd=rstd_f)
+        logits = ops.gemm(hn, P["lm_head"], self.buf("logits", (M, V)))
+        per_tok, lse_v, logp, avg, count = ops.logp_fwd(logits, new_labels, nseq, T)
+        if keep_stash:
+            st.update(x_final=x, rstd_f=rstd_f, hn=hn, logits=logits, lse_v=lse_v, count=count)
+            self._stash = st
+        return dict(per_token_logps=per_tok, logp=logp, avg_logp=avg, labels=new_labels, T=T)
+
+    # ------------------------------------------------------------------ backward
+    def backward_logps(self, d_logp, use_average=False, accumulate=False):
+        """Gradients of sum_b d_logp[b] * logp[b] into store.grad (bf16; `accumulate` adds to what is
+        there — used for the 2nd.. micro-batch of a step)."""
+        st = self._stash
+        assert st is not None, "forward_logps(keep_stash=True) must precede backward_logps"
+        d, P, G = self.dims, self.store.p, self.store.g
+        dev = self.device
+        nseq, T, b = st["nseq"], st["T"], st["b"]
+        M = nseq * T
+        H, F, V = d.hidden_size, d.intermediate_size, d.vocab_size
+        nh, hd = d.num_heads, d.head_dim
+        scale = hd ** -0.5
+        cos, sin = self.rope_tables(T)
+        acc = bool(accumulate)
+
+        dlogits = ops.logp_bwd(st["logits"], st["labels"], st["lse_v"], d_logp, nseq, T,
+                               count=st["count"] if use_average else None)
+        ops.gemm(dlogits, st["hn"], G["lm_head"], a_mn=True, b_mn=True, accumulate=acc)        # dW = dlogits^T hn
+        dhn = ops.gemm(dlogits, P["lm_head"], self.buf("dn", (M, H)), b_mn=True)                # dhn = dlogits W
+        dx = ops.rmsnorm_bwd(dhn, st["x_final"], P["norm"], st["rstd_f"], self.buf("dx_a", (M, H)), G["norm"],
+                             dw_accumulate=acc)
+        for i in reversed(range(d.num_layers)):
+            ls = st["layers"][i]
+            # ---- MLP ----
+            act = ops.swiglu_fwd(ls["gu"], self.buf("act", (M, F)))                               # recompute
+            ops.gemm(dx, act, G[f"l{i}.down"], a_mn=True, b_mn=True, accumulate=acc)
+            dact = ops.gemm(dx, P[f"l{i}.down"], self.buf("dact", (M, F)), b_mn=True)
+            dgu = ops.swiglu_bwd(ls["gu"], dact, self.buf("dgu", (M, 2 * F)))
+            n2 = ops.rmsnorm_fwd(ls["x2"], P[f"l{i}.ln2"], d.rms_eps, out=self.buf("n", (M, H)))    # recompute
+            ops.gemm(dgu, n2, G[f"l{i}.gu"], a_mn=True, b_mn=True, accumulate=acc)
+            dn2 = ops.gemm(dgu, P[f"l{i}.gu"], self.buf("dn", (M, H)), b_mn=True)
+            dx2 = ops.rmsnorm_bwd(dn2, ls["x2"], P[f"l{i}.ln2"], ls["rstd2"], self.buf("dx_b", (M, H)),
+                                  G[f"l{i}.ln2"], dres=dx, dw_accumulate=acc)
+            # ---- attention ----
+            ops.gemm(dx2, ls["att"], G[f"l{i}.o"], a_mn=True, b_mn=True, accumulate=acc)
+            datt = ops.gemm(dx2, P[f"l{i}.o"], self.buf("datt", (M, H)), b_mn=True)
+            qkv = ls["qkv"]
+            dq32 = self.buf("dq32", (M, H), _F32)
+            dq32.zero_()
+            dqkv = self.buf("dqkv", (M, 3 * H))
+            ops.attention_bwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], ls["att"], datt, ls["lse"], nseq, T, nh, hd,
+                              scale, dq32, dqkv[:, H:2 * H], dqkv[:, 2 * H:], self.buf("delta", (nseq, nh, T), _F32))
+            ops.rope_bwd(dqkv, dq32, cos, sin, T, nh, hd)
+            n1 = ops.rmsnorm_fwd(ls["x"], P[f"l{i}.ln1"], d.rms_eps, out=self.buf("n", (M, H)))     # recompute
+            ops.gemm(dqkv, n1, G[f"l{i}.qkv"], a_mn=True, b_mn=True, accumulate=acc)
+            dn1 = ops.gemm(dqkv, P[f"l{i}.qkv"], self.buf("dn", (M, H)), b_mn=True)
+            dx = ops.rmsnorm_bwd(dn1, ls["x"], P[f"l{i}.ln1"], ls["rstd1"], self.buf("dx_a", (M, H)), G[f"l{i}.ln1"],
+                                 dres=dx2, dw_accumulate=acc)
+            st["layers"][i] = None   # release this layer's stash
+            if self.on_layer_grads_ready is not None:
+                self.on_layer_grads_ready(i)
+        # ---- splice backward: embedding rows + projected image rows ----
+        if self.embed_grad_f32 is None:
+            self.embed_grad_f32 = torch.zeros((V, H), dtype=_F32, device=dev)
+        elif not acc:
+            self.embed_grad_f32.zero_()
+        n_feat_rows = st["proj_pre"].shape[0]
+        dfeat32 = self.buf("dfeat32", (n_feat_rows, H), _F32)
+        dfeat32.zero_()
+        ops.splice_scatter(st["src"], st["input_ids"], dx, self.embed_grad_f32, dfeat32)
+        dproj = ops.f32_to_bf16(dfeat32, self.buf("dproj", (n_feat_rows, H)))
+        # ---- projector ----
+        ops.gemm(dproj, st["proj_post"], G["proj.w2"], a_mn=True, b_mn=True, accumulate=acc)
+        ops.colsum(dproj, G["proj.b2"], accumulate=acc)
+        dpost = ops.gemm(dproj, P["proj.w2"], self.buf("dpost", (n_feat_rows, H)), b_mn=True)
+        dpre = ops.gelu_bwd(st["proj_pre"], dpost, self.buf("dpre", (n_feat_rows, H)))
+        ops.gemm(dpre, st["feats"], G["proj.w0"], a_mn=True, b_mn=True, accumulate=acc)
+        ops.colsum(dpre, G["proj.b0"], accumulate=acc)
+        self._stash = None
+
+    on_layer_grads_ready = None
+
+    def finalize_embed_grad(self):
+        """fp32 embedding-row accumulator -> bf16 flat gradient (once per optimizer step)."""
+        ops.f32_to_bf16(self.embed_grad_f32.view(-1), self.store.g["embed"].view(-1))

@@ -1,0 +1,115 @@
+"""ZeRO-2 style data-parallel AdamW over the flat parameter buckets (script/zero2.json:16-22;
+optimizer = adamw_torch, muffin/train/train_llava15.py:75; lr/wd/schedule flags of
+script/train/llava15_train.sh:31-34).
+
+Every bucket of ParamStore (embed | layer i | head | projector) is cut into `world` equal slices;
+rank r owns slice r of every bucket: fp32 master weights and Adam moments exist only for owned
+slices (12 B/param / world), gradients are reduce-scattered in place into the owned slice as soon
+as a bucket's backward has finished (overlapping the rest of the backward on a side stream), the
+fused AdamW kernel updates the slice and writes bf16 straight into the parameter buffer, and an
+in-place all-gather redistributes the updated parameters.  With world == 1 the collectives vanish.
+
+torch.distributed (NCCL) is the transport; nothing here computes on the host.
+"""
+import math
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+_F32 = torch.float32
+
+
+def cosine_lr(step, total_steps, base_lr, warmup_ratio=0.05):
+    """HF get_cosine_schedule_with_warmup value used for optimizer step `step` (0-based)."""
+    warm = math.ceil(total_steps * warmup_ratio)
+    if step < warm:
+        return base_lr * step / max(1, warm)
+    prog = (step - warm) / max(1, total_steps - warm)
+    return base_lr * max(0.0, 0.5 * (1.0 + math.cos(math.pi * prog)))
+
+
+class Zero2AdamW:
+    def __init__(self, store, lr=5e-7, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, rank=0, world=1,
+                 group=None):
+        self.store = store
+        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self.rank, self.world, self.group = rank, world, group
+        self.step_count = 0
+        dev = store.flat.device
+        self.slices = []   # (bucket, s0, s1) absolute element offsets of the owned slice
+        total = 0
+        for b in store.buckets:
+            assert b.size % (world * 8) == 0
+            n = b.size // world
+            self.slices.append((b, b.start + rank * n, b.start + (rank + 1) * n, total))
+            total += n
+        self.owned = total
+        self.master = torch.empty(total, dtype=_F32, device=dev)
+        self.exp_avg = torch.zeros(total, dtype=_F32, device=dev)
+        self.exp_avg_sq = torch.zeros(total, dtype=_F32, device=dev)
+        for b, s0, s1, o in self.slices:
+            self.master[o:o + (s1 - s0)].copy_(store.flat[s0:s1])
+        self.comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+        self._pending = []
+
+    # ---- gradient reduction (called from the backward as buckets complete) ----
+    def reduce_bucket(self, bucket_index):
+        if self.world == 1:
+            return
+        b, s0, s1, _ = self.slices[bucket_index]
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(ev)
+            g = self.store.grad[b.start:b.start + b.size]
+            dist.reduce_scatter_tensor(self.store.grad[s0:s1], g, op=dist.ReduceOp.SUM, group=self.group)
+
+    def reduce_all(self):
+        for i in range(len(self.slices)):
+            self.reduce_bucket(i)
+
+    # ---- optimizer step ----
+    def step(self, lr=None):
+        lr = self.lr if lr is None else lr
+        self.step_count += 1
+        cur = torch.cuda.current_stream()
+        if self.world > 1:
+            cur.wait_stream(self.comm_stream)
+        b1, b2 = self.betas
+        for b, s0, s1, o in self.slices:
+            dec_end = min(s1, b.start + b.decay_size)
+            # decay part
+            if dec_end > s0:
+                n = dec_end - s0
+                ops.adamw_step(self.master[o:o + n], self.exp_avg[o:o + n], self.exp_avg_sq[o:o + n],
+                               self.store.grad[s0:dec_end], self.store.flat[s0:dec_end], lr, b1, b2, self.eps,
+                               self.wd, self.step_count)
+            nd0 = max(s0, b.start + b.decay_size)
+            if s1 > nd0:
+                n = s1 - nd0
+                oo = o + (nd0 - s0)
+                ops.adamw_step(self.master[oo:oo + n], self.exp_avg[oo:oo + n], self.exp_avg_sq[oo:oo + n],
+                               self.store.grad[nd0:s1], self.store.flat[nd0:s1], lr, b1, b2, self.eps, 0.0,
+                               self.step_count)
+        if self.world > 1:
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            with torch.cuda.stream(self.comm_stream):
+                self.comm_stream.wait_event(ev)
+                for b, s0, s1, _ in self.slices:
+                    dist.all_gather_into_tensor(self.store.flat[b.start:b.start + b.size], self.store.flat[s0:s1],
+                                                group=self.group)
+            cur.wait_stream(self.comm_stream)
+
+    def state_dict(self):
+        return {"step": self.step_count, "master": self.master, "exp_avg": self.exp_avg,
+                "exp_avg_sq": self.exp_avg_sq, "rank": self.rank, "world": self.world}
+
+    def load_state_dict(self, sd):
+        assert sd["world"] == self.world and sd["rank"] == self.rank
+        self.step_count = sd["step"]
+        self.master.copy_(sd["master"])
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])

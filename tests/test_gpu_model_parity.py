@@ -1,0 +1,119 @@
+"""-m gpu parity tests: the CUDA path (through the C ABI) vs the oracle and the golden fixtures that
+were produced by the unmodified reference (oracle/gen_golden.py).
+
+Tolerances: index work bit-exact; per-token / summed logps and DPO loss <= 1e-3
+relative vs the bf16-op-order oracle and the fp32 reference fixture at <= 5e-3 (the fixture is
+fp32 math, the CUDA path is bf16 storage: bf16 has 8 bits of mantissa, so fp32-vs-bf16 agreement is
+bounded by the reference's own bf16 rounding, not by the kernels).
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import llava_dpo_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def tiny_dims():
+    from rlaifv_b200.model import LlavaDims
+    c = O.TINY
+    return LlavaDims(vocab_size=c.vocab_size, hidden_size=c.hidden_size, intermediate_size=c.intermediate_size,
+                     num_layers=c.num_layers, num_heads=c.num_heads, clip_hidden=c.clip_hidden,
+                     clip_intermediate=c.clip_intermediate, clip_layers=c.clip_layers, clip_heads=c.clip_heads,
+                     image_size=c.image_size, patch_size=c.patch_size)
+
+
+@pytest.fixture(scope="module")
+def policy():
+    from rlaifv_b200.model import LlavaDPOPolicy
+    params = O.make_params(O.TINY, seed=0)
+    return LlavaDPOPolicy(tiny_dims(), "cuda", hf_state=params), params
+
+
+def rel(a, b):
+    a = torch.as_tensor(a).double().cpu()
+    b = torch.as_tensor(b).double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_forward_matches_reference_fixture(policy, path):
+    pol, params = policy
+    fx = np.load(path)
+    assert abs(O.params_checksum(params) - float(fx["params_checksum"])) < 1e-6 * float(fx["params_checksum"])
+    ids = torch.from_numpy(fx["concatenated_input_ids"])
+    labels = torch.from_numpy(fx["concatenated_labels"])
+    images = torch.from_numpy(fx["images"])
+    out = pol.forward_logps(ids, labels, images, keep_stash=False)
+    torch.cuda.synchronize()
+    # integer work: bit exact
+    assert torch.equal(out["labels"].cpu(), torch.from_numpy(fx["spliced_labels"]))
+    # bf16-op-order oracle on the same bf16-rounded parameters
+    pb = {k: v.to(torch.bfloat16) for k, v in params.items()}
+    ob = O.policy_logps(pb, O.TINY, ids, labels, images.to(torch.bfloat16))
+    B = ids.shape[0] // 2
+    logp = out["logp"].cpu()
+    print("logp cuda", logp.tolist(), "oracle bf16", ob["logp"].tolist(),
+          "ref fp32", fx["policy_win_logp"].tolist(), fx["policy_rej_logp"].tolist())
+    ref_fp32 = torch.cat([torch.from_numpy(fx["policy_win_logp"]), torch.from_numpy(fx["policy_rej_logp"])])
+    # summed log-probs: the 1e-3 gate of BASELINE.md §5, against both the bf16-op-order oracle and
+    # the fp32 outputs of the unmodified reference
+    assert rel(logp, ob["logp"]) <= 1e-3
+    assert rel(logp, ref_fp32) <= 1e-3
+    # per-token log-probs: a single bf16 logit of magnitude ~2 carries up to 8e-3 absolute rounding
+    # error, so two valid bf16 evaluation orders differ by a few 1e-3 relative per token.  The gate
+    # is therefore: the CUDA path is as close to the fp32 reference as the reference's own bf16
+    # op order is (x1.5), and never worse than 1e-2.
+    mask = torch.from_numpy(fx["spliced_labels"])[:, 1:] != -100
+    pt = out["per_token_logps"].cpu()
+    ref_pt = torch.from_numpy(fx["per_token_logps"])
+    inherent = rel(ob["per_token_logps"][mask], ref_pt[mask])
+    e_ref = rel(pt[mask], ref_pt[mask])
+    e_orc = rel(pt[mask], ob["per_token_logps"][mask])
+    print(f"per-token rel err: cuda-vs-fp32ref {e_ref:.2e}, cuda-vs-bf16oracle {e_orc:.2e}, "
+          f"bf16oracle-vs-fp32ref (inherent) {inherent:.2e}")
+    assert e_ref <= max(1e-3, 1.5 * inherent) and e_ref <= 1e-2
+    assert e_orc <= max(1e-3, 2.5 * inherent) and e_orc <= 1e-2
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_dpo_loss_and_grads_match_reference_fixture(policy, path):
+    from rlaifv_b200 import ops
+    pol, params = policy
+    fx = np.load(path)
+    ids = torch.from_numpy(fx["concatenated_input_ids"])
+    labels = torch.from_numpy(fx["concatenated_labels"])
+    images = torch.from_numpy(fx["images"])
+    B = int(fx["B"])
+    out = pol.forward_logps(ids, labels, images, keep_stash=True)
+    rw = torch.from_numpy(fx["ref_win_logp"]).cuda()
+    rr = torch.from_numpy(fx["ref_rej_logp"]).cuda()
+    losses, cr, rj, dpw, dpr, out9 = ops.dpo_loss(out["logp"][:B].contiguous(), out["logp"][B:].contiguous(), rw, rr,
+                                                  float(fx["beta"]))
+    pol.backward_logps(torch.cat([dpw, dpr]).contiguous())
+    pol.finalize_embed_grad()
+    torch.cuda.synchronize()
+    assert rel(losses, fx["losses"]) <= 2e-2          # loss depends on a difference of logps: looser
+    assert rel(out9[0], fx["loss"]) <= 2e-2
+    assert rel(cr, fx["chosen_rewards"]) <= 5e-3
+    grads = pol.store.hf_grad_views()
+    for key in fx.files:
+        if not key.startswith("gradsample:"):
+            continue
+        name = key.split(":", 1)[1]
+        g = grads[name].float().flatten().cpu()
+        idx = torch.linspace(0, g.numel() - 1, 64).long()
+        got = g[idx]
+        ref = torch.from_numpy(fx[key])
+        gn = float(fx["gradnorm:" + name])
+        err = float((got - ref).abs().max())
+        scale = float(ref.abs().max()) + 1e-12
+        nrm = float(g.double().norm())
+        print(f"{name}: sample max err {err:.3e} (ref max {scale:.3e}); norm {nrm:.4e} vs ref {gn:.4e}")
+        assert abs(nrm - gn) <= 3e-2 * gn, name
+        assert err <= 6e-2 * scale, name
