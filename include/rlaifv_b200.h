@@ -36,6 +36,10 @@ int rlaifv_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B
                      const void* residual, long long ldr, int act, int accumulate, int tile_n,
                      void* stream);
 
+/* tile_n = 512 selects the 2-CTA kernel (cta_group::2, 256x256 tile per CTA pair). rlaifv_gemm_set_2cta(1)
+ * lets tile_n = 0 (auto) pick it for large problems. */
+int rlaifv_gemm_set_2cta(int enable);
+
 /* ---- attention (tcgen05, S/O accumulators in TMEM) ---------------------------------------------
  * q/k/v/out: [nseq*S][ld] bf16, head h at columns [h*head_dim, (h+1)*head_dim); lse fp32
  * [nseq][n_heads][S]. head_dim 128 (Llama, causal) or 64 (CLIP, non-causal).

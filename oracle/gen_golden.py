@@ -100,10 +100,13 @@ def make_instances(batch, ref, B):
 
 
 CASES = {
-    # name: (B, prompt_len, resp_len, seed, image_pos, ragged)
-    "tiny_equal": (1, 20, 16, 11, None, False),
-    "tiny_ragged_b2": (2, 24, 20, 12, 5, True),
-    "tiny_image_first": (2, 16, 12, 13, 1, True),
+    # name: (B, prompt_len, resp_len, seed, image_pos, ragged, param_scale)
+    "tiny_equal": (1, 20, 16, 11, None, False, 1.0),
+    "tiny_ragged_b2": (2, 24, 20, 12, 5, True, 1.0),
+    "tiny_image_first": (2, 16, 12, 13, 1, True, 1.0),
+    # cooler weights: logits of the magnitude a real checkpoint produces, so the strict 1e-3 bf16 gate applies
+    "cool_ragged_b2": (2, 24, 40, 14, 9, True, 0.4),
+    "cool_long_b1": (1, 30, 150, 15, 20, False, 0.4),
 }
 
 
@@ -111,9 +114,7 @@ def main():
     from oracle import llava_dpo_oracle as O
     R = import_reference()
     cfg = O.TINY
-    params = O.make_params(cfg, seed=0)
-    model = build_reference_model(R, cfg, params)
-    model.train()
+    models = {}
     out_dir = os.path.join(REPO, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
 
@@ -125,7 +126,13 @@ def main():
         dpo_token_weighted = False
         task = "DPO"
 
-    for name, (B, P, Rl, seed, ipos, ragged) in CASES.items():
+    for name, (B, P, Rl, seed, ipos, ragged, pscale) in CASES.items():
+        if pscale not in models:
+            prm = O.make_params(cfg, seed=0, scale=pscale)
+            mdl = build_reference_model(R, cfg, prm)
+            mdl.train()
+            models[pscale] = (prm, mdl)
+        params, model = models[pscale]
         batch = O.synthetic_pair_batch(cfg, B, P, Rl, seed, image_pos=ipos, ragged=ragged)
         g = torch.Generator().manual_seed(seed + 100)
         ref = {k: (-40.0 + 3.0 * torch.randn(B, generator=g)) for k in ("ref_win_logp", "ref_rej_logp")}
@@ -183,7 +190,7 @@ def main():
         fx = dict(
             B=np.int64(B), prompt_len=np.int64(P), resp_len=np.int64(Rl), seed=np.int64(seed),
             image_pos=np.int64(-1 if ipos is None else ipos), ragged=np.int64(int(ragged)),
-            params_checksum=np.float64(O.params_checksum(params)),
+            params_checksum=np.float64(O.params_checksum(params)), param_scale=np.float64(pscale),
             concatenated_input_ids=keep_ids.numpy(), concatenated_labels=keep_labels.numpy(),
             images=data["images"].numpy().astype(np.float32),
             ref_win_logp=ref["ref_win_logp"].numpy(), ref_rej_logp=ref["ref_rej_logp"].numpy(),
@@ -201,6 +208,61 @@ def main():
             idx = torch.linspace(0, flat.numel() - 1, 64).long()
             fx["gradsample:" + k] = flat[idx].numpy()
         np.savez_compressed(os.path.join(out_dir, name + ".npz"), **fx)
+    # ---- collator fixture: the reference's DataCollatorForDPODataset on pairs that share edits ----
+    g = torch.Generator().manual_seed(77)
+    inst, flat = [], {}
+    for i in range(3):
+        base = torch.randint(3, 500, (40 + 7 * i,), generator=g)
+        win = base.clone()
+        rej = base.clone()
+        rej[10:14] = torch.randint(3, 500, (4,), generator=g)              # substitution
+        rej = torch.cat([rej[:25], torch.randint(3, 500, (3 + i,), generator=g), rej[25:]])   # insertion
+        win = torch.cat([win[:33], win[36:]])                              # deletion on the win side
+        prompt = torch.randint(3, 500, (12,), generator=g)
+        prompt[0] = 1
+        prompt[5] = -200
+        def mk(resp, kind):
+            ids = torch.cat([prompt, resp])
+            labs = torch.cat([torch.full((12,), -100), resp])
+            d = {"input_ids": ids, "labels": labs, "image": torch.randn(3, 8, 8, generator=g),
+                 f"ref_{kind}_logp": float(-10.0 - i), f"ref_{kind}_avg_logp": float(-0.5 - 0.1 * i),
+                 f"ref_{kind}_per_token_logp": torch.randn(len(ids) + 5, generator=g).tolist()}
+            return d
+        r, w = mk(rej, "rej"), mk(win, "win")
+        inst.append((r, w))
+        for kind, d in (("rej", r), ("win", w)):
+            flat[f"in{i}_{kind}_input_ids"] = d["input_ids"].numpy()
+            flat[f"in{i}_{kind}_labels"] = d["labels"].numpy()
+            flat[f"in{i}_{kind}_image"] = d["image"].numpy()
+            flat[f"in{i}_{kind}_logp"] = np.float64(d[f"ref_{kind}_logp"])
+            flat[f"in{i}_{kind}_avg_logp"] = np.float64(d[f"ref_{kind}_avg_logp"])
+            flat[f"in{i}_{kind}_per_token"] = np.asarray(d[f"ref_{kind}_per_token_logp"], dtype=np.float64)
+    coll = R["DataCollatorForDPODataset"](tokenizer=Tok(), beta=0.1, mod_token_weight=3.0)
+    outb = coll(inst)
+    assert len(outb) == 20
+    for k, v in outb.items():
+        flat["out_" + k] = v.numpy() if torch.is_tensor(v) else np.float64(v)
+    os.makedirs(os.path.join(REPO, "tests", "golden_host"), exist_ok=True)
+    np.savez_compressed(os.path.join(REPO, "tests", "golden_host", "collator_case.npz"), n=np.int64(3), **flat)
+    # ---- sample-encoding fixture: reference preprocess_v1 / encode_multimodal_preference_sample ----
+    from functools import partial
+    from oracle.toy_tokenizer import ToyTokenizer
+    from muffin.train.train_utils import encode_multimodal_preference_sample as ref_encode, preprocess_v1 as ref_pre
+    tok = ToyTokenizer()
+    enc = {}
+    samples = [("<image>\nwhat is shown here ?", "a red bus on a street", "a blue car"),
+               ("describe the <image> scene in detail please", "two dogs play . they run", "one cat sleeps"),
+               ("<image>\nhow many ?", "three", "four apples on the table near a window")]
+    for i, (q, c, r) in enumerate(samples):
+        src = {"question": {"from": "human", "value": q}, "chosen": {"from": "gpt", "value": c},
+               "rejected": {"from": "gpt", "value": r}, "image": "IMG"}
+        cfgm = {"image_processor": lambda im: torch.zeros(3, 4, 4), "is_multimodal": True, "image_token_len": 576,
+                "use_im_start_end": False, "keep_image_tag": True}
+        rej_d, win_d = ref_encode(src, tok, cfgm, preprocess_func=partial(ref_pre, has_image=True))
+        enc[f"s{i}_q"], enc[f"s{i}_c"], enc[f"s{i}_r"] = np.array(q), np.array(c), np.array(r)
+        enc[f"s{i}_win_ids"], enc[f"s{i}_win_labels"] = win_d["input_ids"].numpy(), win_d["labels"].numpy()
+        enc[f"s{i}_rej_ids"], enc[f"s{i}_rej_labels"] = rej_d["input_ids"].numpy(), rej_d["labels"].numpy()
+    np.savez_compressed(os.path.join(REPO, "tests", "golden_host", "encode_case.npz"), n=np.int64(len(samples)), **enc)
     print("golden fixtures written to", out_dir)
 
 

@@ -75,12 +75,13 @@ TINY = OracleConfig(vocab_size=512, hidden_size=256, intermediate_size=512, num_
 # deterministic synthetic parameters (shared by the golden generator, the oracle tests and the GPU
 # parity tests so that no weight file has to be committed)
 # ------------------------------------------------------------------------------------------------
-def make_params(cfg: OracleConfig, seed: int = 0, std: float = 0.02, dtype=torch.float32):
+def make_params(cfg: OracleConfig, seed: int = 0, std: float = 0.02, dtype=torch.float32, scale: float = 1.0):
+    """`scale` multiplies every random matrix's std (scale < 1 gives cooler logits, i.e. less bf16 noise)."""
     g = torch.Generator().manual_seed(seed)
     p = {}
 
     def rnd(name, *shape, s=std):
-        p[name] = (torch.randn(*shape, generator=g) * s).to(dtype)
+        p[name] = (torch.randn(*shape, generator=g) * (s * scale)).to(dtype)
 
     def ones_ish(name, n):
         p[name] = (1.0 + 0.1 * torch.randn(n, generator=g)).to(dtype)

@@ -59,6 +59,52 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
+
+// Epilogue math for 32 consecutive accumulator columns of one output row (registers r[32]).
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int col0, int N, bf16* c_row,
+                                               const bf16* r_row, const GemmEpilogue& epi) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int col = col0 + g * 8;
+    if (col < N) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+      if (epi.bias) {
+        uint4 b4 = __ldg(reinterpret_cast<const uint4*>(epi.bias + col));
+        float2 b0 = unpack_bf16(b4.x), b1 = unpack_bf16(b4.y), b2 = unpack_bf16(b4.z), b3 = unpack_bf16(b4.w);
+        v[0] += b0.x; v[1] += b0.y; v[2] += b1.x; v[3] += b1.y;
+        v[4] += b2.x; v[5] += b2.y; v[6] += b3.x; v[7] += b3.y;
+      }
+      if (epi.act) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = apply_act(bf16_round(v[j]), epi.act);
+      }
+      if (r_row) {
+        uint4 q4 = *reinterpret_cast<const uint4*>(r_row + col);
+        float2 q0 = unpack_bf16(q4.x), q1 = unpack_bf16(q4.y), q2 = unpack_bf16(q4.z), q3 = unpack_bf16(q4.w);
+        // reference adds two bf16 tensors: round the linear output first
+        v[0] = bf16_round(v[0]) + q0.x; v[1] = bf16_round(v[1]) + q0.y;
+        v[2] = bf16_round(v[2]) + q1.x; v[3] = bf16_round(v[3]) + q1.y;
+        v[4] = bf16_round(v[4]) + q2.x; v[5] = bf16_round(v[5]) + q2.y;
+        v[6] = bf16_round(v[6]) + q3.x; v[7] = bf16_round(v[7]) + q3.y;
+      }
+      if (epi.accumulate) {
+        uint4 o4 = *reinterpret_cast<const uint4*>(c_row + col);
+        float2 o0 = unpack_bf16(o4.x), o1 = unpack_bf16(o4.y), o2 = unpack_bf16(o4.z), o3 = unpack_bf16(o4.w);
+        v[0] += o0.x; v[1] += o0.y; v[2] += o1.x; v[3] += o1.y;
+        v[4] += o2.x; v[5] += o2.y; v[6] += o3.x; v[7] += o3.y;
+      }
+      uint4 o;
+      o.x = pack_bf16(v[0], v[1]);
+      o.y = pack_bf16(v[2], v[3]);
+      o.z = pack_bf16(v[4], v[5]);
+      o.w = pack_bf16(v[6], v[7]);
+      *reinterpret_cast<uint4*>(c_row + col) = o;
+    }
+  }
+}
+
 template <bool A_MN, bool B_MN, int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -191,51 +237,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tmem_ld_32x32b_x32(t_addr + ch * 32, r);
         tmem_wait_ld();
         const int col0 = n_blk * BN + ch * 32;
-        if (row_ok && col0 < N) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = col0 + g * 8;
-            if (col < N) {
-              float v[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
-              if (epi.bias) {
-                uint4 b4 = __ldg(reinterpret_cast<const uint4*>(epi.bias + col));
-                float2 b0 = unpack_bf16(b4.x), b1 = unpack_bf16(b4.y), b2 = unpack_bf16(b4.z),
-                       b3 = unpack_bf16(b4.w);
-                v[0] += b0.x; v[1] += b0.y; v[2] += b1.x; v[3] += b1.y;
-                v[4] += b2.x; v[5] += b2.y; v[6] += b3.x; v[7] += b3.y;
-              }
-              if (epi.act) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = apply_act(bf16_round(v[j]), epi.act);
-              }
-              if (r_row) {
-                uint4 q4 = *reinterpret_cast<const uint4*>(r_row + col);
-                float2 q0 = unpack_bf16(q4.x), q1 = unpack_bf16(q4.y), q2 = unpack_bf16(q4.z),
-                       q3 = unpack_bf16(q4.w);
-                // reference adds two bf16 tensors: round the linear output first
-                v[0] = bf16_round(v[0]) + q0.x; v[1] = bf16_round(v[1]) + q0.y;
-                v[2] = bf16_round(v[2]) + q1.x; v[3] = bf16_round(v[3]) + q1.y;
-                v[4] = bf16_round(v[4]) + q2.x; v[5] = bf16_round(v[5]) + q2.y;
-                v[6] = bf16_round(v[6]) + q3.x; v[7] = bf16_round(v[7]) + q3.y;
-              }
-              if (epi.accumulate) {
-                uint4 o4 = *reinterpret_cast<const uint4*>(c_row + col);
-                float2 o0 = unpack_bf16(o4.x), o1 = unpack_bf16(o4.y), o2 = unpack_bf16(o4.z),
-                       o3 = unpack_bf16(o4.w);
-                v[0] += o0.x; v[1] += o0.y; v[2] += o1.x; v[3] += o1.y;
-                v[4] += o2.x; v[5] += o2.y; v[6] += o3.x; v[7] += o3.y;
-              }
-              uint4 o;
-              o.x = pack_bf16(v[0], v[1]);
-              o.y = pack_bf16(v[2], v[3]);
-              o.z = pack_bf16(v[4], v[5]);
-              o.w = pack_bf16(v[6], v[7]);
-              *reinterpret_cast<uint4*>(c_row + col) = o;
-            }
-          }
-        }
+        if (row_ok && col0 < N) epilogue_chunk(r, col0, N, c_row, r_row, epi);
       }
       tc_fence_before();
       __syncwarp();
@@ -249,6 +251,209 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tc_fence_after();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// 2-CTA variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x 256 tile with one
+// UMMA (M=256, N=256, K=16) per step issued by the leader CTA. Each CTA stages only its own 128
+// rows of A and its own 128-row half of B (the tensor cores read the peer's half through the pair's
+// shared-memory link), which halves the shared-memory traffic per SM and allows a 6-stage ring.
+// ------------------------------------------------------------------------------------------------
+constexpr int GEMM2_STAGES = 6;
+constexpr uint32_t GEMM2_A_BYTES = 128 * GEMM_BK * 2;
+constexpr uint32_t GEMM2_B_BYTES = 128 * GEMM_BK * 2;
+constexpr uint32_t GEMM2_STAGE_BYTES = GEMM2_A_BYTES + GEMM2_B_BYTES;
+constexpr uint32_t GEMM2_SMEM_BYTES = GEMM2_STAGES * GEMM2_STAGE_BYTES + 256 + 1024;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
+  return r;
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  int M, int N, int K, GemmEpilogue epi) {
+  constexpr int STAGES = GEMM2_STAGES;
+  constexpr int BN = 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * GEMM2_STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int num_m = (M + 255) / 256;
+  const int num_n = (N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_k = (K + GEMM_BK - 1) / GEMM_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < STAGES; ++i) {
+        mbar_init(&full[i], 2);    // leader: own arrive.expect_tx + peer's remote arrive
+        mbar_init(&empty[i], 1);   // multicast tcgen05.commit
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&tfull[i], 1);   // multicast tcgen05.commit
+        mbar_init(&tempty[i], 8);  // 4 epilogue warps of each CTA arrive on the leader's barrier
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc_2sm<512>(tmem_slot);
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer (both CTAs) ------------------------------
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        int m_blk, n_blk;
+        tile_coords(t, num_m, num_n, m_blk, n_blk);
+        const int m0 = m_blk * 256 + (int)cta_rank * 128;
+        const int n0 = n_blk * BN + (int)cta_rank * 128;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* a_dst = smem + s * GEMM2_STAGE_BYTES;
+          uint8_t* b_dst = a_dst + GEMM2_A_BYTES;
+          const uint32_t leader_full = mapa_u32(smem_u32(&full[s]), 0);
+          if (cta_rank == 0) mbar_arrive_expect_tx(&full[s], 2 * GEMM2_STAGE_BYTES);
+          else mbar_arrive_cluster(&full[s], 0);
+          const int k0 = kb * GEMM_BK;
+          if (A_MN) {
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+              tma_load_2d_2sm(a_dst + a * (GEMM_BK * 128), &tmA, leader_full, m0 + a * 64, k0);
+          } else {
+            tma_load_2d_2sm(a_dst, &tmA, leader_full, k0, m0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+              tma_load_2d_2sm(b_dst + a * (GEMM_BK * 128), &tmB, leader_full, n0 + a * 64, k0);
+          } else {
+            tma_load_2d_2sm(b_dst, &tmB, leader_full, k0, n0);
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer (leader CTA only) ------------------------------
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, BN, A_MN, B_MN);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_ph = (it >> 1) & 1;
+        mbar_wait(&tempty[acc], acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * GEMM2_STAGE_BYTES);
+          const uint32_t b_addr = a_addr + GEMM2_A_BYTES;
+#pragma unroll
+          for (int k16 = 0; k16 < GEMM_BK / 16; ++k16) {
+            const uint64_t adesc = A_MN ? desc_mnmajor(a_addr, k16, GEMM_BK) : desc_kmajor(a_addr, k16);
+            const uint64_t bdesc = B_MN ? desc_mnmajor(b_addr, k16, GEMM_BK) : desc_kmajor(b_addr, k16);
+            umma_ss_2sm(d_tmem, adesc, bdesc, idesc, (kb > 0 || k16 > 0) ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty[s], 0x3);
+          if (kb == num_k - 1) umma_commit_2sm(&tfull[acc], 0x3);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ------------------------------ epilogue (both CTAs) ------------------------------
+    const int quad = warp & 3;
+    const int row_in_tile = (int)cta_rank * 128 + quad * 32 + lane;
+    int it = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+      int m_blk, n_blk;
+      tile_coords(t, num_m, num_n, m_blk, n_blk);
+      const int acc = it & 1;
+      const uint32_t acc_ph = (it >> 1) & 1;
+      mbar_wait(&tfull[acc], acc_ph);
+      tc_fence_after();
+      const long long row = (long long)m_blk * 256 + row_in_tile;
+      const bool row_ok = row < M;
+      const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
+      bf16* c_row = epi.C + row * epi.ldc;
+      const bf16* r_row = epi.residual ? epi.residual + row * epi.ldr : nullptr;
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_addr + ch * 32, r);
+        tmem_wait_ld();
+        const int col0 = n_blk * BN + ch * 32;
+        if (row_ok && col0 < N) epilogue_chunk(r, col0, N, c_row, r_row, epi);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (cta_rank == 0) mbar_arrive(&tempty[acc]);
+        else mbar_arrive_cluster(&tempty[acc], 0);
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm<512>(tmem_base);
+  }
+}
+
+template <bool A_MN, bool B_MN>
+static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K,
+                        const GemmEpilogue& epi, cudaStream_t stream) {
+  auto kern = gemm2_bf16_kernel<A_MN, B_MN>;
+  static bool configured = false;
+  if (!configured) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)GEMM2_SMEM_BYTES));
+    configured = true;
+  }
+  const int num_tiles = ((M + 255) / 256) * ((N + 255) / 256);
+  int clusters = num_sms() / 2;
+  if (num_tiles < clusters) clusters = num_tiles;
+  kern<<<clusters * 2, GEMM_THREADS, GEMM2_SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, epi);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 template <bool A_MN, bool B_MN, int BN>
@@ -290,6 +495,12 @@ static int operand_tmap(CUtensorMap* tm, const void* ptr, long long ld, bool mn_
 
 using namespace b200;
 
+static int g_enable_2cta = 0;   // auto-selection of the 2-CTA kernel (explicit tile_n = 512 always works)
+extern "C" int rlaifv_gemm_set_2cta(int enable) {
+  g_enable_2cta = enable ? 1 : 0;
+  return 0;
+}
+
 // C ABI — see include/rlaifv_b200.h for the contract.
 extern "C" int rlaifv_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B,
                                 long long ldb, int b_mn_major, void* C, long long ldc, int M, int N,
@@ -304,13 +515,15 @@ extern "C" int rlaifv_gemm_bf16(const void* A, long long lda, int a_mn_major, co
   int bn = tile_n;
   if (bn == 0) {
     const long long tiles256 = (long long)((M + 127) / 128) * ((N + 255) / 256);
-    bn = (N >= 256 && tiles256 >= 120) ? 256 : 128;
+    const long long tiles2 = (long long)((M + 255) / 256) * ((N + 255) / 256);
+    if (g_enable_2cta && N >= 256 && tiles2 >= 64) bn = 512;
+    else bn = (N >= 256 && tiles256 >= 120) ? 256 : 128;
   }
-  B200_REQUIRE(bn == 128 || bn == 256, "gemm: tile_n must be 0, 128 or 256");
+  B200_REQUIRE(bn == 128 || bn == 256 || bn == 512, "gemm: tile_n must be 0, 128, 256 or 512 (2-CTA 256x256)");
   CUtensorMap tmA, tmB;
   int rc = operand_tmap(&tmA, A, lda, a_mn_major != 0, M, K, GEMM_BM);
   if (rc) return rc;
-  rc = operand_tmap(&tmB, B, ldb, b_mn_major != 0, N, K, bn);
+  rc = operand_tmap(&tmB, B, ldb, b_mn_major != 0, N, K, bn == 512 ? 128 : bn);
   if (rc) return rc;
   GemmEpilogue epi;
   epi.C = (bf16*)C;
@@ -321,6 +534,11 @@ extern "C" int rlaifv_gemm_bf16(const void* A, long long lda, int a_mn_major, co
   epi.act = act;
   epi.accumulate = accumulate;
   cudaStream_t st = (cudaStream_t)stream;
+  if (bn == 512) {
+    if (!a_mn_major && !b_mn_major) return launch_gemm2<false, false>(tmA, tmB, M, N, K, epi, st);
+    if (!a_mn_major && b_mn_major) return launch_gemm2<false, true>(tmA, tmB, M, N, K, epi, st);
+    return launch_gemm2<true, true>(tmA, tmB, M, N, K, epi, st);
+  }
   if (!a_mn_major && !b_mn_major)
     return bn == 256 ? launch_gemm<false, false, 256>(tmA, tmB, M, N, K, epi, st)
                      : launch_gemm<false, false, 128>(tmA, tmB, M, N, K, epi, st);

@@ -25,7 +25,7 @@ METRIC_NAMES = ("loss", "rewards_train/chosen", "rewards_train/rejected", "rewar
 class DPOStepEngine:
     def __init__(self, policy: LlavaDPOPolicy, lr=5e-7, weight_decay=0.01, betas=(0.9, 0.999), eps=1e-8,
                  total_steps=2672, warmup_ratio=0.05, dpo_use_average=False, micro_pairs=None,
-                 rank=0, world=1, group=None, constant_lr=False):
+                 rank=0, world=1, group=None, constant_lr=False, hf_deepspeed_input_cast=False):
         self.policy = policy
         self.rank, self.world, self.group = rank, world, group
         self.opt = Zero2AdamW(policy.store, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
@@ -34,6 +34,11 @@ class DPOStepEngine:
         self.constant_lr = constant_lr
         self.dpo_use_average = dpo_use_average
         self.micro_pairs = micro_pairs
+        # HF Trainer._prepare_inputs casts every floating input to bf16 under DeepSpeed-bf16, which
+        # rounds the reference log-probs (|logp| ~ 5e3 -> granularity 32) before dpo_loss. The drop-in
+        # trainer (trainers.LLaVA15DPOTrainer) switches this on to reproduce the shipped recipe; the
+        # engine itself takes get_beta_and_logps' inputs as they are.
+        self.hf_deepspeed_input_cast = hf_deepspeed_input_cast
         self.global_step = 0
         self._metrics = torch.zeros(9, dtype=_F32, device=policy.device)
         self._last_micro = False
@@ -61,10 +66,9 @@ class DPOStepEngine:
         key = "avg_logp" if self.dpo_use_average else "logp"
         rw = self._h2d(batch["ref_win_" + key]).to(_F32)
         rr = self._h2d(batch["ref_rej_" + key]).to(_F32)
-        # HF Trainer._prepare_inputs casts float inputs to bf16 under DeepSpeed bf16:
-        # the reference logps are therefore bf16-rounded before dpo_loss.
-        rw = rw.to(torch.bfloat16).to(_F32)
-        rr = rr.to(torch.bfloat16).to(_F32)
+        if self.hf_deepspeed_input_cast:
+            rw = rw.to(torch.bfloat16).to(_F32)
+            rr = rr.to(torch.bfloat16).to(_F32)
         beta = float(batch["beta"])
         B = images.shape[0]
         mp = self.micro_pairs or B

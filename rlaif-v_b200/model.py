@@ -338,36 +338,17 @@ class LlavaDPOPolicy:
                                    out=self.buf("x0", (nseq * T, d.hidden_size)))
         return embeds, new_labels, src, T
 
-    # ------------------------------------------------------------------ forward
-    def forward_logps(self, input_ids, labels, images, keep_stash=True, return_per_token=True, T_hint=None):
-        """input_ids/labels [2b, L] int64 (win rows first, then rej — preference_collator_fn order),
-        images [b,3,S,S].  Returns dict(per_token_logps [2b,T-1], logp [2b], avg_logp [2b], labels [2b,T])."""
-        d, P = self.dims, self.store.p
-        dev = self.device
-        input_ids = input_ids.to(dev).contiguous()
-        labels = labels.to(dev).contiguous()
-        nseq = input_ids.shape[0]
-        b = images.shape[0]
-        H, F, V = d.hidden_size, d.intermediate_size, d.vocab_size
+    # ------------------------------------------------------------------ decoder layers
+    def _run_layers(self, x, nseq, T, st):
+        """32 x [RMSNorm -> fused qkv GEMM -> RoPE -> causal attention -> o GEMM(+res) -> RMSNorm ->
+        fused gate|up GEMM -> SwiGLU -> down GEMM(+res)]; st (dict or None) receives the per-layer stash."""
+        d, P, dev = self.dims, self.store.p, self.device
+        H, F = d.hidden_size, d.intermediate_size
         nh, hd = d.num_heads, d.head_dim
-        st = {"layers": []} if keep_stash else None
-
-        feats = self.encode_images(images)                                   # [b*Pn, C]
-        pre = ops.gemm(feats, P["proj.w0"], self.buf("proj_pre", (feats.shape[0], H)), bias=P["proj.b0"])
-        post = ops.gelu_fwd(pre, self.buf("proj_post", pre.shape))
-        proj = ops.gemm(post, P["proj.w2"], self.buf("proj_out", pre.shape), bias=P["proj.b2"])
-        # images are shared by the win and rej copy of a pair (trainers.py:190 cat([images, images]))
-        n_slots = nseq
-        img_index = (torch.arange(n_slots, dtype=torch.int32, device=dev) % b).contiguous() if nseq == 2 * b \
-            else torch.arange(n_slots, dtype=torch.int32, device=dev)
-        x, new_labels, src, T = self.splice(input_ids, labels, proj, b, img_index,
-                                            T_hint=(T_hint, n_slots) if T_hint is not None else None)
         M = nseq * T
         cos, sin = self.rope_tables(T)
         scale = hd ** -0.5
-        if keep_stash:
-            st.update(feats=feats, proj_pre=pre, proj_post=post, src=src, input_ids=input_ids, labels=new_labels,
-                      T=T, nseq=nseq, b=b)
+        keep_stash = st is not None
         for i in range(d.num_layers):
             if keep_stash:
                 ls = {"x": x}
@@ -398,6 +379,47 @@ class LlavaDPOPolicy:
                 ls.update(qkv=qkv, att=att, x2=x2, gu=gu, rstd1=rstd1, rstd2=rstd2, lse=lse)
                 st["layers"].append(ls)
             x = x3
+        return x
+
+    def decoder_logits(self, inputs_embeds):
+        """inputs_embeds [nseq,T,H] bf16 -> logits [nseq,T,V] bf16 (inference form, no stash)."""
+        d = self.dims
+        nseq, T, H = inputs_embeds.shape
+        x = inputs_embeds.to(device=self.device, dtype=_BF).reshape(nseq * T, H).contiguous()
+        x = self._run_layers(x, nseq, T, None)
+        hn = ops.rmsnorm_fwd(x, self.store.p["norm"], d.rms_eps, out=self.buf("hn", (nseq * T, H)))
+        logits = ops.gemm(hn, self.store.p["lm_head"])
+        return logits.view(nseq, T, d.vocab_size)
+
+    # ------------------------------------------------------------------ forward
+    def forward_logps(self, input_ids, labels, images, keep_stash=True, return_per_token=True, T_hint=None):
+        """input_ids/labels [2b, L] int64 (win rows first, then rej — preference_collator_fn order),
+        images [b,3,S,S].  Returns dict(per_token_logps [2b,T-1], logp [2b], avg_logp [2b], labels [2b,T])."""
+        d, P = self.dims, self.store.p
+        dev = self.device
+        input_ids = input_ids.to(dev).contiguous()
+        labels = labels.to(dev).contiguous()
+        nseq = input_ids.shape[0]
+        b = images.shape[0]
+        H, F, V = d.hidden_size, d.intermediate_size, d.vocab_size
+        nh, hd = d.num_heads, d.head_dim
+        st = {"layers": []} if keep_stash else None
+
+        feats = self.encode_images(images)                                   # [b*Pn, C]
+        pre = ops.gemm(feats, P["proj.w0"], self.buf("proj_pre", (feats.shape[0], H)), bias=P["proj.b0"])
+        post = ops.gelu_fwd(pre, self.buf("proj_post", pre.shape))
+        proj = ops.gemm(post, P["proj.w2"], self.buf("proj_out", pre.shape), bias=P["proj.b2"])
+        # images are shared by the win and rej copy of a pair (trainers.py:190 cat([images, images]))
+        n_slots = nseq
+        img_index = (torch.arange(n_slots, dtype=torch.int32, device=dev) % b).contiguous() if nseq == 2 * b \
+            else torch.arange(n_slots, dtype=torch.int32, device=dev)
+        x, new_labels, src, T = self.splice(input_ids, labels, proj, b, img_index,
+                                            T_hint=(T_hint, n_slots) if T_hint is not None else None)
+        M = nseq * T
+        if keep_stash:
+            st.update(feats=feats, proj_pre=pre, proj_post=post, src=src, input_ids=input_ids, labels=new_labels,
+                      T=T, nseq=nseq, b=b)
+        x = self._run_layers(x, nseq, T, st)
         rstd_f = torch.empty(M, dtype=_F32, device=dev) if keep_stash else None
         hn = ops.rmsnorm_fwd(x, P["norm"], d.rms_eps, out=self.buf("hn", (M, H)), rstd=rstd_f)
         logits = ops.gemm(hn, P["lm_head"], self.buf("logits", (M, V)))

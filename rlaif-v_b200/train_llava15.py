@@ -1,0 +1,197 @@
+"""Training entry point — drop-in for `muffin/train/train_llava15.py` (same flag names as
+script/train/llava15_train.sh:6-48, same three argument groups, same train() flow):
+
+    torchrun --nproc-per-node 8 -m rlaifv_b200.train_llava15 --deepspeed ./script/zero2.json \
+        --model_name_or_path ... --data_dir ... --task DPO --dpo_beta 0.1 ...
+
+Differences forced by the environment (SURVEY.md §8b "environment drift"): arguments are parsed by
+a small dataclass parser instead of HfArgumentParser/transformers.TrainingArguments (which refuses
+--deepspeed/--bf16 without `accelerate`), the launcher is torchrun (one process per GPU, NCCL)
+instead of `deepspeed`, and `--deepspeed <json>` is read only for its ZeRO stage (2 = what this
+engine implements natively).
+"""
+import argparse
+import dataclasses
+import glob
+import json
+import os
+import pathlib
+from dataclasses import dataclass, field
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+
+@dataclass
+class ModelArguments:                      # muffin/train/train_llava15.py:32-46
+    model_name_or_path: Optional[str] = "facebook/opt-125m"
+    version: Optional[str] = "llava_v1"
+    freeze_backbone: bool = False
+    tune_mm_mlp_adapter: bool = False
+    vision_tower: Optional[str] = None
+    mm_vision_select_layer: Optional[int] = -1
+    pretrain_mm_mlp_adapter: Optional[str] = None
+    mm_projector_type: Optional[str] = "linear"
+    mm_use_im_start_end: bool = False
+    mm_use_im_patch_token: bool = True
+    mm_patch_merge_type: Optional[str] = "flat"
+    mm_vision_select_feature: Optional[str] = "patch"
+
+
+@dataclass
+class DataArguments:                       # muffin/train/train_llava15.py:49-69
+    lazy_preprocess: bool = False
+    is_multimodal: bool = False
+    image_token_len: int = 0
+    image_folder: Optional[str] = None
+    image_aspect_ratio: str = "square"
+    parquet: bool = False
+    data_source_names: str = "unimm-chat"
+    data_source_weights: str = "100"
+    eval_data_source_names: Optional[str] = None
+    data_dir: str = "./RLAIF-V-Dataset/"
+    kto_win_data_source_names: str = "100"
+    kto_win_data_source_weights: str = "100"
+    kto_rej_data_source_names: str = "100"
+    kto_rej_data_source_weights: str = "100"
+    dpo_beta: float = 0.5
+    dpo_token_weight: float = 3.0
+    shuffle_data: bool = True
+
+
+@dataclass
+class TrainingArguments:                   # muffin/train/train_llava15.py:72-100 + the HF fields the script sets
+    output_dir: str = "./checkpoints"
+    cache_dir: Optional[str] = None
+    optim: str = "adamw_torch"
+    remove_unused_columns: bool = False
+    freeze_mm_mlp_adapter: bool = False
+    force_fsdp: bool = False
+    model_max_length: int = 512
+    max_steps: int = 1000
+    no_randaug: bool = False
+    task: str = "LM"
+    dpo_use_average: bool = False
+    dpo_token_weighted: bool = False
+    mm_projector_lr: Optional[float] = None
+    group_by_modality_length: bool = False
+    fully_tune: bool = False
+    deepspeed: Optional[str] = None
+    bf16: bool = False
+    tf32: bool = False
+    num_train_epochs: float = 3.0
+    per_device_train_batch_size: int = 8
+    per_device_eval_batch_size: int = 8
+    gradient_accumulation_steps: int = 1
+    evaluation_strategy: str = "no"
+    save_strategy: str = "steps"
+    save_steps: int = 500
+    save_total_limit: Optional[int] = None
+    learning_rate: float = 5e-5
+    weight_decay: float = 0.0
+    adam_beta1: float = 0.9
+    adam_beta2: float = 0.999
+    adam_epsilon: float = 1e-8
+    warmup_ratio: float = 0.0
+    lr_scheduler_type: str = "linear"
+    logging_steps: int = 500
+    logging_dir: Optional[str] = None
+    gradient_checkpointing: bool = False
+    report_to: str = "none"
+    run_name: Optional[str] = None
+    dataloader_num_workers: int = 0
+    seed: int = 42
+    local_rank: int = -1
+    micro_pairs: Optional[int] = None      # B200 engine knob: pairs per micro-batch (None = whole batch)
+
+
+def _add_fields(parser, cls):
+    for f in dataclasses.fields(cls):
+        typ = f.type
+        base = typ.__args__[0] if getattr(typ, "__args__", None) else typ
+        if base is bool:
+            parser.add_argument("--" + f.name, type=lambda s: str(s).lower() in ("1", "true", "yes"),
+                                nargs="?", const=True, default=f.default)
+        else:
+            parser.add_argument("--" + f.name, type=base, default=f.default)
+
+
+def parse_args_into_dataclasses(argv=None):
+    parser = argparse.ArgumentParser(allow_abbrev=False)
+    for cls in (ModelArguments, DataArguments, TrainingArguments):
+        _add_fields(parser, cls)
+    ns, unknown = parser.parse_known_args(argv)
+    if unknown:
+        raise SystemExit("unknown arguments: %s" % unknown)
+    out = []
+    for cls in (ModelArguments, DataArguments, TrainingArguments):
+        out.append(cls(**{f.name: getattr(ns, f.name) for f in dataclasses.fields(cls)}))
+    return tuple(out)
+
+
+def zero_stage(path):
+    if not path:
+        return 0
+    with open(path) as f:
+        return int(json.load(f).get("zero_optimization", {}).get("stage", 0))
+
+
+def safe_save_model_for_hf_trainer(trainer, output_dir):
+    """muffin/train/train_llava15.py:102-112 — full state dict to CPU, saved by the main process."""
+    if trainer.args.should_save:
+        trainer._save(output_dir, state_dict={k: v.cpu() for k, v in trainer.model.state_dict().items()})
+
+
+def init_distributed():
+    if "RANK" in os.environ and int(os.environ.get("WORLD_SIZE", "1")) > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    return int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def init_model(model_args, data_args, training_args, attn_implementation=None):
+    """muffin/train/train_llava15.py:198-281: policy model (+ frozen reference used once for the
+    log-prob pre-pass inside the dataset), tokenizer, data module."""
+    from .llava_model import LlavaLlamaForCausalLM
+    from .model import LlavaDims
+    from .data import make_dpo_data_module, load_tokenizer, load_hf_checkpoint
+    local_rank = init_distributed()
+    dims = LlavaDims(select_layer=model_args.mm_vision_select_layer, max_len=training_args.model_max_length)
+    state = load_hf_checkpoint(model_args.model_name_or_path, model_args.vision_tower)
+    model = LlavaLlamaForCausalLM(dims, torch.device("cuda", local_rank), hf_state=state)
+    model.config.use_cache = False
+    tokenizer = load_tokenizer(model_args.model_name_or_path, training_args.model_max_length)
+    data_args.is_multimodal = True
+    data_args.image_token_len = dims.num_patches
+    data_module = make_dpo_data_module(tokenizer=tokenizer, data_args=data_args, reference_model=model)
+    return model, data_module, tokenizer
+
+
+def train(attn_implementation=None, argv=None):
+    model_args, data_args, training_args = parse_args_into_dataclasses(argv)
+    data_args.data_source_names = data_args.data_source_names.split("#")
+    data_args.data_source_weights = [int(x) for x in data_args.data_source_weights.split("#")]
+    if data_args.eval_data_source_names is not None:
+        data_args.eval_data_source_names = data_args.eval_data_source_names.split("#")
+    if zero_stage(training_args.deepspeed) not in (0, 2):
+        raise NotImplementedError("only ZeRO stage 2 (script/zero2.json) is implemented natively")
+    model, data_module, tokenizer = init_model(model_args, data_args, training_args, attn_implementation)
+    if training_args.task != "DPO":
+        raise NotImplementedError
+    from .trainers import LLaVA15DPOTrainer
+    trainer = LLaVA15DPOTrainer(model=model, tokenizer=tokenizer, args=training_args, **data_module)
+    if list(pathlib.Path(training_args.output_dir).glob("checkpoint-*")):
+        print("Resume from checkpoint.")
+        trainer.train(resume_from_checkpoint=True)
+    else:
+        print("Train from start.")
+        trainer.train()
+    trainer.save_state()
+    safe_save_model_for_hf_trainer(trainer=trainer, output_dir=training_args.output_dir)
+
+
+if __name__ == "__main__":
+    train(attn_implementation="flash_attention_2")

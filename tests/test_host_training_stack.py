@@ -1,0 +1,141 @@
+"""CPU tests of the host-side training stack: flag parsing (every flag of the reference launch
+script), the llava_v1 sample encoding with a toy tokenizer, the ZeRO-2 partition / collective
+plumbing on world_size-2 gloo, and the parquet contract of the reference log-prob cache."""
+import json
+import os
+import re
+import subprocess
+import sys
+import textwrap
+
+import pytest
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def script_flags():
+    txt = open(os.path.join(REPO, "script", "train", "llava15_train.sh")).read()
+    txt = txt[txt.index("rlaifv_b200.train_llava15"):]
+    toks = re.findall(r"(--[a-z_0-9]+)\s+([^\\\n]+?)\s*(?:\\|$)", txt, flags=re.M)
+    argv = []
+    for k, v in toks:
+        argv += [k, v.strip().strip("'\"")]
+    return argv
+
+
+def test_every_reference_flag_parses():
+    from rlaifv_b200.train_llava15 import parse_args_into_dataclasses, zero_stage
+    argv = [a.replace("$task_name-$exp_name", "x").replace("$exp_name", "x") for a in script_flags()]
+    m, d, t = parse_args_into_dataclasses(argv)
+    assert t.task == "DPO" and d.dpo_beta == 0.1 and t.dpo_use_average is False and t.max_steps == 2672
+    assert t.learning_rate == 5e-7 and t.weight_decay == 0.01 and t.warmup_ratio == 0.05 and t.bf16 is True
+    assert m.mm_vision_select_layer == -2 and m.mm_projector_type == "mlp2x_gelu" and t.model_max_length == 2048
+    assert zero_stage(os.path.join(REPO, "script", "zero2.json")) == 2
+    assert len(argv) // 2 >= 40
+
+
+def test_llava_v1_encoding_matches_reference_fixture():
+    """ids and label masks of encode_multimodal_preference_sample / preprocess_v1 equal the unmodified
+    reference's (fixture from oracle/gen_golden.py, same toy tokenizer)."""
+    import numpy as np
+    from oracle.toy_tokenizer import ToyTokenizer
+    from rlaifv_b200.data import IMAGE_TOKEN_INDEX, encode_multimodal_preference_sample
+    fx = np.load(os.path.join(REPO, "tests", "golden_host", "encode_case.npz"))
+    tok = ToyTokenizer()
+    cfg = {"image_processor": lambda im: torch.zeros(3, 4, 4), "is_multimodal": True, "image_token_len": 576,
+           "use_im_start_end": False, "keep_image_tag": True}
+    for i in range(int(fx["n"])):
+        src = {"question": {"from": "human", "value": str(fx[f"s{i}_q"])},
+               "chosen": {"from": "gpt", "value": str(fx[f"s{i}_c"])},
+               "rejected": {"from": "gpt", "value": str(fx[f"s{i}_r"])}, "image": "IMG",
+               "ref_win_logp": -1.0, "ref_rej_logp": -2.0, "ref_win_avg_logp": -0.1, "ref_rej_avg_logp": -0.2,
+               "ref_win_per_token_logp": [0.0] * 9, "ref_rej_per_token_logp": [0.0] * 9}
+        rej, win = encode_multimodal_preference_sample(src, tok, cfg)
+        assert np.array_equal(win["input_ids"].numpy(), fx[f"s{i}_win_ids"])
+        assert np.array_equal(win["labels"].numpy(), fx[f"s{i}_win_labels"])
+        assert np.array_equal(rej["input_ids"].numpy(), fx[f"s{i}_rej_ids"])
+        assert np.array_equal(rej["labels"].numpy(), fx[f"s{i}_rej_labels"])
+        assert (win["input_ids"] == IMAGE_TOKEN_INDEX).sum() == 1 and win["labels"][0] == -100
+        assert win["ref_win_logp"] == -1.0 and rej["ref_rej_logp"] == -2.0
+
+
+def test_logp_parquet_contract_roundtrip(tmp_path):
+    from rlaifv_b200.data import _load_parquet_dir, write_logp_to_preference_parquet
+    rows = [{"question": f"q{i}", "chosen": "c", "rejected": "r", "idx": i, "image": {"bytes": b"x"}} for i in range(3)]
+    logps = [(-1.0 * i, -0.1, [0.5, 0.25], -2.0, -0.2, [0.125]) for i in range(3)]
+    write_logp_to_preference_parquet(rows, str(tmp_path), logps)
+    files = os.listdir(tmp_path)
+    assert files == ["RLAIF-V-Dataset-withlogp_000-3.parquet"]
+    back = _load_parquet_dir(str(tmp_path))
+    v = json.loads(back[2]["logps"])["logps"]
+    assert v[0] == -2.0 and v[2] == [0.5, 0.25] and v[5] == [0.125] and len(v) == 6
+
+
+GLOO_WORKER = textwrap.dedent('''
+    import os, sys, torch, torch.distributed as dist
+    sys.path.insert(0, %r)
+    rank, world = int(sys.argv[1]), 2
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = sys.argv[2]
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from rlaifv_b200.model import LlavaDims, ParamStore
+    from rlaifv_b200 import zero2, ops
+    # test double for the CUDA AdamW kernel (this test covers partitioning + collectives on CPU only)
+    def fake_adamw(master, m, v, grad, param, lr, b1, b2, eps, wd, step, grad_scale=1.0):
+        master.mul_(1 - lr * wd).add_(grad.float(), alpha=-lr)
+        param.copy_(master.to(param.dtype))
+    ops.adamw_step = fake_adamw
+    zero2.ops.adamw_step = fake_adamw
+    class Ev:
+        def record(self, *a): pass
+    class St:
+        def wait_stream(self, *a): pass
+        def wait_event(self, *a): pass
+    import contextlib
+    torch.cuda.Event = lambda *a, **k: Ev()
+    torch.cuda.current_stream = lambda *a, **k: St()
+    torch.cuda.Stream = lambda *a, **k: St()
+    torch.cuda.stream = lambda s: contextlib.nullcontext()
+    # gloo lacks reduce_scatter_tensor: emulate with all_reduce + slice (same semantics)
+    def rs(out, inp, op=None, group=None):
+        t = inp.float(); dist.all_reduce(t); n = inp.numel() // world
+        out.copy_(t[rank * n:(rank + 1) * n].to(out.dtype))
+    def ag(out, inp, group=None):
+        parts = [torch.empty_like(inp) for _ in range(world)]
+        dist.all_gather(parts, inp.clone()); out.copy_(torch.cat(parts))
+    dist.reduce_scatter_tensor = rs; dist.all_gather_into_tensor = ag
+    zero2.dist.reduce_scatter_tensor = rs; zero2.dist.all_gather_into_tensor = ag
+    d = LlavaDims(vocab_size=64, hidden_size=64, intermediate_size=128, num_layers=2, num_heads=1,
+                  clip_hidden=64, clip_intermediate=64, clip_layers=2, clip_heads=1, image_size=28)
+    st = ParamStore(d, "cpu")
+    torch.manual_seed(0)
+    st.flat.copy_(torch.randn(st.numel).bfloat16())
+    p0 = st.flat.clone().float()
+    torch.manual_seed(100 + rank)
+    st.grad.copy_((torch.randn(st.numel) * 0.5).bfloat16())        # rank-local grads (already 1/world scaled)
+    gsum = st.grad.float().clone(); dist.all_reduce(gsum)
+    opt = zero2.Zero2AdamW(st, lr=0.1, weight_decay=0.0, rank=rank, world=world)
+    assert opt.owned * world == st.numel
+    opt.reduce_all()
+    opt.step(0.1)
+    expect = (p0 - 0.1 * gsum.bfloat16().float()).bfloat16().float()
+    err = (st.flat.float() - expect).abs().max().item()
+    # every rank holds the full updated parameters after the all-gather
+    chk = st.flat.float().clone(); dist.all_reduce(chk)
+    same = (chk / world - st.flat.float()).abs().max().item()
+    print("RESULT", rank, err, same)
+    assert err <= 4e-2 and same == 0.0
+    dist.destroy_process_group()
+''')
+
+
+def test_zero2_partition_and_collectives_gloo_world2(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(GLOO_WORKER % REPO)
+    port = str(29000 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), port], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "RESULT" in o

@@ -19,9 +19,18 @@ def rel(a, b):
     return float((a - b).abs().max() / (b.abs().max() + 1e-12))
 
 
+_PARAMS = {}
+
+
+def params_for(scale):
+    if scale not in _PARAMS:
+        _PARAMS[scale] = O.make_params(O.TINY, seed=0, scale=scale)
+    return _PARAMS[scale]
+
+
 @pytest.fixture(scope="module")
 def params():
-    return O.make_params(O.TINY, seed=0)
+    return params_for(1.0)
 
 
 def test_fixtures_exist():
@@ -29,8 +38,9 @@ def test_fixtures_exist():
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
-def test_oracle_matches_reference_outputs(params, path):
+def test_oracle_matches_reference_outputs(path):
     fx = np.load(path)
+    params = params_for(float(fx["param_scale"]))
     assert abs(O.params_checksum(params) - float(fx["params_checksum"])) <= 1e-9 * float(fx["params_checksum"])
     p = {k: v.clone().requires_grad_(k.startswith(O.TRAINABLE_PREFIXES)) for k, v in params.items()}
     batch = dict(concatenated_input_ids=torch.from_numpy(fx["concatenated_input_ids"]),

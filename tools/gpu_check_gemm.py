@@ -59,6 +59,18 @@ try:
     run_case(1000, 1024, 4096, False, False, 0, bias=True, act=2)
     run_case(777, 768, 512, False, False, 0, residual=True)
     run_case(512, 768, 1135, True, True, 0, accumulate=True)
+    # 2-CTA kernel (tile_n=512)
+    run_case(256, 256, 64, False, False, 512)
+    run_case(256, 256, 512, False, False, 512)
+    run_case(256, 256, 64, False, True, 512)
+    run_case(256, 256, 64, True, True, 512)
+    run_case(1000, 768, 512, False, False, 512, bias=True, act=1)
+    run_case(777, 768, 512, False, True, 512, residual=True)
+    run_case(512, 768, 1135, True, True, 512, accumulate=True)
+    run_case(4096, 4096, 1024, False, False, 512)
+    run_case(4096, 4096, 1024, False, True, 512)
+    run_case(4096, 4096, 1135, True, True, 512)
+    run_case(18160, 4096, 512, False, False, 512)
     # many tiles / persistent loop with several tiles per CTA
     run_case(4096, 4096, 1024, False, False, 256)
     run_case(4096, 4096, 1024, False, True, 256)
@@ -91,6 +103,12 @@ def bench(M, N, K, a_mn, b_mn, tile_n=0, iters=10):
 if fails == 0:
     try:
         Mtok = 18160
+        for bn in (256, 512):
+            bench(Mtok, 12288, 4096, False, False, bn)
+            bench(Mtok, 4096, 11008, False, False, bn)
+            bench(Mtok, 11008, 4096, False, True, bn)
+            bench(4096, 11008, Mtok, True, True, bn)
+            bench(22016, 4096, Mtok, True, True, bn)
         bench(Mtok, 12288, 4096, False, False)      # qkv fwd
         bench(Mtok, 4096, 4096, False, False)       # o fwd
         bench(Mtok, 22016, 4096, False, False)      # gate|up fwd

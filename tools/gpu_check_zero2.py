@@ -1,0 +1,65 @@
+"""torchrun worker: 2-rank ZeRO-2 DPO step vs single-GPU step on the same global batch (tiny dims)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, torch.distributed as dist
+from oracle import llava_dpo_oracle as O
+from rlaifv_b200.engine import DPOStepEngine
+from rlaifv_b200.model import LlavaDims, LlavaDPOPolicy
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+c = O.TINY
+dims = LlavaDims(vocab_size=c.vocab_size, hidden_size=c.hidden_size, intermediate_size=c.intermediate_size,
+                 num_layers=c.num_layers, num_heads=c.num_heads, clip_hidden=c.clip_hidden,
+                 clip_intermediate=c.clip_intermediate, clip_layers=c.clip_layers, clip_heads=c.clip_heads,
+                 image_size=c.image_size, patch_size=c.patch_size)
+params = O.make_params(c, seed=0, scale=0.4)
+Bg = 2 * world                                    # global pairs
+full = O.synthetic_pair_batch(c, Bg, 24, 20, seed=21, image_pos=6, ragged=False)
+g = torch.Generator().manual_seed(5)
+full["ref_win_logp"] = -80.0 + torch.randn(Bg, generator=g)
+full["ref_rej_logp"] = -80.0 + torch.randn(Bg, generator=g)
+full["beta"] = 0.1
+
+def shard(b, lo, hi):
+    ids, lab = b["concatenated_input_ids"], b["concatenated_labels"]
+    return {"concatenated_input_ids": torch.cat([ids[lo:hi], ids[Bg + lo:Bg + hi]]),
+            "concatenated_labels": torch.cat([lab[lo:hi], lab[Bg + lo:Bg + hi]]),
+            "images": b["images"][lo:hi], "ref_win_logp": b["ref_win_logp"][lo:hi],
+            "ref_rej_logp": b["ref_rej_logp"][lo:hi], "beta": b["beta"]}
+
+pol = LlavaDPOPolicy(dims, torch.device("cuda", local), hf_state=params)
+eng = DPOStepEngine(pol, lr=1e-3, weight_decay=0.01, total_steps=10, constant_lr=True, rank=rank, world=world)
+for step in range(2):
+    m = eng.train_step(shard(full, 2 * rank, 2 * rank + 2))
+md = eng.metrics_dict(m)
+torch.cuda.synchronize()
+dist.barrier()
+ok = True
+if rank == 0:
+    pol1 = LlavaDPOPolicy(dims, torch.device("cuda", local), hf_state=params)
+    eng1 = DPOStepEngine(pol1, lr=1e-3, weight_decay=0.01, total_steps=10, constant_lr=True, micro_pairs=2)
+    for step in range(2):
+        m1 = eng1.train_step(full)
+    md1 = eng1.metrics_dict(m1)
+    torch.cuda.synchronize()
+    a, b = pol.store.flat.float(), pol1.store.flat.float()
+    p0 = LlavaDPOPolicy(dims, torch.device("cuda", local), hf_state=params).store.flat.float()
+    upd_ref = (b - p0)
+    err = (a - b).abs().max().item()
+    rel_upd = ((a - b).norm() / (upd_ref.norm() + 1e-12)).item()
+    print("loss dp %.6f single %.6f | max |dW| %.3e, update-relative diff %.3e, update norm %.3e" %
+          (md["loss"], md1["loss"], err, rel_upd, upd_ref.norm().item()), flush=True)
+    ok = abs(md["loss"] - md1["loss"]) <= 1e-3 * max(1.0, abs(md1["loss"])) and rel_upd <= 5e-2 and upd_ref.norm().item() > 0
+# all ranks must hold identical parameters after the all-gather
+chk = pol.store.flat.float().clone()
+dist.all_reduce(chk)
+same = (chk / world - pol.store.flat.float()).abs().max().item()
+flag = torch.tensor([1.0 if (ok and same == 0.0) else 0.0], device="cuda")
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("replicas identical:", same == 0.0)
+    print("ZERO2_OK" if flag.item() == 1.0 else "ZERO2_FAIL", flush=True)
+dist.destroy_process_group()
+sys.exit(0 if flag.item() == 1.0 else 1)
