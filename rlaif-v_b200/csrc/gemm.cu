@@ -495,9 +495,10 @@ static int operand_tmap(CUtensorMap* tm, const void* ptr, long long ld, bool mn_
 
 using namespace b200;
 
-static int g_enable_2cta = 0;   // auto-selection of the 2-CTA kernel (explicit tile_n = 512 always works)
+// auto-selection policy for tile_n = 0: 0 never, 1 whenever the problem is large, 2 (default) where measured faster
+static int g_enable_2cta = 2;
 extern "C" int rlaifv_gemm_set_2cta(int enable) {
-  g_enable_2cta = enable ? 1 : 0;
+  g_enable_2cta = enable;
   return 0;
 }
 
@@ -516,7 +517,11 @@ extern "C" int rlaifv_gemm_bf16(const void* A, long long lda, int a_mn_major, co
   if (bn == 0) {
     const long long tiles256 = (long long)((M + 127) / 128) * ((N + 255) / 256);
     const long long tiles2 = (long long)((M + 255) / 256) * ((N + 255) / 256);
-    if (g_enable_2cta && N >= 256 && tiles2 >= 64) bn = 512;
+    // measured on B200 (profiles/r01_gemm_1cta_vs_2cta.log): the CTA-pair kernel wins for long-K
+    // forward/dgrad shapes (down_proj, K=11008: +6%) and the very wide lm_head (+4%); elsewhere the
+    // 1-CTA 128x256 kernel is equal or better.
+    const bool pair_wins = !a_mn_major && tiles2 >= 64 && (K >= 8192 || N >= 30000);
+    if (N >= 256 && (g_enable_2cta == 1 ? tiles2 >= 64 : (g_enable_2cta == 2 && pair_wins))) bn = 512;
     else bn = (N >= 256 && tiles256 >= 120) ? 256 : 128;
   }
   B200_REQUIRE(bn == 128 || bn == 256 || bn == 512, "gemm: tile_n must be 0, 128, 256 or 512 (2-CTA 256x256)");

