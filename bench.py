@@ -191,6 +191,7 @@ def main():
     ap.add_argument("--micro-pairs", type=int, default=0, help="pairs per micro-batch (0 = auto)")
     ap.add_argument("--layers", type=int, default=32, help="debug only; anything but 32 is not the benchmark")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stash-extra", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -211,10 +212,13 @@ def main():
 
     dims = LlavaDims(num_layers=args.layers)
     B = PAIRS_PER_GPU
-    micro = args.micro_pairs or (4 if world == 1 else B)   # 1 GPU holds the unsharded 81 GB optimizer state
+    micro = args.micro_pairs or B
     policy = LlavaDPOPolicy(dims, torch.device("cuda", local_rank), seed=0)
     engine = DPOStepEngine(policy, lr=5e-7, weight_decay=0.01, total_steps=2672, micro_pairs=micro,
                            rank=rank, world=world)
+    # HBM plan: with the optimizer state sharded over >= 2 GPUs there is room to stash the normalised inputs
+    # and the SwiGLU product (no recompute in the backward); one GPU holds the unsharded 81 GB state.
+    policy.stash_extra = world > 1 and not args.no_stash_extra
     T = PROMPT_LEN + RESP_LEN - 1 + dims.num_patches
 
     # frozen-reference log-probs = initial policy log-probs (step-0 loss = ln 2 known answer)
@@ -246,8 +250,19 @@ def main():
                 loss_host.copy_(m, non_blocking=True)
                 torch.cuda.current_stream().synchronize()
 
-    step0 = engine.train_step(dev_batches[0], optimizer_step=False)   # known-answer check (no update)
-    loss0 = float(step0[0].item())
+    try:
+        step0 = engine.train_step(dev_batches[0], optimizer_step=False)   # known-answer check (no update)
+        loss0 = float(step0[0].item())
+    except torch.OutOfMemoryError:
+        # whole-batch activations did not fit next to the optimizer state: fall back to 2 micro-batches
+        policy._stash = None
+        policy._bufs.clear()
+        policy.stash_extra = False
+        torch.cuda.empty_cache()
+        micro = max(1, B // 2)
+        engine.micro_pairs = micro
+        step0 = engine.train_step(dev_batches[0], optimizer_step=False)
+        loss0 = float(step0[0].item())
 
     # ---- device-resident timing (value) ----
     run_steps(dev_batches, args.warmup, False)
@@ -257,7 +272,9 @@ def main():
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t_host0 = time.perf_counter()
     run_steps(dev_batches, args.steps, False)
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps   # CPU time to enqueue one step
     e1.record()
     barrier()
     ms_dev = e0.elapsed_time(e1) / args.steps
@@ -320,7 +337,8 @@ def main():
                    "step0_loss": loss0, "step0_loss_expected": math.log(2.0)},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 36,
                 "ms_per_step": ms_e2e},
-        "gpu_launches": int(launches),
+        "hbm_peak_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
+        "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms,
         "clocks": clocks,
         "model_flops_per_pair": f_pair,
         "step_tflops_per_gpu": value / world * f_pair / 1e12,

@@ -39,6 +39,9 @@ int rlaifv_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B
 /* tile_n = 512 selects the 2-CTA kernel (cta_group::2, 256x256 tile per CTA pair). rlaifv_gemm_set_2cta(1)
  * lets tile_n = 0 (auto) pick it for large problems. */
 int rlaifv_gemm_set_2cta(int enable);
+/* raster group size (row-blocks per group, default 16) and profiling switches (debug: bit0 skip stores,
+ * bit1 skip TMEM loads too — results are then garbage; for roofline experiments only). */
+int rlaifv_gemm_set_tuning(int group_m, int debug);
 
 /* ---- attention (tcgen05, S/O accumulators in TMEM) ---------------------------------------------
  * q/k/v/out: [nseq*S][ld] bf16, head h at columns [h*head_dim, (h+1)*head_dim); lse fp32

@@ -26,6 +26,8 @@ struct GemmEpilogue {
   long long ldr;
   int act;         // 0 none, 1 GELU(erf), 2 quick_gelu (x*sigmoid(1.702x))
   int accumulate;  // C = C + result (fp32 add of the old bf16 value)
+  int group_m;     // raster: tiles are walked m-fastest inside groups of `group_m` row-blocks
+  int debug;       // profiling only: bit0 skip global stores, bit1 skip the TMEM loads as well
 };
 
 constexpr int GEMM_BM = 128;
@@ -42,8 +44,7 @@ struct GemmCfg {
   static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;  // + barriers + align
 };
 
-__device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& m_blk, int& n_blk) {
-  constexpr int GROUP_M = 16;
+__device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int GROUP_M, int& m_blk, int& n_blk) {
   int per_group = GROUP_M * num_n;
   int g = t / per_group;
   int first_m = g * GROUP_M;
@@ -158,7 +159,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         int m_blk, n_blk;
-        tile_coords(t, num_m, num_n, m_blk, n_blk);
+        tile_coords(t, num_m, num_n, epi.group_m, m_blk, n_blk);
         const int m0 = m_blk * GEMM_BM, n0 = n_blk * BN;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
@@ -221,7 +222,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       int m_blk, n_blk;
-      tile_coords(t, num_m, num_n, m_blk, n_blk);
+      tile_coords(t, num_m, num_n, epi.group_m, m_blk, n_blk);
       const int acc = it & 1;
       const uint32_t acc_ph = (it >> 1) & 1;
       mbar_wait(&tfull[acc], acc_ph);
@@ -233,11 +234,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bf16* r_row = epi.residual ? epi.residual + row * epi.ldr : nullptr;
 #pragma unroll 1
       for (int ch = 0; ch < BN / 32; ++ch) {
+        if (epi.debug & 2) break;
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_addr + ch * 32, r);
         tmem_wait_ld();
         const int col0 = n_blk * BN + ch * 32;
-        if (row_ok && col0 < N) epilogue_chunk(r, col0, N, c_row, r_row, epi);
+        if (row_ok && col0 < N && !(epi.debug & 1)) epilogue_chunk(r, col0, N, c_row, r_row, epi);
       }
       tc_fence_before();
       __syncwarp();
@@ -337,7 +339,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t ph = 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
         int m_blk, n_blk;
-        tile_coords(t, num_m, num_n, m_blk, n_blk);
+        tile_coords(t, num_m, num_n, epi.group_m, m_blk, n_blk);
         const int m0 = m_blk * 256 + (int)cta_rank * 128;
         const int n0 = n_blk * BN + (int)cta_rank * 128;
         for (int kb = 0; kb < num_k; ++kb) {
@@ -403,7 +405,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int it = 0;
     for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
       int m_blk, n_blk;
-      tile_coords(t, num_m, num_n, m_blk, n_blk);
+      tile_coords(t, num_m, num_n, epi.group_m, m_blk, n_blk);
       const int acc = it & 1;
       const uint32_t acc_ph = (it >> 1) & 1;
       mbar_wait(&tfull[acc], acc_ph);
@@ -415,11 +417,12 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const bf16* r_row = epi.residual ? epi.residual + row * epi.ldr : nullptr;
 #pragma unroll 1
       for (int ch = 0; ch < BN / 32; ++ch) {
+        if (epi.debug & 2) break;
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_addr + ch * 32, r);
         tmem_wait_ld();
         const int col0 = n_blk * BN + ch * 32;
-        if (row_ok && col0 < N) epilogue_chunk(r, col0, N, c_row, r_row, epi);
+        if (row_ok && col0 < N && !(epi.debug & 1)) epilogue_chunk(r, col0, N, c_row, r_row, epi);
       }
       tc_fence_before();
       __syncwarp();
@@ -495,6 +498,13 @@ static int operand_tmap(CUtensorMap* tm, const void* ptr, long long ld, bool mn_
 
 using namespace b200;
 
+static int g_group_m = 16;
+static int g_debug = 0;
+extern "C" int rlaifv_gemm_set_tuning(int group_m, int debug) {
+  if (group_m > 0) g_group_m = group_m;
+  g_debug = debug;
+  return 0;
+}
 // auto-selection policy for tile_n = 0: 0 never, 1 whenever the problem is large, 2 (default) where measured faster
 static int g_enable_2cta = 2;
 extern "C" int rlaifv_gemm_set_2cta(int enable) {
@@ -538,6 +548,8 @@ extern "C" int rlaifv_gemm_bf16(const void* A, long long lda, int a_mn_major, co
   epi.ldr = ldr;
   epi.act = act;
   epi.accumulate = accumulate;
+  epi.group_m = g_group_m;
+  epi.debug = g_debug;
   cudaStream_t st = (cudaStream_t)stream;
   if (bn == 512) {
     if (!a_mn_major && !b_mn_major) return launch_gemm2<false, false>(tmA, tmB, M, N, K, epi, st);

@@ -155,15 +155,25 @@ rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
   }
 }
 
-// dw[h] (bf16, accumulate or overwrite) from fp32 partials [P][H]
-__global__ void reduce_partials_kernel(const float* __restrict__ part, int P, int H,
-                                       bf16* __restrict__ dw, int accumulate) {
-  const int h = blockIdx.x * blockDim.x + threadIdx.x;
-  if (h >= H) return;
+// dw[h] (bf16, accumulate or overwrite) from fp32 partials [P][H].
+// Block = 32 columns x 8 row-lanes: coalesced 128-byte reads, rows strided by 8, smem tree at the end.
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float* __restrict__ part, int P, int H, bf16* __restrict__ dw, int accumulate) {
+  __shared__ float sm[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int h = blockIdx.x * 32 + cx;
   float s = 0.f;
-  for (int p = 0; p < P; ++p) s += part[(long long)p * H + h];
-  if (accumulate) s += __bfloat162float(dw[h]);
-  dw[h] = __float2bfloat16_rn(s);
+  if (h < H)
+    for (int p = ry; p < P; p += 8) s += part[(long long)p * H + h];
+  sm[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0 && h < H) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[i][cx];
+    if (accumulate) t += __bfloat162float(dw[h]);
+    dw[h] = __float2bfloat16_rn(t);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -818,17 +828,17 @@ extern "C" int rlaifv_rmsnorm_fwd(const void* x, const void* w, void* y, float* 
 }
 
 // workspace: fp32 [rlaifv_rmsnorm_bwd_partials() * H]
-extern "C" int rlaifv_rmsnorm_bwd_partials(void) { return num_sms() * 4; }
+extern "C" int rlaifv_rmsnorm_bwd_partials(void) { return num_sms() * 2; }
 extern "C" int rlaifv_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd,
                                   const void* dres, void* dx, void* dw, int dw_accumulate,
                                   float* workspace, int M, int H, void* stream) {
   B200_REQUIRE(H % 8 == 0 && H <= NORM_THREADS * 8 * NORM_MAXCH, "rmsnorm_bwd: H=%d unsupported", H);
-  int grid = num_sms() * 4;
+  int grid = num_sms() * 2;
   if (grid > M) grid = M;
   rmsnorm_bwd_kernel<<<grid, NORM_THREADS, 0, ST>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, rstd,
                                                    (const bf16*)dres, (bf16*)dx, workspace, M, H);
   B200_CHECK_CUDA(cudaGetLastError());
-  reduce_partials_kernel<<<(H + 255) / 256, 256, 0, ST>>>(workspace, grid, H, (bf16*)dw, dw_accumulate);
+  reduce_partials_kernel<<<(H + 31) / 32, 256, 0, ST>>>(workspace, grid, H, (bf16*)dw, dw_accumulate);
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -894,7 +904,7 @@ extern "C" int rlaifv_colsum(const void* x, long long M, int N, void* db, int ac
   dim3 grid((N / 2 + 127) / 128, P);
   colsum_kernel<<<grid, 128, 0, ST>>>((const bf16*)x, M, N, workspace);
   B200_CHECK_CUDA(cudaGetLastError());
-  reduce_partials_kernel<<<(N + 255) / 256, 256, 0, ST>>>(workspace, P, N, (bf16*)db, accumulate);
+  reduce_partials_kernel<<<(N + 31) / 32, 256, 0, ST>>>(workspace, P, N, (bf16*)db, accumulate);
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

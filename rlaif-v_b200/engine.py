@@ -11,6 +11,7 @@ import os
 import torch
 import torch.distributed as dist
 
+from . import lib as _lib
 from . import ops
 from .model import LlavaDPOPolicy
 from .zero2 import Zero2AdamW, cosine_lr
@@ -59,6 +60,14 @@ class DPOStepEngine:
     def train_step(self, batch, optimizer_step=True):
         """batch: dict with concatenated_input_ids/labels [2B,L] (win rows first), images [B,3,S,S],
         ref_win_logp / ref_rej_logp [B] (or the *_avg_* variants when dpo_use_average), beta."""
+        pol = self.policy
+        _lib.bind_stream(torch.cuda.current_stream())
+        try:
+            return self._train_step(batch, optimizer_step)
+        finally:
+            _lib.bind_stream(None)
+
+    def _train_step(self, batch, optimizer_step):
         pol = self.policy
         ids = self._h2d(batch["concatenated_input_ids"])
         labels = self._h2d(batch["concatenated_labels"])

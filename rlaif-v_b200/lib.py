@@ -22,6 +22,7 @@ _SIGNATURES = {
     "rlaifv_gemm_bf16": [c_void_p, c_ll, c_int, c_void_p, c_ll, c_int, c_void_p, c_ll, c_int, c_int, c_int,
                          c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_void_p],
     "rlaifv_gemm_set_2cta": [c_int],
+    "rlaifv_gemm_set_tuning": [c_int, c_int],
     "rlaifv_rmsnorm_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p],
     "rlaifv_rmsnorm_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                            c_void_p, c_int, c_int, c_void_p],
@@ -124,7 +125,19 @@ def call(name, *args):
         raise B200Error("%s failed (rc=%d): %s" % (name, rc, last_error()))
 
 
+_bound_stream = None
+
+
+def bind_stream(stream=None):
+    """Pin the stream all following launches go to (saves the ~13 us torch.cuda.current_stream() lookup
+    per launch). Call with None to return to per-call lookup. The engine binds at the start of a step."""
+    global _bound_stream
+    _bound_stream = None if stream is None else c_void_p(stream.cuda_stream)
+
+
 def stream_ptr():
+    if _bound_stream is not None:
+        return _bound_stream
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 

@@ -34,7 +34,8 @@ class _PolicyLogps(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, anchor, policy, input_ids, labels, images, use_average):
-        out = policy.forward_logps(input_ids, labels, images, keep_stash=torch.is_grad_enabled())
+        # (inside Function.forward grad mode is off: the anchor carries the caller's intent)
+        out = policy.forward_logps(input_ids, labels, images, keep_stash=anchor.requires_grad)
         ctx.policy, ctx.use_average = policy, use_average
         return (out["avg_logp"] if use_average else out["logp"]).clone()
 

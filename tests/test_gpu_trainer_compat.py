@@ -1,0 +1,128 @@
+"""-m gpu tests of the drop-in trainer layer: compute_loss (autograd bridge) == fused engine path,
+frozen-reference log-prob pre-pass vs oracle, train()/checkpoint/resume on a synthetic dataset."""
+import os
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+from oracle import llava_dpo_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def dims():
+    from rlaifv_b200.model import LlavaDims
+    c = O.TINY
+    return LlavaDims(vocab_size=c.vocab_size, hidden_size=c.hidden_size, intermediate_size=c.intermediate_size,
+                     num_layers=c.num_layers, num_heads=c.num_heads, clip_hidden=c.clip_hidden,
+                     clip_intermediate=c.clip_intermediate, clip_layers=c.clip_layers, clip_heads=c.clip_heads,
+                     image_size=c.image_size, patch_size=c.patch_size)
+
+
+def instances(B, seed, ragged=True):
+    """(rej_dict, win_dict) tuples like DPODataset.__getitem__ yields."""
+    b = O.synthetic_pair_batch(O.TINY, B, 20, 16, seed=seed, image_pos=5, ragged=ragged)
+    ids, labs = b["concatenated_input_ids"], b["concatenated_labels"]
+    out = []
+    for i in range(B):
+        def one(row, kind):
+            n = int((ids[row] != 0).sum())
+            return {"input_ids": ids[row, :n].clone(), "labels": labs[row, :n].clone(), "image": b["images"][i],
+                    f"ref_{kind}_logp": -40.0 - i, f"ref_{kind}_avg_logp": -2.5, f"ref_{kind}_per_token_logp": [0.0] * (n + 600)}
+        out.append((one(B + i, "rej"), one(i, "win")))
+    return out
+
+
+class Tok:
+    pad_token_id = 0
+
+
+def make_args(tmp, **kw):
+    a = SimpleNamespace(learning_rate=1e-3, weight_decay=0.01, max_steps=4, warmup_ratio=0.0, dpo_use_average=False,
+                        dpo_token_weighted=False, task="DPO", output_dir=str(tmp), logging_steps=1, save_strategy="steps",
+                        save_steps=2, save_total_limit=5, per_device_train_batch_size=2, dataloader_num_workers=0,
+                        lr_scheduler_type="constant", bf16=True, deepspeed=None, seed=1)
+    for k, v in kw.items():
+        setattr(a, k, v)
+    return a
+
+
+def test_compute_loss_autograd_bridge_equals_engine(tmp_path):
+    from rlaifv_b200.collator import DataCollatorForDPODataset
+    from rlaifv_b200.llava_model import LlavaLlamaForCausalLM
+    from rlaifv_b200.trainers import LLaVA15DPOTrainer
+    params = O.make_params(O.TINY, seed=0, scale=0.4)
+    model = LlavaLlamaForCausalLM(dims(), "cuda", hf_state=params)
+    coll = DataCollatorForDPODataset(tokenizer=Tok(), beta=0.1, mod_token_weight=1.0)
+    trainer = LLaVA15DPOTrainer(model=model, tokenizer=Tok(), args=make_args(tmp_path), train_dataset=None,
+                                data_collator=coll)
+    batch = coll(instances(2, seed=3))
+    loss = trainer.compute_loss(model, dict(batch))
+    loss.backward()
+    g_bridge = model.policy.store.grad.clone()
+    m = trainer.engine.train_step(dict(batch), optimizer_step=False)
+    g_engine = model.policy.store.grad.clone()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(m[0])) <= 1e-5 * max(1.0, abs(float(loss)))
+    assert torch.equal(g_bridge, g_engine)        # same kernels, same order -> bit-identical gradients
+    logged = trainer.state["log_history"][-1]
+    assert set(k for k in logged if "/" in k) == {"rewards_train/chosen", "rewards_train/rejected",
+                                                  "rewards_train/accuracies", "rewards_train/margins",
+                                                  "logps_train/rejected", "logps_train/chosen",
+                                                  "logps_train/ref_rejected", "logps_train/ref_chosen"}
+
+
+def test_reference_logp_prepass_matches_oracle():
+    from rlaifv_b200.collator import preference_collator_fn
+    from rlaifv_b200.data import get_multimodal_sample_logps
+    from rlaifv_b200.llava_model import LlavaLlamaForCausalLM
+    params = O.make_params(O.TINY, seed=0, scale=0.4)
+    model = LlavaLlamaForCausalLM(dims(), "cuda", hf_state=params)
+    inst = instances(3, seed=8)
+    batches = [preference_collator_fn(inst[:2], 0), preference_collator_fn(inst[2:], 0)]
+    outs = get_multimodal_sample_logps(model, batches)
+    pb = {k: v.to(torch.bfloat16) for k, v in params.items()}
+    P = O.TINY.num_patches
+    for i, (rej, win) in enumerate(inst):
+        for kind, d, base in (("win", win, 0), ("rej", rej, 3)):
+            ids, labs = d["input_ids"][None], d["labels"][None]
+            o = O.policy_logps(pb, O.TINY, torch.cat([ids, ids]), torch.cat([labs, labs]), d["image"][None].to(torch.bfloat16))
+            per_tok = outs[base + 2][i]
+            assert len(per_tok) == ids.shape[1] - 1 + P - 1          # T_i - 1 entries, like the reference's batch-1 pass
+            ref_sum = float(o["logp"][0])
+            assert abs(outs[base][i] - ref_sum) <= 1e-3 * abs(ref_sum)
+            assert abs(outs[base + 1][i] - float(o["avg_logp"][0])) <= 1e-3 * abs(float(o["avg_logp"][0]))
+            mask = o["labels"][0, 1:] != -100
+            got = torch.tensor(per_tok)[mask]
+            want = o["per_token_logps"][0][mask]
+            assert float((got - want).abs().max()) <= 1e-2 * float(want.abs().max())
+
+
+def test_train_loop_checkpoint_resume(tmp_path):
+    from rlaifv_b200.collator import DataCollatorForDPODataset
+    from rlaifv_b200.llava_model import LlavaLlamaForCausalLM
+    from rlaifv_b200.trainers import LLaVA15DPOTrainer
+    params = O.make_params(O.TINY, seed=0, scale=0.4)
+    data = instances(8, seed=11)
+    coll = DataCollatorForDPODataset(tokenizer=Tok(), beta=0.1, mod_token_weight=1.0)
+
+    def run(max_steps, resume):
+        model = LlavaLlamaForCausalLM(dims(), "cuda", hf_state=params)
+        tr = LLaVA15DPOTrainer(model=model, tokenizer=Tok(), args=make_args(tmp_path, max_steps=max_steps),
+                               train_dataset=data, data_collator=coll)
+        tr.train(resume_from_checkpoint=resume)
+        torch.cuda.synchronize()
+        return model, tr
+
+    m1, t1 = run(2, False)                       # writes checkpoint-2
+    assert os.path.isdir(tmp_path / "checkpoint-2")
+    m2, t2 = run(4, True)                        # resumes at step 2, runs to 4
+    assert t2.state["global_step"] == 4
+    losses = [h["loss"] for h in t2.state["log_history"] if "loss" in h]
+    assert len(losses) == 4 and all(l == l for l in losses)      # steps 1,2 restored from the log + 3,4 new
+    w0 = params["model.layers.0.mlp.down_proj.weight"].to(torch.bfloat16)
+    w2 = m2.state_dict()["model.layers.0.mlp.down_proj.weight"].cpu()
+    assert float((w2.float() - w0.float()).abs().max()) > 0     # parameters moved
+    t2.save_state()
+    assert os.path.exists(tmp_path / "trainer_state.json")
