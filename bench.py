@@ -249,6 +249,7 @@ def main():
             if read_back:
                 loss_host.copy_(m, non_blocking=True)
                 torch.cuda.current_stream().synchronize()
+        engine.opt.wait_all()      # the last step's parameter all-gathers belong to the timed region
 
     try:
         step0 = engine.train_step(dev_batches[0], optimizer_step=False)   # known-answer check (no update)

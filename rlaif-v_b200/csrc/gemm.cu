@@ -28,11 +28,25 @@ struct GemmEpilogue {
   int accumulate;  // C = C + result (fp32 add of the old bf16 value)
   int group_m;     // raster: tiles are walked m-fastest inside groups of `group_m` row-blocks
   int debug;       // profiling only: bit0 skip global stores, bit1 skip the TMEM loads as well
+  int dynamic;     // 1: tiles drawn from the global counter; 0: static round-robin (tile = cta + i*grid)
 };
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 192;
+
+// Dynamic tile scheduler: CTAs pull tile indices from a global counter, so a CTA that becomes
+// resident late (an NCCL kernel of the overlapped ZeRO-2 reduce-scatter is holding its SM) simply
+// processes fewer tiles instead of stretching the whole GEMM. The last CTA to leave resets the
+// counter pair, so no memset is needed between launches; a pool of 64 pairs is cycled per launch.
+struct TileCounter {
+  unsigned int next;
+  unsigned int done;
+};
+__device__ TileCounter g_tile_counters[64];
+constexpr int GEMM_TQ = 4;   // depth of the in-CTA tile-index queue (producer -> MMA / epilogue warps)
+static TileCounter* g_counter_pool = nullptr;
+static unsigned int g_launch_seq = 0;
 
 template <int BN>
 struct GemmCfg {
@@ -41,7 +55,7 @@ struct GemmCfg {
   static constexpr uint32_t B_BYTES = BN * GEMM_BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t TMEM_COLS = 2 * BN;
-  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;  // + barriers + align
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 512 + 1024;  // + barriers/queue + align
 };
 
 __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int GROUP_M, int& m_blk, int& n_blk) {
@@ -109,7 +123,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int col0
 template <bool A_MN, bool B_MN, int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 int M, int N, int K, GemmEpilogue epi) {
+                 int M, int N, int K, GemmEpilogue epi, TileCounter* ctr) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -119,7 +133,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* tq_full = tempty + 2;
+  uint64_t* tq_empty = tq_full + GEMM_TQ;
+  volatile int* tile_q = reinterpret_cast<volatile int*>(tq_empty + GEMM_TQ);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(const_cast<int*>(tile_q) + GEMM_TQ);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -142,6 +159,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_init(&tfull[i], 1);
         mbar_init(&tempty[i], 4);
       }
+      for (int i = 0; i < GEMM_TQ; ++i) {
+        mbar_init(&tq_full[i], 1);
+        mbar_init(&tq_empty[i], 5);   // MMA thread + 4 epilogue warps
+      }
       fence_barrier_init();
     }
     __syncwarp();
@@ -157,7 +178,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int qs = 0;
+      uint32_t qph = 0;
+      for (int iter = 0;; ++iter) {
+        int t = epi.dynamic ? (int)atomicAdd(&ctr->next, 1u) : (int)(blockIdx.x + iter * gridDim.x);
+        if (t >= num_tiles) t = -1;
+        mbar_wait(&tq_empty[qs], qph ^ 1);
+        tile_q[qs] = t;
+        mbar_arrive(&tq_full[qs]);
+        if (++qs == GEMM_TQ) { qs = 0; qph ^= 1; }
+        if (t < 0) break;
         int m_blk, n_blk;
         tile_coords(t, num_m, num_n, epi.group_m, m_blk, n_blk);
         const int m0 = m_blk * GEMM_BM, n0 = n_blk * BN;
@@ -191,8 +221,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, A_MN, B_MN);
       int s = 0;
       uint32_t ph = 0;
-      int it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      int qs = 0;
+      uint32_t qph = 0;
+      for (int it = 0;; ++it) {
+        mbar_wait(&tq_full[qs], qph);
+        const int t = tile_q[qs];
+        mbar_arrive(&tq_empty[qs]);
+        if (++qs == GEMM_TQ) { qs = 0; qph ^= 1; }
+        if (t < 0) break;
         const int acc = it & 1;
         const uint32_t acc_ph = (it >> 1) & 1;
         mbar_wait(&tempty[acc], acc_ph ^ 1);
@@ -219,8 +255,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ------------------------------ epilogue ------------------------------
     const int quad = warp & 3;
     const int row_in_tile = quad * 32 + lane;
-    int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    int qs = 0;
+    uint32_t qph = 0;
+    for (int it = 0;; ++it) {
+      mbar_wait(&tq_full[qs], qph);
+      const int t = tile_q[qs];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tq_empty[qs]);
+      if (++qs == GEMM_TQ) { qs = 0; qph ^= 1; }
+      if (t < 0) break;
       int m_blk, n_blk;
       tile_coords(t, num_m, num_n, epi.group_m, m_blk, n_blk);
       const int acc = it & 1;
@@ -252,6 +295,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+  if (threadIdx.x == 0) {
+    const unsigned int d = atomicAdd(&ctr->done, 1u);
+    if (d == gridDim.x - 1) {   // every CTA has drawn its last index: re-arm for the next launch
+      ctr->next = 0;
+      ctr->done = 0;
+      __threadfence();
+    }
   }
 }
 
@@ -472,7 +523,9 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, in
   }
   const int num_tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, epi);
+  if (!g_counter_pool) B200_CHECK_CUDA(cudaGetSymbolAddress((void**)&g_counter_pool, g_tile_counters));
+  TileCounter* ctr = g_counter_pool + (g_launch_seq++ & 63);
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, epi, ctr);
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -549,7 +602,8 @@ extern "C" int rlaifv_gemm_bf16(const void* A, long long lda, int a_mn_major, co
   epi.act = act;
   epi.accumulate = accumulate;
   epi.group_m = g_group_m;
-  epi.debug = g_debug;
+  epi.debug = g_debug & 3;
+  epi.dynamic = (g_debug & 4) ? 0 : 1;
   cudaStream_t st = (cudaStream_t)stream;
   if (bn == 512) {
     if (!a_mn_major && !b_mn_major) return launch_gemm2<false, false>(tmA, tmB, M, N, K, epi, st);

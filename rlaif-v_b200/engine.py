@@ -41,14 +41,25 @@ class DPOStepEngine:
         # engine itself takes get_beta_and_logps' inputs as they are.
         self.hf_deepspeed_input_cast = hf_deepspeed_input_cast
         self.global_step = 0
+        if world > 1:
+            # the CTA-pair GEMM still uses a static tile assignment; next to overlapped NCCL kernels only the
+            # dynamically scheduled 1-CTA kernel degrades gracefully
+            _lib.load().rlaifv_gemm_set_2cta(0)
         self._metrics = torch.zeros(9, dtype=_F32, device=policy.device)
         self._last_micro = False
         # ZeRO-2 overlap: reduce a layer's bucket as soon as its backward finished (last micro-batch only)
         policy.on_layer_grads_ready = self._layer_ready
+        policy.on_head_grads_ready = self._head_ready
+        self._bucket_index = {b.name: i for i, b in enumerate(policy.store.buckets)}
+        policy.param_ready = lambda name: self.opt.wait_bucket(self._bucket_index[name])
 
     def _layer_ready(self, layer):
         if self._last_micro:
             self.opt.reduce_bucket(1 + layer)      # bucket order: embed, layer0.., head, projector
+
+    def _head_ready(self):
+        if self._last_micro and self.world > 1:
+            self.opt.reduce_bucket(len(self.opt.slices) - 2)      # head bucket: final right after its backward
 
     def _h2d(self, t, dtype=None):
         if not t.is_cuda:
@@ -102,7 +113,6 @@ class DPOStepEngine:
         pol.finalize_embed_grad()
         if self.world > 1:
             self.opt.reduce_bucket(0)                         # embed
-            self.opt.reduce_bucket(len(self.opt.slices) - 2)  # head
             self.opt.reduce_bucket(len(self.opt.slices) - 1)  # projector
         if optimizer_step:
             lr = self.base_lr if self.constant_lr else cosine_lr(self.global_step, self.total_steps, self.base_lr,

@@ -53,6 +53,9 @@ class LlavaLlamaForCausalLM:
         return self.policy.clip
 
     def state_dict(self):
+        if self.policy.param_ready is not None:          # pending ZeRO-2 parameter all-gathers
+            for b in self.policy.store.buckets:
+                self.policy.param_ready(b.name)
         return {k: v for k, v in self.policy.store.hf_views().items()}
 
     def load_state_dict(self, state, strict=True):
@@ -66,6 +69,7 @@ class LlavaLlamaForCausalLM:
         """[n,3,S,S] -> projected image features [n, P, hidden] (bf16)."""
         pol, P = self.policy, self.policy.store.p
         feats = pol.encode_images(images)
+        pol._need("projector")
         pre = ops.gemm(feats, P["proj.w0"], bias=P["proj.b0"])
         post = ops.gelu_fwd(pre)
         out = ops.gemm(post, P["proj.w2"], bias=P["proj.b2"])

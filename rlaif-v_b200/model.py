@@ -353,6 +353,7 @@ class LlavaDPOPolicy:
         scale = hd ** -0.5
         keep_stash = st is not None
         for i in range(d.num_layers):
+            self._need("layer%d" % i)
             if keep_stash:
                 ls = {"x": x}
                 qkv = torch.empty((M, 3 * H), dtype=_BF, device=dev)
@@ -397,6 +398,7 @@ class LlavaDPOPolicy:
         nseq, T, H = inputs_embeds.shape
         x = inputs_embeds.to(device=self.device, dtype=_BF).reshape(nseq * T, H).contiguous()
         x = self._run_layers(x, nseq, T, None)
+        self._need("head")
         hn = ops.rmsnorm_fwd(x, self.store.p["norm"], d.rms_eps, out=self.buf("hn", (nseq * T, H)))
         logits = ops.gemm(hn, self.store.p["lm_head"])
         return logits.view(nseq, T, d.vocab_size)
@@ -416,6 +418,7 @@ class LlavaDPOPolicy:
         st = {"layers": []} if keep_stash else None
 
         feats = self.encode_images(images)                                   # [b*Pn, C]
+        self._need("projector")
         pre = ops.gemm(feats, P["proj.w0"], self.buf("proj_pre", (feats.shape[0], H)), bias=P["proj.b0"])
         post = ops.gelu_fwd(pre, self.buf("proj_post", pre.shape))
         proj = ops.gemm(post, P["proj.w2"], self.buf("proj_out", pre.shape), bias=P["proj.b2"])
@@ -423,6 +426,7 @@ class LlavaDPOPolicy:
         n_slots = nseq
         img_index = (torch.arange(n_slots, dtype=torch.int32, device=dev) % b).contiguous() if nseq == 2 * b \
             else torch.arange(n_slots, dtype=torch.int32, device=dev)
+        self._need("embed")
         x, new_labels, src, T = self.splice(input_ids, labels, proj, b, img_index,
                                             T_hint=(T_hint, n_slots) if T_hint is not None else None)
         M = nseq * T
@@ -430,6 +434,7 @@ class LlavaDPOPolicy:
             st.update(feats=feats, proj_pre=pre, proj_post=post, src=src, input_ids=input_ids, labels=new_labels,
                       T=T, nseq=nseq, b=b)
         x = self._run_layers(x, nseq, T, st)
+        self._need("head")
         rstd_f = torch.empty(M, dtype=_F32, device=dev) if keep_stash else None
         hn = ops.rmsnorm_fwd(x, P["norm"], d.rms_eps, out=self.buf("hn", (M, H)), rstd=rstd_f)
         logits = ops.gemm(hn, P["lm_head"], self.buf("logits", (M, V)))
@@ -461,6 +466,8 @@ class LlavaDPOPolicy:
         dhn = ops.gemm(dlogits, P["lm_head"], self.buf("dn", (M, H)), b_mn=True)                # dhn = dlogits W
         dx = ops.rmsnorm_bwd(dhn, st["x_final"], P["norm"], st["rstd_f"], self.buf("dx_a", (M, H)), G["norm"],
                              dw_accumulate=acc)
+        if self.on_head_grads_ready is not None:
+            self.on_head_grads_ready()
         for i in reversed(range(d.num_layers)):
             ls = st["layers"][i]
             # ---- MLP ----
@@ -513,6 +520,12 @@ class LlavaDPOPolicy:
         self._stash = None
 
     on_layer_grads_ready = None
+    on_head_grads_ready = None
+    param_ready = None          # callable(bucket_name): wait for that bucket's parameter all-gather (ZeRO-2)
+
+    def _need(self, bucket):
+        if self.param_ready is not None:
+            self.param_ready(bucket)
 
     def finalize_embed_grad(self):
         """fp32 embedding-row accumulator -> bf16 flat gradient (once per optimizer step)."""

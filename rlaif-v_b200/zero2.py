@@ -52,7 +52,7 @@ class Zero2AdamW:
         for b, s0, s1, o in self.slices:
             self.master[o:o + (s1 - s0)].copy_(store.flat[s0:s1])
         self.comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
-        self._pending = []
+        self._gathered = {}
 
     # ---- gradient reduction (called from the backward as buckets complete) ----
     def reduce_bucket(self, bucket_index):
@@ -72,15 +72,21 @@ class Zero2AdamW:
 
     # ---- optimizer step ----
     def step(self, lr=None):
+        """Fused AdamW on the owned slices, then (world > 1) the in-place parameter all-gather.
+        Buckets are processed in the order the next forward needs them (projector, embed, layer 0..,
+        head); each bucket's all-gather runs on the comm stream as soon as its AdamW kernels are done
+        and is awaited lazily by `wait_bucket` — so the gathers overlap the remaining AdamW work and the
+        beginning of the next step (frozen CLIP tower first) instead of sitting exposed at the step end."""
         lr = self.lr if lr is None else lr
         self.step_count += 1
         cur = torch.cuda.current_stream()
         if self.world > 1:
-            cur.wait_stream(self.comm_stream)
+            cur.wait_stream(self.comm_stream)        # all gradient reduce-scatters have landed
         b1, b2 = self.betas
-        for b, s0, s1, o in self.slices:
+        order = [len(self.slices) - 1, 0] + list(range(1, len(self.slices) - 1))
+        for bi in order:
+            b, s0, s1, o = self.slices[bi]
             dec_end = min(s1, b.start + b.decay_size)
-            # decay part
             if dec_end > s0:
                 n = dec_end - s0
                 ops.adamw_step(self.master[o:o + n], self.exp_avg[o:o + n], self.exp_avg_sq[o:o + n],
@@ -93,15 +99,26 @@ class Zero2AdamW:
                 ops.adamw_step(self.master[oo:oo + n], self.exp_avg[oo:oo + n], self.exp_avg_sq[oo:oo + n],
                                self.store.grad[nd0:s1], self.store.flat[nd0:s1], lr, b1, b2, self.eps, 0.0,
                                self.step_count)
-        if self.world > 1:
-            ev = torch.cuda.Event()
-            ev.record(cur)
-            with torch.cuda.stream(self.comm_stream):
-                self.comm_stream.wait_event(ev)
-                for b, s0, s1, _ in self.slices:
+            if self.world > 1:
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                with torch.cuda.stream(self.comm_stream):
+                    self.comm_stream.wait_event(ev)
                     dist.all_gather_into_tensor(self.store.flat[b.start:b.start + b.size], self.store.flat[s0:s1],
                                                 group=self.group)
-            cur.wait_stream(self.comm_stream)
+                    done = torch.cuda.Event()
+                    done.record(self.comm_stream)
+                self._gathered[bi] = done
+
+    def wait_bucket(self, bucket_index):
+        """Make the current stream wait for bucket's parameter all-gather of the last step (no-op if none)."""
+        ev = self._gathered.pop(bucket_index, None)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+
+    def wait_all(self):
+        for bi in list(self._gathered):
+            self.wait_bucket(bi)
 
     def state_dict(self):
         return {"step": self.step_count, "master": self.master, "exp_avg": self.exp_avg,
