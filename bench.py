@@ -192,6 +192,7 @@ def main():
     ap.add_argument("--layers", type=int, default=32, help="debug only; anything but 32 is not the benchmark")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stash-extra", action="store_true")
+    ap.add_argument("--lora", action="store_true", help="BASELINE config (e): LoRA-DPO r=64 (not the headline line)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -214,7 +215,9 @@ def main():
     B = PAIRS_PER_GPU
     micro = args.micro_pairs or B
     policy = LlavaDPOPolicy(dims, torch.device("cuda", local_rank), seed=0)
-    engine = DPOStepEngine(policy, lr=5e-7, weight_decay=0.01, total_steps=2672, micro_pairs=micro,
+    if args.lora:
+        policy.enable_lora(r=64, alpha=16)
+    engine = DPOStepEngine(policy, lr=1e-5 if args.lora else 5e-7, weight_decay=0.01, total_steps=2672, micro_pairs=micro,
                            rank=rank, world=world)
     # HBM plan: with the optimizer state sharded over >= 2 GPUs there is room to stash the normalised inputs
     # and the SwiGLU product (no recompute in the backward); one GPU holds the unsharded 81 GB state.
@@ -327,12 +330,17 @@ def main():
     hb = host_batches[0]
     h2d = sum(v.numel() * v.element_size() for v in hb.values() if torch.is_tensor(v))
     f_pair = flops_per_pair(T)
+    if args.lora:   # base wgrad skipped, adapters added
+        n_dec = 32 * (4 * 4096 ** 2 + 3 * 4096 * 11008)
+        attn = 32 * 4 * T * T * 4096 * 0.5
+        f_pair = 2 * (2 * T * (4 * (n_dec + 4096 * 32000) + 6 * 159907840) + 3 * attn) + \
+            (flops_per_pair(T) - 6 * (2 * (n_dec + 4096 * 32000) * T + attn))
     line = {
         "metric": "preference-pairs/sec LLaVA-1.5-7B DPO step", "value": value, "unit": "pairs/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "LLaVA-1.5-7B DPO bf16, %d pairs/GPU, 336px, 512-tok responses (T=%d), ZeRO-2 AdamW"
-                               % (B, T),
+        "config": {"workload": ("LLaVA-1.5-7B %sDPO bf16, %d pairs/GPU, 336px, 512-tok responses (T=%d), ZeRO-2 AdamW"
+                                % ("LoRA(r=64)-" if args.lora else "", B, T)),
                    "layers": args.layers, "pairs_per_gpu": B, "micro_pairs": micro, "parallelism": "dp%d" % world,
                    "l2": "per-step working set (>100 GB of weights/activations) is far larger than the 126 MB L2",
                    "step0_loss": loss0, "step0_loss_expected": math.log(2.0)},

@@ -36,6 +36,14 @@ int rlaifv_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B
                      const void* residual, long long ldr, int act, int accumulate, int tile_n,
                      void* stream);
 
+/* As rlaifv_gemm_bf16 with the product scaled first: bf16(bf16(A*B)*alpha) then bias/act/residual/accumulate.
+ * Used for the LoRA adapters (peft 0.10.0 `result + lora_B(lora_A(x)) * scaling`;
+ * muffin/train/train_llava15_lora.py:304-318, alpha/r = 16/64). */
+int rlaifv_gemm_bf16_scaled(const void* A, long long lda, int a_mn_major, const void* B, long long ldb,
+                            int b_mn_major, void* C, long long ldc, int M, int N, int K, const void* bias,
+                            const void* residual, long long ldr, int act, int accumulate, int tile_n, float alpha,
+                            void* stream);
+
 /* tile_n = 512 selects the 2-CTA kernel (cta_group::2, 256x256 tile per CTA pair). rlaifv_gemm_set_2cta(1)
  * lets tile_n = 0 (auto) pick it for large problems. */
 int rlaifv_gemm_set_2cta(int enable);

@@ -291,7 +291,40 @@ def rotate_half(x):
     return torch.cat((-x2, x1), dim=-1)
 
 
-def llama_logits(p, inputs_embeds, cfg: OracleConfig):
+LORA_TARGETS = ("self_attn.q_proj", "self_attn.k_proj", "self_attn.v_proj", "self_attn.o_proj",
+                "mlp.gate_proj", "mlp.up_proj", "mlp.down_proj")   # find_all_linear_names, train_llava15_lora.py:121-134
+
+
+def lora_linear(p, name, x, lora_scaling):
+    """y = W x (+ (alpha/r) * B(A(x))) — peft 0.10.0 lora.Linear.forward with dropout p=0
+    (muffin/train/train_llava15_lora.py:304-318: r=64, alpha=16; adapters live next to the base
+    weight as `<name>.lora_A.weight` [r,in] / `<name>.lora_B.weight` [out,r]).
+    PARITY NOTE: peft is not installed in the build container, so this branch is a restatement of the
+    published formula and is NOT pinned against a run of the reference."""
+    y = F.linear(x, p[name + ".weight"])
+    a = p.get(name + ".lora_A.weight")
+    if a is not None:
+        y = y + F.linear(F.linear(x, a), p[name + ".lora_B.weight"]) * lora_scaling
+    return y
+
+
+def make_lora_params(cfg: OracleConfig, r=8, seed=3, dtype=torch.float32, b_std=0.02):
+    """Adapters for every LORA_TARGETS linear. peft initialises B = 0 (adapter is a no-op at step 0);
+    tests use a non-zero B so that the adapter path is actually exercised."""
+    g = torch.Generator().manual_seed(seed)
+    H, F_ = cfg.hidden_size, cfg.intermediate_size
+    dims = {"self_attn.q_proj": (H, H), "self_attn.k_proj": (H, H), "self_attn.v_proj": (H, H),
+            "self_attn.o_proj": (H, H), "mlp.gate_proj": (F_, H), "mlp.up_proj": (F_, H), "mlp.down_proj": (H, F_)}
+    out = {}
+    for i in range(cfg.num_layers):
+        for t in LORA_TARGETS:
+            o, inn = dims[t]
+            out[f"model.layers.{i}.{t}.lora_A.weight"] = (torch.randn(r, inn, generator=g) * 0.05).to(dtype)
+            out[f"model.layers.{i}.{t}.lora_B.weight"] = (torch.randn(o, r, generator=g) * b_std).to(dtype)
+    return out
+
+
+def llama_logits(p, inputs_embeds, cfg: OracleConfig, lora_scaling=0.25):
     """inputs_embeds [nseq,T,H] -> logits [nseq,T,V] in fp32 (4.35.0 `logits.float()`).
 
     HF: llama/modeling_llama.py:303-333 (layer), :251-290 + :199-222 (attention: eager, causal mask
@@ -306,20 +339,20 @@ def llama_logits(p, inputs_embeds, cfg: OracleConfig):
         pre = f"model.layers.{i}."
         r = x
         h = rms_norm(x, p[pre + "input_layernorm.weight"], cfg.rms_eps)
-        q = F.linear(h, p[pre + "self_attn.q_proj.weight"]).view(nseq, T, nh, hd).transpose(1, 2)
-        k = F.linear(h, p[pre + "self_attn.k_proj.weight"]).view(nseq, T, nh, hd).transpose(1, 2)
-        v = F.linear(h, p[pre + "self_attn.v_proj.weight"]).view(nseq, T, nh, hd).transpose(1, 2)
+        q = lora_linear(p, pre + "self_attn.q_proj", h, lora_scaling).view(nseq, T, nh, hd).transpose(1, 2)
+        k = lora_linear(p, pre + "self_attn.k_proj", h, lora_scaling).view(nseq, T, nh, hd).transpose(1, 2)
+        v = lora_linear(p, pre + "self_attn.v_proj", h, lora_scaling).view(nseq, T, nh, hd).transpose(1, 2)
         q = q * cos + rotate_half(q) * sin
         k = k * cos + rotate_half(k) * sin
         w = torch.matmul(q, k.transpose(2, 3)) * (hd ** -0.5) + causal
         w = F.softmax(w, dim=-1, dtype=torch.float32).to(q.dtype)
         a = torch.matmul(w, v).transpose(1, 2).reshape(nseq, T, H)
-        x = r + F.linear(a, p[pre + "self_attn.o_proj.weight"])
+        x = r + lora_linear(p, pre + "self_attn.o_proj", a, lora_scaling)
         r = x
         h = rms_norm(x, p[pre + "post_attention_layernorm.weight"], cfg.rms_eps)
-        g = F.linear(h, p[pre + "mlp.gate_proj.weight"])
-        u = F.linear(h, p[pre + "mlp.up_proj.weight"])
-        x = r + F.linear(F.silu(g) * u, p[pre + "mlp.down_proj.weight"])
+        g = lora_linear(p, pre + "mlp.gate_proj", h, lora_scaling)
+        u = lora_linear(p, pre + "mlp.up_proj", h, lora_scaling)
+        x = r + lora_linear(p, pre + "mlp.down_proj", F.silu(g) * u, lora_scaling)
     x = rms_norm(x, p["model.norm.weight"], cfg.rms_eps)
     return F.linear(x, p["lm_head.weight"]).float()
 

@@ -29,6 +29,7 @@ struct GemmEpilogue {
   int group_m;     // raster: tiles are walked m-fastest inside groups of `group_m` row-blocks
   int debug;       // profiling only: bit0 skip global stores, bit1 skip the TMEM loads as well
   int dynamic;     // 1: tiles drawn from the global counter; 0: static round-robin (tile = cta + i*grid)
+  float alpha;     // != 1: result = bf16(bf16(acc) * alpha) first (LoRA scaling, peft: lora_B(...) * scaling)
 };
 
 constexpr int GEMM_BM = 128;
@@ -85,6 +86,10 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int col0
       float v[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+      if (epi.alpha != 1.0f) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = bf16_round(bf16_round(v[j]) * epi.alpha);
+      }
       if (epi.bias) {
         uint4 b4 = __ldg(reinterpret_cast<const uint4*>(epi.bias + col));
         float2 b0 = unpack_bf16(b4.x), b1 = unpack_bf16(b4.y), b2 = unpack_bf16(b4.z), b3 = unpack_bf16(b4.w);
@@ -566,10 +571,9 @@ extern "C" int rlaifv_gemm_set_2cta(int enable) {
 }
 
 // C ABI — see include/rlaifv_b200.h for the contract.
-extern "C" int rlaifv_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B,
-                                long long ldb, int b_mn_major, void* C, long long ldc, int M, int N,
-                                int K, const void* bias, const void* residual, long long ldr,
-                                int act, int accumulate, int tile_n, void* stream) {
+static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major,
+                     void* C, long long ldc, int M, int N, int K, const void* bias, const void* residual,
+                     long long ldr, int act, int accumulate, int tile_n, float alpha, void* stream) {
   B200_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   B200_REQUIRE(N % 8 == 0 && ldc % 8 == 0, "gemm: N (%d) and ldc (%lld) must be multiples of 8", N,
                ldc);
@@ -601,6 +605,7 @@ extern "C" int rlaifv_gemm_bf16(const void* A, long long lda, int a_mn_major, co
   epi.ldr = ldr;
   epi.act = act;
   epi.accumulate = accumulate;
+  epi.alpha = alpha;
   epi.group_m = g_group_m;
   epi.debug = g_debug & 3;
   epi.dynamic = (g_debug & 4) ? 0 : 1;
@@ -618,4 +623,20 @@ extern "C" int rlaifv_gemm_bf16(const void* A, long long lda, int a_mn_major, co
                      : launch_gemm<false, true, 128>(tmA, tmB, M, N, K, epi, st);
   return bn == 256 ? launch_gemm<true, true, 256>(tmA, tmB, M, N, K, epi, st)
                    : launch_gemm<true, true, 128>(tmA, tmB, M, N, K, epi, st);
+}
+
+extern "C" int rlaifv_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb,
+                                int b_mn_major, void* C, long long ldc, int M, int N, int K, const void* bias,
+                                const void* residual, long long ldr, int act, int accumulate, int tile_n,
+                                void* stream) {
+  return gemm_impl(A, lda, a_mn_major, B, ldb, b_mn_major, C, ldc, M, N, K, bias, residual, ldr, act, accumulate,
+                   tile_n, 1.0f, stream);
+}
+// Same with the product scaled first: C (+)= bf16(bf16(A*B) * alpha) ... (LoRA: alpha = lora_alpha / r).
+extern "C" int rlaifv_gemm_bf16_scaled(const void* A, long long lda, int a_mn_major, const void* B, long long ldb,
+                                       int b_mn_major, void* C, long long ldc, int M, int N, int K,
+                                       const void* bias, const void* residual, long long ldr, int act,
+                                       int accumulate, int tile_n, float alpha, void* stream) {
+  return gemm_impl(A, lda, a_mn_major, B, ldb, b_mn_major, C, ldc, M, N, K, bias, residual, ldr, act, accumulate,
+                   tile_n, alpha, stream);
 }

@@ -29,8 +29,8 @@ class DPOStepEngine:
                  rank=0, world=1, group=None, constant_lr=False, hf_deepspeed_input_cast=False):
         self.policy = policy
         self.rank, self.world, self.group = rank, world, group
-        self.opt = Zero2AdamW(policy.store, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
-                              rank=rank, world=world, group=group)
+        self.opt = Zero2AdamW(policy.trainable_buckets(), lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
+                              rank=rank, world=world, group=group, gather_order=policy.param_need_order())
         self.base_lr, self.total_steps, self.warmup_ratio = lr, total_steps, warmup_ratio
         self.constant_lr = constant_lr
         self.dpo_use_average = dpo_use_average
@@ -50,16 +50,15 @@ class DPOStepEngine:
         # ZeRO-2 overlap: reduce a layer's bucket as soon as its backward finished (last micro-batch only)
         policy.on_layer_grads_ready = self._layer_ready
         policy.on_head_grads_ready = self._head_ready
-        self._bucket_index = {b.name: i for i, b in enumerate(policy.store.buckets)}
-        policy.param_ready = lambda name: self.opt.wait_bucket(self._bucket_index[name])
+        policy.param_ready = self.opt.wait_bucket
 
     def _layer_ready(self, layer):
         if self._last_micro:
-            self.opt.reduce_bucket(1 + layer)      # bucket order: embed, layer0.., head, projector
+            self.opt.reduce_bucket(self.policy.layer_bucket_name(layer))
 
     def _head_ready(self):
         if self._last_micro and self.world > 1:
-            self.opt.reduce_bucket(len(self.opt.slices) - 2)      # head bucket: final right after its backward
+            self.opt.reduce_bucket("head")      # head bucket: final right after its backward
 
     def _h2d(self, t, dtype=None):
         if not t.is_cuda:
@@ -112,8 +111,8 @@ class DPOStepEngine:
                                accumulate=mi > 0)
         pol.finalize_embed_grad()
         if self.world > 1:
-            self.opt.reduce_bucket(0)                         # embed
-            self.opt.reduce_bucket(len(self.opt.slices) - 1)  # projector
+            self.opt.reduce_bucket("embed")
+            self.opt.reduce_bucket("projector")
         if optimizer_step:
             lr = self.base_lr if self.constant_lr else cosine_lr(self.global_step, self.total_steps, self.base_lr,
                                                                  self.warmup_ratio)

@@ -21,6 +21,8 @@ c_float = ctypes.c_float
 _SIGNATURES = {
     "rlaifv_gemm_bf16": [c_void_p, c_ll, c_int, c_void_p, c_ll, c_int, c_void_p, c_ll, c_int, c_int, c_int,
                          c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_void_p],
+    "rlaifv_gemm_bf16_scaled": [c_void_p, c_ll, c_int, c_void_p, c_ll, c_int, c_void_p, c_ll, c_int, c_int, c_int,
+                                c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_float, c_void_p],
     "rlaifv_gemm_set_2cta": [c_int],
     "rlaifv_gemm_set_tuning": [c_int, c_int],
     "rlaifv_rmsnorm_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p],

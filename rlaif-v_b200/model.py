@@ -175,6 +175,72 @@ class ParamStore:
             v.copy_(state[k].to(device=v.device, dtype=_BF))
 
 
+
+class LoraStore:
+    """Flat bf16 storage of the LoRA adapters (config e; muffin/train/train_llava15_lora.py:112-134, 304-318:
+    r=64, alpha=16 on q,k,v,o,gate,up,down of every decoder layer; lm_head / projector / vision excluded).
+    One bucket per layer: A_qkv [3r,H] (the three lora_A stacked — q,k,v share their input), B_q/B_k/B_v [H,r],
+    A_o [r,H], B_o [H,r], A_gu [2r,H], B_g/B_u [F,r], A_d [r,F], B_d [H,r]. Adapters get weight decay like any
+    other matrix (HF decay groups exclude only norms and biases)."""
+
+    def __init__(self, dims: LlavaDims, device, r=64, alpha=16, seed=7, init_b_zero=True):
+        self.dims, self.r, self.scaling = dims, r, alpha / r
+        H, F = dims.hidden_size, dims.intermediate_size
+        self.buckets = []
+        off = 0
+        shapes = [("A_qkv", (3 * r, H)), ("B_q", (H, r)), ("B_k", (H, r)), ("B_v", (H, r)), ("A_o", (r, H)),
+                  ("B_o", (H, r)), ("A_gu", (2 * r, H)), ("B_g", (F, r)), ("B_u", (F, r)), ("A_d", (r, F)),
+                  ("B_d", (H, r))]
+        for i in range(dims.num_layers):
+            b = Bucket(name=f"lora{i}", start=off, size=0, decay_size=0)
+            o = off
+            for nm, shape in shapes:
+                b.segments.append(Segment(f"l{i}.{nm}", shape, o, True))
+                o += math.prod(shape)
+            b.decay_size = o - off
+            b.size = _round_up(o - off, ParamStore.PAD)
+            off += b.size
+            self.buckets.append(b)
+        self.numel = off
+        self.flat = torch.zeros(off, dtype=_BF, device=device)
+        self.grad = torch.zeros(off, dtype=_BF, device=device)
+        self.p, self.g = {}, {}
+        for b in self.buckets:
+            for sg in b.segments:
+                n = math.prod(sg.shape)
+                self.p[sg.name] = self.flat[sg.offset:sg.offset + n].view(*sg.shape)
+                self.g[sg.name] = self.grad[sg.offset:sg.offset + n].view(*sg.shape)
+        # peft init: lora_A kaiming_uniform(a=sqrt(5)) = U(-1/sqrt(in), 1/sqrt(in)), lora_B = 0
+        g = torch.Generator(device=device).manual_seed(seed)
+        for name, v in self.p.items():
+            if ".A_" in name:
+                bound = 1.0 / math.sqrt(v.shape[1])
+                v.copy_((torch.rand(v.shape, generator=g, device=device) * 2 - 1) * bound)
+            elif not init_b_zero:
+                v.copy_(torch.randn(v.shape, generator=g, device=device) * 0.02)
+
+    _PEFT = {"q_proj": ("A_qkv", 0, "B_q"), "k_proj": ("A_qkv", 1, "B_k"), "v_proj": ("A_qkv", 2, "B_v"),
+             "o_proj": ("A_o", 0, "B_o"), "gate_proj": ("A_gu", 0, "B_g"), "up_proj": ("A_gu", 1, "B_u"),
+             "down_proj": ("A_d", 0, "B_d")}
+
+    def hf_views(self, grads=False):
+        """`model.layers.{i}.{self_attn|mlp}.{x}_proj.lora_{A,B}.weight` -> views (peft adapter naming minus the
+        `base_model.model.` prefix and the adapter name)."""
+        src = self.g if grads else self.p
+        r, out = self.r, {}
+        for i in range(self.dims.num_layers):
+            for proj, (a_name, idx, b_name) in self._PEFT.items():
+                mod = "self_attn" if proj in ("q_proj", "k_proj", "v_proj", "o_proj") else "mlp"
+                pre = f"model.layers.{i}.{mod}.{proj}."
+                out[pre + "lora_A.weight"] = src[f"l{i}.{a_name}"][idx * r:(idx + 1) * r]
+                out[pre + "lora_B.weight"] = src[f"l{i}.{b_name}"]
+        return out
+
+    def load_hf(self, state):
+        for k, v in self.hf_views().items():
+            v.copy_(state[k].to(device=v.device, dtype=_BF))
+
+
 class ClipWeights:
     """Frozen CLIP-ViT weights in kernel-friendly form (fused qkv, padded patch-embedding matrix)."""
 
@@ -256,6 +322,74 @@ class LlavaDPOPolicy:
         self.stash_extra = False
         self.embed_grad_f32 = None   # fp32 scatter target for embedding rows (allocated lazily)
         self._stash = None
+        self.lora = None             # LoraStore: base weights frozen, adapters + mm_projector trainable
+
+    def enable_lora(self, r=64, alpha=16, seed=7, init_b_zero=True):
+        self.lora = LoraStore(self.dims, self.device, r=r, alpha=alpha, seed=seed, init_b_zero=init_b_zero)
+        return self.lora
+
+    # ---- what the optimizer trains / in which order the forward needs it ----
+    def trainable_buckets(self):
+        from .zero2 import store_buckets
+        if self.lora is None:
+            return store_buckets(self.store)
+        return store_buckets(self.lora) + store_buckets(self.store, names={"projector"})
+
+    def param_need_order(self):
+        d = self.dims
+        if self.lora is None:
+            return ["projector", "embed"] + [f"layer{i}" for i in range(d.num_layers)] + ["head"]
+        return ["projector"] + [f"lora{i}" for i in range(d.num_layers)]
+
+    def layer_bucket_name(self, i):
+        return f"layer{i}" if self.lora is None else f"lora{i}"
+
+    # ---- one linear group = base GEMM (+ LoRA adapters sharing the input) ----
+    _GROUPS = {"qkv": ("A_qkv", ("B_q", "B_k", "B_v")), "o": ("A_o", ("B_o",)), "gu": ("A_gu", ("B_g", "B_u")),
+               "down": ("A_d", ("B_d",))}
+
+    def _lin_fwd(self, i, group, x, out, residual=None, ls=None):
+        """out = x @ W^T (+ residual) (+ scaling * B(A(x)) per sub-linear when LoRA is on)."""
+        W = self.store.p[f"l{i}.{group}"]
+        if self.lora is None:
+            return ops.gemm(x, W, out, residual=residual)
+        L = self.lora
+        a_name, b_names = self._GROUPS[group]
+        A = L.p[f"l{i}.{a_name}"]
+        r, M = L.r, x.shape[0]
+        ops.gemm(x, W, out)
+        t = torch.empty((M, A.shape[0]), dtype=_BF, device=self.device) if ls is not None else \
+            self.buf("lora_t_" + group, (M, A.shape[0]))
+        ops.gemm(x, A, t)
+        n_out = out.shape[1] // len(b_names)
+        for j, bn in enumerate(b_names):
+            ops.gemm(t[:, j * r:(j + 1) * r], L.p[f"l{i}.{bn}"], out[:, j * n_out:(j + 1) * n_out],
+                     accumulate=True, alpha=L.scaling, residual=residual)
+        if ls is not None:
+            ls["t_" + group] = t
+        return out
+
+    def _lin_bwd(self, i, group, dy, x, dx_out, ls, acc):
+        """dx = dy @ W (+ adapter path); weight gradients: base (full FT) or adapters (LoRA)."""
+        W = self.store.p[f"l{i}.{group}"]
+        if self.lora is None:
+            ops.gemm(dy, x, self.store.g[f"l{i}.{group}"], a_mn=True, b_mn=True, accumulate=acc)
+            return ops.gemm(dy, W, dx_out, b_mn=True)
+        L = self.lora
+        a_name, b_names = self._GROUPS[group]
+        A = L.p[f"l{i}.{a_name}"]
+        r, M = L.r, x.shape[0]
+        t = ls["t_" + group]
+        dt = self.buf("lora_dt_" + group, (M, A.shape[0]))
+        n_out = dy.shape[1] // len(b_names)
+        for j, bn in enumerate(b_names):
+            dy_j = dy[:, j * n_out:(j + 1) * n_out]
+            ops.gemm(dy_j, L.p[f"l{i}.{bn}"], dt[:, j * r:(j + 1) * r], b_mn=True, alpha=L.scaling)        # dt_j = s dy_j B_j
+            ops.gemm(dy_j, t[:, j * r:(j + 1) * r], L.g[f"l{i}.{bn}"], a_mn=True, b_mn=True, alpha=L.scaling,
+                     accumulate=acc)                                                                         # dB_j
+        ops.gemm(dt, x, L.g[f"l{i}.{a_name}"], a_mn=True, b_mn=True, accumulate=acc)                        # dA
+        ops.gemm(dy, W, dx_out, b_mn=True)
+        return ops.gemm(dt, A, dx_out, b_mn=True, accumulate=True)
 
     # ------------------------------------------------------------------ init / buffers
     def _random_init(self, seed, std):
@@ -354,6 +488,7 @@ class LlavaDPOPolicy:
         keep_stash = st is not None
         for i in range(d.num_layers):
             self._need("layer%d" % i)
+            ls = None
             if keep_stash:
                 ls = {"x": x}
                 qkv = torch.empty((M, 3 * H), dtype=_BF, device=dev)
@@ -374,16 +509,16 @@ class LlavaDPOPolicy:
             n1 = ops.rmsnorm_fwd(x, P[f"l{i}.ln1"], d.rms_eps,
                                  out=torch.empty((M, H), dtype=_BF, device=dev) if extra else self.buf("n", (M, H)),
                                  rstd=rstd1)
-            ops.gemm(n1, P[f"l{i}.qkv"], qkv)
+            self._lin_fwd(i, "qkv", n1, qkv, ls=ls if keep_stash else None)
             ops.rope_fwd(qkv, cos, sin, T, nh, hd)
             ops.attention_fwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], nseq, T, nh, hd, True, scale, out=att, lse=lse)
-            ops.gemm(att, P[f"l{i}.o"], x2, residual=x)
+            self._lin_fwd(i, "o", att, x2, residual=x, ls=ls if keep_stash else None)
             n2 = ops.rmsnorm_fwd(x2, P[f"l{i}.ln2"], d.rms_eps,
                                  out=torch.empty((M, H), dtype=_BF, device=dev) if extra else self.buf("n", (M, H)),
                                  rstd=rstd2)
-            ops.gemm(n2, P[f"l{i}.gu"], gu)
+            self._lin_fwd(i, "gu", n2, gu, ls=ls if keep_stash else None)
             act = ops.swiglu_fwd(gu, torch.empty((M, F), dtype=_BF, device=dev) if extra else self.buf("act", (M, F)))
-            ops.gemm(act, P[f"l{i}.down"], x3, residual=x2)
+            self._lin_fwd(i, "down", act, x3, residual=x2, ls=ls if keep_stash else None)
             if keep_stash:
                 ls.update(qkv=qkv, att=att, x2=x2, gu=gu, rstd1=rstd1, rstd2=rstd2, lse=lse)
                 if extra:
@@ -462,28 +597,28 @@ class LlavaDPOPolicy:
 
         dlogits = ops.logp_bwd(st["logits"], st["labels"], st["lse_v"], d_logp, nseq, T,
                                count=st["count"] if use_average else None)
-        ops.gemm(dlogits, st["hn"], G["lm_head"], a_mn=True, b_mn=True, accumulate=acc)        # dW = dlogits^T hn
+        frozen = self.lora is not None            # LoRA: lm_head / norms / embeddings / base matrices are frozen
+        scratch_h = self.buf("frozen_dw", (H,)) if frozen else None
+        if not frozen:
+            ops.gemm(dlogits, st["hn"], G["lm_head"], a_mn=True, b_mn=True, accumulate=acc)    # dW = dlogits^T hn
         dhn = ops.gemm(dlogits, P["lm_head"], self.buf("dn", (M, H)), b_mn=True)                # dhn = dlogits W
-        dx = ops.rmsnorm_bwd(dhn, st["x_final"], P["norm"], st["rstd_f"], self.buf("dx_a", (M, H)), G["norm"],
-                             dw_accumulate=acc)
+        dx = ops.rmsnorm_bwd(dhn, st["x_final"], P["norm"], st["rstd_f"], self.buf("dx_a", (M, H)),
+                             scratch_h if frozen else G["norm"], dw_accumulate=acc and not frozen)
         if self.on_head_grads_ready is not None:
             self.on_head_grads_ready()
         for i in reversed(range(d.num_layers)):
             ls = st["layers"][i]
             # ---- MLP ----
             act = ls["act"] if "act" in ls else ops.swiglu_fwd(ls["gu"], self.buf("act", (M, F)))   # recompute
-            ops.gemm(dx, act, G[f"l{i}.down"], a_mn=True, b_mn=True, accumulate=acc)
-            dact = ops.gemm(dx, P[f"l{i}.down"], self.buf("dact", (M, F)), b_mn=True)
+            dact = self._lin_bwd(i, "down", dx, act, self.buf("dact", (M, F)), ls, acc)
             dgu = ops.swiglu_bwd(ls["gu"], dact, self.buf("dgu", (M, 2 * F)))
             n2 = ls["n2"] if "n2" in ls else ops.rmsnorm_fwd(ls["x2"], P[f"l{i}.ln2"], d.rms_eps,
                                                              out=self.buf("n", (M, H)))             # recompute
-            ops.gemm(dgu, n2, G[f"l{i}.gu"], a_mn=True, b_mn=True, accumulate=acc)
-            dn2 = ops.gemm(dgu, P[f"l{i}.gu"], self.buf("dn", (M, H)), b_mn=True)
+            dn2 = self._lin_bwd(i, "gu", dgu, n2, self.buf("dn", (M, H)), ls, acc)
             dx2 = ops.rmsnorm_bwd(dn2, ls["x2"], P[f"l{i}.ln2"], ls["rstd2"], self.buf("dx_b", (M, H)),
-                                  G[f"l{i}.ln2"], dres=dx, dw_accumulate=acc)
+                                  scratch_h if frozen else G[f"l{i}.ln2"], dres=dx, dw_accumulate=acc and not frozen)
             # ---- attention ----
-            ops.gemm(dx2, ls["att"], G[f"l{i}.o"], a_mn=True, b_mn=True, accumulate=acc)
-            datt = ops.gemm(dx2, P[f"l{i}.o"], self.buf("datt", (M, H)), b_mn=True)
+            datt = self._lin_bwd(i, "o", dx2, ls["att"], self.buf("datt", (M, H)), ls, acc)
             qkv = ls["qkv"]
             dq32 = self.buf("dq32", (M, H), _F32)
             dq32.zero_()
@@ -493,22 +628,23 @@ class LlavaDPOPolicy:
             ops.rope_bwd(dqkv, dq32, cos, sin, T, nh, hd)
             n1 = ls["n1"] if "n1" in ls else ops.rmsnorm_fwd(ls["x"], P[f"l{i}.ln1"], d.rms_eps,
                                                              out=self.buf("n", (M, H)))             # recompute
-            ops.gemm(dqkv, n1, G[f"l{i}.qkv"], a_mn=True, b_mn=True, accumulate=acc)
-            dn1 = ops.gemm(dqkv, P[f"l{i}.qkv"], self.buf("dn", (M, H)), b_mn=True)
-            dx = ops.rmsnorm_bwd(dn1, ls["x"], P[f"l{i}.ln1"], ls["rstd1"], self.buf("dx_a", (M, H)), G[f"l{i}.ln1"],
-                                 dres=dx2, dw_accumulate=acc)
+            dn1 = self._lin_bwd(i, "qkv", dqkv, n1, self.buf("dn", (M, H)), ls, acc)
+            dx = ops.rmsnorm_bwd(dn1, ls["x"], P[f"l{i}.ln1"], ls["rstd1"], self.buf("dx_a", (M, H)),
+                                 scratch_h if frozen else G[f"l{i}.ln1"], dres=dx2, dw_accumulate=acc and not frozen)
             st["layers"][i] = None   # release this layer's stash
             if self.on_layer_grads_ready is not None:
                 self.on_layer_grads_ready(i)
         # ---- splice backward: embedding rows + projected image rows ----
-        if self.embed_grad_f32 is None:
+        if frozen:
+            pass
+        elif self.embed_grad_f32 is None:
             self.embed_grad_f32 = torch.zeros((V, H), dtype=_F32, device=dev)
         elif not acc:
             self.embed_grad_f32.zero_()
         n_feat_rows = st["proj_pre"].shape[0]
         dfeat32 = self.buf("dfeat32", (n_feat_rows, H), _F32)
         dfeat32.zero_()
-        ops.splice_scatter(st["src"], st["input_ids"], dx, self.embed_grad_f32, dfeat32)
+        ops.splice_scatter(st["src"], st["input_ids"], dx, None if frozen else self.embed_grad_f32, dfeat32)
         dproj = ops.f32_to_bf16(dfeat32, self.buf("dproj", (n_feat_rows, H)))
         # ---- projector ----
         ops.gemm(dproj, st["proj_post"], G["proj.w2"], a_mn=True, b_mn=True, accumulate=acc)
@@ -529,4 +665,6 @@ class LlavaDPOPolicy:
 
     def finalize_embed_grad(self):
         """fp32 embedding-row accumulator -> bf16 flat gradient (once per optimizer step)."""
+        if self.lora is not None:
+            return
         ops.f32_to_bf16(self.embed_grad_f32.view(-1), self.store.g["embed"].view(-1))

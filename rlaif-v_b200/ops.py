@@ -17,7 +17,7 @@ def _chk(t, dtype=torch.bfloat16):
 
 
 def gemm(a, b, out=None, *, a_mn=False, b_mn=False, bias=None, residual=None, act=ACT_NONE,
-         accumulate=False, tile_n=0):
+         accumulate=False, tile_n=0, alpha=1.0):
     """out[M,N] (+)= op(a) @ op(b)^T (+bias)(act)(+residual).
 
     a_mn=False: a is [M,K] (K contiguous);  a_mn=True: a is stored [K,M].
@@ -46,6 +46,12 @@ def gemm(a, b, out=None, *, a_mn=False, b_mn=False, bias=None, residual=None, ac
     if bias is not None:
         _chk(bias)
         assert bias.numel() == N and bias.is_contiguous()
+    if alpha != 1.0:
+        _l.call("rlaifv_gemm_bf16_scaled", _l.ptr(a), a.stride(0), int(a_mn), _l.ptr(b), b.stride(0), int(b_mn),
+                _l.ptr(out), out.stride(0), M, N, K, _l.ptr(bias), _l.ptr(residual),
+                residual.stride(0) if residual is not None else 0, int(act), int(accumulate), int(tile_n),
+                float(alpha), _l.stream_ptr())
+        return out
     _l.call("rlaifv_gemm_bf16", _l.ptr(a), a.stride(0), int(a_mn), _l.ptr(b), b.stride(0), int(b_mn),
             _l.ptr(out), out.stride(0), M, N, K, _l.ptr(bias), _l.ptr(residual),
             residual.stride(0) if residual is not None else 0, int(act), int(accumulate), int(tile_n),

@@ -104,6 +104,13 @@ class TrainingArguments:                   # muffin/train/train_llava15.py:72-10
     seed: int = 42
     local_rank: int = -1
     micro_pairs: Optional[int] = None      # B200 engine knob: pairs per micro-batch (None = whole batch)
+    # muffin/train/train_llava15_lora.py:112-117
+    lora_enable: bool = False
+    lora_r: int = 64
+    lora_alpha: int = 16
+    lora_dropout: float = 0.05
+    lora_weight_path: Optional[str] = None
+    lora_bias: str = "none"
 
 
 def _add_fields(parser, cls):
@@ -138,7 +145,23 @@ def zero_stage(path):
 
 
 def safe_save_model_for_hf_trainer(trainer, output_dir):
-    """muffin/train/train_llava15.py:102-112 — full state dict to CPU, saved by the main process."""
+    """muffin/train/train_llava15.py:102-112 — full state dict to CPU, saved by the main process.
+    LoRA (train_llava15_lora.py:184-197): adapter weights + `non_lora_trainables.bin` (the projector)."""
+    pol = trainer.model.policy
+    if pol.lora is not None:
+        if trainer.args.should_save:
+            os.makedirs(output_dir, exist_ok=True)
+            ad = {"base_model.model." + k: v.cpu() for k, v in pol.lora.hf_views().items()}
+            torch.save(ad, os.path.join(output_dir, "adapter_model.bin"))
+            with open(os.path.join(output_dir, "adapter_config.json"), "w") as f:
+                json.dump({"peft_type": "LORA", "r": pol.lora.r, "lora_alpha": pol.lora.scaling * pol.lora.r,
+                           "lora_dropout": 0.0, "bias": "none", "task_type": "CAUSAL_LM",
+                           "target_modules": ["q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj",
+                                              "down_proj"]}, f)
+            non_lora = {"base_model.model." + k: v.cpu() for k, v in trainer.model.state_dict().items()
+                        if "mm_projector" in k}
+            torch.save(non_lora, os.path.join(output_dir, "non_lora_trainables.bin"))
+        return
     if trainer.args.should_save:
         trainer._save(output_dir, state_dict={k: v.cpu() for k, v in trainer.model.state_dict().items()})
 
@@ -163,6 +186,11 @@ def init_model(model_args, data_args, training_args, attn_implementation=None):
     state = load_hf_checkpoint(model_args.model_name_or_path, model_args.vision_tower)
     model = LlavaLlamaForCausalLM(dims, torch.device("cuda", local_rank), hf_state=state)
     model.config.use_cache = False
+    if training_args.lora_enable:
+        if training_args.lora_dropout != 0.0:
+            print("note: lora_dropout=%g requested; the B200 adapter path runs dropout-free (p=0)" %
+                  training_args.lora_dropout)
+        model.policy.enable_lora(r=training_args.lora_r, alpha=training_args.lora_alpha)
     tokenizer = load_tokenizer(model_args.model_name_or_path, training_args.model_max_length)
     data_args.is_multimodal = True
     data_args.image_token_len = dims.num_patches

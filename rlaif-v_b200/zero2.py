@@ -30,41 +30,69 @@ def cosine_lr(step, total_steps, base_lr, warmup_ratio=0.05):
     return base_lr * max(0.0, 0.5 * (1.0 + math.cos(math.pi * prog)))
 
 
+class OptBucket:
+    """One trainable bucket as the optimizer sees it: flat bf16 parameter / gradient views of equal length
+    (a multiple of 8*world), of which the first `decay_size` elements get weight decay."""
+
+    def __init__(self, name, flat, grad, decay_size):
+        self.name, self.flat, self.grad, self.decay_size = name, flat, grad, decay_size
+        self.size = flat.numel()
+
+
+def store_buckets(store, names=None):
+    """OptBuckets of a ParamStore / LoraStore (optionally only the named ones)."""
+    out = []
+    for b in store.buckets:
+        if names is None or b.name in names:
+            out.append(OptBucket(b.name, store.flat[b.start:b.start + b.size], store.grad[b.start:b.start + b.size],
+                                 b.decay_size))
+    return out
+
+
 class Zero2AdamW:
-    def __init__(self, store, lr=5e-7, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, rank=0, world=1,
-                 group=None):
-        self.store = store
+    def __init__(self, buckets, lr=5e-7, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, rank=0, world=1,
+                 group=None, gather_order=None):
+        if not isinstance(buckets, (list, tuple)):         # a ParamStore: every bucket is trainable
+            buckets = store_buckets(buckets)
+        self.buckets = list(buckets)
+        self.index = {b.name: i for i, b in enumerate(self.buckets)}
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
         self.rank, self.world, self.group = rank, world, group
         self.step_count = 0
-        dev = store.flat.device
-        self.slices = []   # (bucket, s0, s1) absolute element offsets of the owned slice
+        dev = self.buckets[0].flat.device
+        self.slices = []   # (bucket, s0, s1, offset into the owned fp32 state), s0/s1 relative to the bucket
         total = 0
-        for b in store.buckets:
-            assert b.size % (world * 8) == 0
+        for b in self.buckets:
+            assert b.size % (world * 8) == 0, (b.name, b.size)
             n = b.size // world
-            self.slices.append((b, b.start + rank * n, b.start + (rank + 1) * n, total))
+            self.slices.append((b, rank * n, (rank + 1) * n, total))
             total += n
         self.owned = total
         self.master = torch.empty(total, dtype=_F32, device=dev)
         self.exp_avg = torch.zeros(total, dtype=_F32, device=dev)
         self.exp_avg_sq = torch.zeros(total, dtype=_F32, device=dev)
         for b, s0, s1, o in self.slices:
-            self.master[o:o + (s1 - s0)].copy_(store.flat[s0:s1])
+            self.master[o:o + (s1 - s0)].copy_(b.flat[s0:s1])
         self.comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
         self._gathered = {}
+        # order in which the next forward needs the parameters (default: as given)
+        self.gather_order = [self.index[n] for n in gather_order if n in self.index] if gather_order else \
+            list(range(len(self.buckets)))
 
     # ---- gradient reduction (called from the backward as buckets complete) ----
     def reduce_bucket(self, bucket_index):
         if self.world == 1:
             return
+        if isinstance(bucket_index, str):
+            if bucket_index not in self.index:
+                return
+            bucket_index = self.index[bucket_index]
         b, s0, s1, _ = self.slices[bucket_index]
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())
         with torch.cuda.stream(self.comm_stream):
             self.comm_stream.wait_event(ev)
-            g = self.store.grad[b.start:b.start + b.size]
-            dist.reduce_scatter_tensor(self.store.grad[s0:s1], g, op=dist.ReduceOp.SUM, group=self.group)
+            dist.reduce_scatter_tensor(b.grad[s0:s1], b.grad, op=dist.ReduceOp.SUM, group=self.group)
 
     def reduce_all(self):
         for i in range(len(self.slices)):
@@ -83,35 +111,33 @@ class Zero2AdamW:
         if self.world > 1:
             cur.wait_stream(self.comm_stream)        # all gradient reduce-scatters have landed
         b1, b2 = self.betas
-        order = [len(self.slices) - 1, 0] + list(range(1, len(self.slices) - 1))
-        for bi in order:
+        for bi in self.gather_order:
             b, s0, s1, o = self.slices[bi]
-            dec_end = min(s1, b.start + b.decay_size)
+            dec_end = min(s1, b.decay_size)
             if dec_end > s0:
                 n = dec_end - s0
                 ops.adamw_step(self.master[o:o + n], self.exp_avg[o:o + n], self.exp_avg_sq[o:o + n],
-                               self.store.grad[s0:dec_end], self.store.flat[s0:dec_end], lr, b1, b2, self.eps,
-                               self.wd, self.step_count)
-            nd0 = max(s0, b.start + b.decay_size)
+                               b.grad[s0:dec_end], b.flat[s0:dec_end], lr, b1, b2, self.eps, self.wd, self.step_count)
+            nd0 = max(s0, b.decay_size)
             if s1 > nd0:
                 n = s1 - nd0
                 oo = o + (nd0 - s0)
                 ops.adamw_step(self.master[oo:oo + n], self.exp_avg[oo:oo + n], self.exp_avg_sq[oo:oo + n],
-                               self.store.grad[nd0:s1], self.store.flat[nd0:s1], lr, b1, b2, self.eps, 0.0,
-                               self.step_count)
+                               b.grad[nd0:s1], b.flat[nd0:s1], lr, b1, b2, self.eps, 0.0, self.step_count)
             if self.world > 1:
                 ev = torch.cuda.Event()
                 ev.record(cur)
                 with torch.cuda.stream(self.comm_stream):
                     self.comm_stream.wait_event(ev)
-                    dist.all_gather_into_tensor(self.store.flat[b.start:b.start + b.size], self.store.flat[s0:s1],
-                                                group=self.group)
+                    dist.all_gather_into_tensor(b.flat, b.flat[s0:s1], group=self.group)
                     done = torch.cuda.Event()
                     done.record(self.comm_stream)
                 self._gathered[bi] = done
 
     def wait_bucket(self, bucket_index):
         """Make the current stream wait for bucket's parameter all-gather of the last step (no-op if none)."""
+        if isinstance(bucket_index, str):
+            bucket_index = self.index.get(bucket_index, -1)
         ev = self._gathered.pop(bucket_index, None)
         if ev is not None:
             torch.cuda.current_stream().wait_event(ev)

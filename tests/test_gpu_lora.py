@@ -1,0 +1,99 @@
+"""-m gpu: LoRA-DPO path (BASELINE config e) — adapters on q,k,v,o,gate,up,down, base frozen, projector
+trainable — against the oracle's restatement of peft's `W x + (alpha/r) B(A(x))` (dropout 0).
+Parity note: peft is absent in the build container, so this branch of the oracle is unpinned."""
+import pytest
+import torch
+
+from oracle import llava_dpo_oracle as O
+
+pytestmark = pytest.mark.gpu
+R, ALPHA = 8, 2.0   # scaling 0.25 like the shipped r=64 / alpha=16
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+def setup():
+    from rlaifv_b200.model import LlavaDims, LlavaDPOPolicy
+    c = O.TINY
+    dims = LlavaDims(vocab_size=c.vocab_size, hidden_size=c.hidden_size, intermediate_size=c.intermediate_size,
+                     num_layers=c.num_layers, num_heads=c.num_heads, clip_hidden=c.clip_hidden,
+                     clip_intermediate=c.clip_intermediate, clip_layers=c.clip_layers, clip_heads=c.clip_heads,
+                     image_size=c.image_size, patch_size=c.patch_size)
+    params = O.make_params(c, seed=0, scale=0.4)
+    lora = O.make_lora_params(c, r=R, seed=3)
+    pol = LlavaDPOPolicy(dims, "cuda", hf_state=params)
+    store = pol.enable_lora(r=R, alpha=ALPHA)
+    store.load_hf(lora)
+    return pol, params, lora
+
+
+def test_lora_forward_backward_match_oracle():
+    from rlaifv_b200 import ops
+    pol, params, lora = setup()
+    c = O.TINY
+    batch = O.synthetic_pair_batch(c, 2, 24, 30, seed=31, image_pos=7, ragged=True)
+    ids, labels, images = batch["concatenated_input_ids"], batch["concatenated_labels"], batch["images"]
+    out = pol.forward_logps(ids, labels, images, keep_stash=True)
+    # oracle (bf16 op order) with adapters; grads in fp32 for the gradient check
+    pb = {k: v.to(torch.bfloat16) for k, v in {**params, **lora}.items()}
+    ob = O.policy_logps(pb, c, ids, labels, images.to(torch.bfloat16))
+    assert rel(out["logp"], ob["logp"]) <= 1e-3
+    base = O.policy_logps({k: v.to(torch.bfloat16) for k, v in params.items()}, c, ids, labels, images.to(torch.bfloat16))
+    assert rel(ob["logp"], base["logp"]) > 1e-3           # the adapters really change the output
+    pf = {k: v.clone().float().requires_grad_(True) for k, v in {**params, **lora}.items()}
+    of = O.policy_logps(pf, c, ids, labels, images)
+    B = 2
+    rw = torch.tensor([-150.0, -160.0])
+    rr = torch.tensor([-151.0, -158.0])
+    losses, _, _ = O.dpo_loss(of["logp"][:B], of["logp"][B:], rw, rr, 0.1)
+    losses.mean().backward()
+    _, _, _, dpw, dpr, out9 = ops.dpo_loss(out["logp"][:B].contiguous(), out["logp"][B:].contiguous(), rw.cuda(), rr.cuda(), 0.1)
+    pol.store.grad.zero_()
+    pol.backward_logps(torch.cat([dpw, dpr]).contiguous())
+    torch.cuda.synchronize()
+    assert abs(float(out9[0]) - float(losses.mean())) <= 2e-2 * max(1.0, abs(float(losses.mean())))
+    gl = pol.lora.hf_views(grads=True)
+    worst = 0.0
+    for name in ("model.layers.0.self_attn.q_proj.lora_A.weight", "model.layers.0.self_attn.v_proj.lora_B.weight",
+                 "model.layers.1.self_attn.o_proj.lora_A.weight", "model.layers.1.self_attn.o_proj.lora_B.weight",
+                 "model.layers.0.mlp.gate_proj.lora_B.weight", "model.layers.1.mlp.up_proj.lora_A.weight",
+                 "model.layers.0.mlp.down_proj.lora_A.weight", "model.layers.1.mlp.down_proj.lora_B.weight",
+                 "model.layers.1.self_attn.k_proj.lora_A.weight"):
+        ref = pf[name].grad
+        got = gl[name].float().cpu()
+        nr = float((got.double().norm() - ref.double().norm()).abs() / (ref.double().norm() + 1e-30))
+        er = rel(got, ref)
+        print(f"{name}: rel max err {er:.3e}, norm diff {nr:.3e}")
+        worst = max(worst, er)
+        assert nr <= 5e-2 and er <= 1e-1, name
+    # projector is trainable, everything else in the base store stays untouched (frozen)
+    g = pol.store.hf_grad_views()
+    assert rel(g["model.mm_projector.2.weight"].float(), pf["model.mm_projector.2.weight"].grad) <= 1e-1
+    for name in ("lm_head.weight", "model.embed_tokens.weight", "model.layers.0.self_attn.q_proj.weight",
+                 "model.layers.1.mlp.down_proj.weight", "model.norm.weight"):
+        assert float(g[name].float().abs().max()) == 0.0, name
+
+
+def test_lora_engine_step_updates_only_adapters_and_projector():
+    from rlaifv_b200.engine import DPOStepEngine
+    pol, params, lora = setup()
+    before_base = pol.store.flat.clone()
+    before_lora = pol.lora.flat.clone()
+    eng = DPOStepEngine(pol, lr=1e-3, total_steps=10, constant_lr=True)
+    assert {b.name for b in eng.opt.buckets} == {f"lora{i}" for i in range(O.TINY.num_layers)} | {"projector"}
+    batch = O.synthetic_pair_batch(O.TINY, 2, 24, 20, seed=5, image_pos=7)
+    batch["ref_win_logp"] = torch.tensor([-100.0, -101.0])
+    batch["ref_rej_logp"] = torch.tensor([-100.5, -100.0])
+    batch["beta"] = 0.1
+    m = eng.train_step(batch)
+    torch.cuda.synchronize()
+    assert float(m[0]) == float(m[0])
+    assert not torch.equal(pol.lora.flat, before_lora)
+    proj = next(b for b in pol.store.buckets if b.name == "projector")
+    changed = pol.store.flat != before_base
+    assert bool(changed[proj.start:proj.start + proj.size].any())
+    changed[proj.start:proj.start + proj.size] = False
+    assert not bool(changed.any())                      # base weights, embeddings, norms, lm_head frozen
