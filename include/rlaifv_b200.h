@@ -44,6 +44,14 @@ int rlaifv_gemm_bf16_scaled(const void* A, long long lda, int a_mn_major, const 
                             const void* residual, long long ldr, int act, int accumulate, int tile_n, float alpha,
                             void* stream);
 
+/* Two operand pairs, one accumulator: C (+)= A*B^T + A2[:, koff:koff+K2]*B2^T with koff = (n0/n_sub)*r
+ * (n_sub > 0: forward over fused sub-linears whose adapters' lora_A outputs sit side by side in A2) or 0.
+ * The LoRA rank-r update is computed in the same CTA pass as the frozen base GEMM — no extra pass over C. */
+int rlaifv_gemm_bf16_dual(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major,
+                          const void* A2, long long lda2, const void* B2, long long ldb2, int K2, int r, int n_sub,
+                          void* C, long long ldc, int M, int N, int K, const void* bias, const void* residual,
+                          long long ldr, int act, int accumulate, void* stream);
+
 /* tile_n = 512 selects the 2-CTA kernel (cta_group::2, 256x256 tile per CTA pair). rlaifv_gemm_set_2cta(1)
  * lets tile_n = 0 (auto) pick it for large problems. */
 int rlaifv_gemm_set_2cta(int enable);

@@ -32,6 +32,16 @@ struct GemmEpilogue {
   float alpha;     // != 1: result = bf16(bf16(acc) * alpha) first (LoRA scaling, peft: lora_B(...) * scaling)
 };
 
+// Optional second operand pair accumulated into the same TMEM tile after the first K loop:
+//   C = A1 * B1^T + A2[:, koff : koff + K2] * B2^T,   koff = (n0 / n_sub) * r   (0 when n_sub == 0).
+// This is how the LoRA rank-r update rides in the same CTA pass as the frozen base GEMM
+// (forward: A2 = s*A(x) [M, g*r], B2 = stacked lora_B [N, r]; dgrad: A2 = s*dy*B [M, g*r], B2 = stacked lora_A).
+struct GemmSecondSource {
+  int K2;      // 0 = disabled
+  int r;       // adapter rank (column-block width of A2 per sub-linear)
+  int n_sub;   // output columns per sub-linear (forward) or 0
+};
+
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 192;
@@ -128,7 +138,8 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int col0
 template <bool A_MN, bool B_MN, int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 int M, int N, int K, GemmEpilogue epi, TileCounter* ctr) {
+                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+                 int M, int N, int K, GemmSecondSource src2, GemmEpilogue epi, TileCounter* ctr) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -148,11 +159,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int num_m = (M + GEMM_BM - 1) / GEMM_BM;
   const int num_n = (N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
-  const int num_k = (K + GEMM_BK - 1) / GEMM_BK;
+  const int num_k1 = (K + GEMM_BK - 1) / GEMM_BK;
+  const int num_k = num_k1 + (src2.K2 + GEMM_BK - 1) / GEMM_BK;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (src2.K2 > 0) {
+      tma_prefetch_desc(&tmA2);
+      tma_prefetch_desc(&tmB2);
+    }
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -201,20 +217,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
           uint8_t* b_dst = a_dst + Cfg::A_BYTES;
           mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
-          const int k0 = kb * GEMM_BK;
+          const bool second = kb >= num_k1;
+          const CUtensorMap* mA = second ? &tmA2 : &tmA;
+          const CUtensorMap* mB = second ? &tmB2 : &tmB;
+          const int kB = (second ? kb - num_k1 : kb) * GEMM_BK;                      // k index into B
+          const int kA = second ? kB + (src2.n_sub > 0 ? (n0 / src2.n_sub) * src2.r : 0) : kB;   // into A
           if (A_MN) {
 #pragma unroll
             for (int a = 0; a < GEMM_BM / 64; ++a)
-              tma_load_2d(a_dst + a * (GEMM_BK * 128), &tmA, &full[s], m0 + a * 64, k0);
+              tma_load_2d(a_dst + a * (GEMM_BK * 128), mA, &full[s], m0 + a * 64, kA);
           } else {
-            tma_load_2d(a_dst, &tmA, &full[s], k0, m0);
+            tma_load_2d(a_dst, mA, &full[s], kA, m0);
           }
           if (B_MN) {
 #pragma unroll
             for (int a = 0; a < BN / 64; ++a)
-              tma_load_2d(b_dst + a * (GEMM_BK * 128), &tmB, &full[s], n0 + a * 64, k0);
+              tma_load_2d(b_dst + a * (GEMM_BK * 128), mB, &full[s], n0 + a * 64, kB);
           } else {
-            tma_load_2d(b_dst, &tmB, &full[s], k0, n0);
+            tma_load_2d(b_dst, mB, &full[s], kB, n0);
           }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
@@ -516,7 +536,8 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, i
 }
 
 template <bool A_MN, bool B_MN, int BN>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K,
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA2,
+                       const CUtensorMap& tmB2, int M, int N, int K, const GemmSecondSource& src2,
                        const GemmEpilogue& epi, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_bf16_kernel<A_MN, B_MN, BN>;
@@ -530,7 +551,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, in
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
   if (!g_counter_pool) B200_CHECK_CUDA(cudaGetSymbolAddress((void**)&g_counter_pool, g_tile_counters));
   TileCounter* ctr = g_counter_pool + (g_launch_seq++ & 63);
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, epi, ctr);
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmA2, tmB2, M, N, K, src2, epi, ctr);
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -573,7 +594,9 @@ extern "C" int rlaifv_gemm_set_2cta(int enable) {
 // C ABI — see include/rlaifv_b200.h for the contract.
 static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major,
                      void* C, long long ldc, int M, int N, int K, const void* bias, const void* residual,
-                     long long ldr, int act, int accumulate, int tile_n, float alpha, void* stream) {
+                     long long ldr, int act, int accumulate, int tile_n, float alpha, void* stream,
+                     const void* A2 = nullptr, long long lda2 = 0, const void* B2 = nullptr, long long ldb2 = 0,
+                     int K2 = 0, int r2 = 0, int n_sub = 0) {
   B200_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   B200_REQUIRE(N % 8 == 0 && ldc % 8 == 0, "gemm: N (%d) and ldc (%lld) must be multiples of 8", N,
                ldc);
@@ -592,11 +615,29 @@ static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B
     else bn = (N >= 256 && tiles256 >= 120) ? 256 : 128;
   }
   B200_REQUIRE(bn == 128 || bn == 256 || bn == 512, "gemm: tile_n must be 0, 128, 256 or 512 (2-CTA 256x256)");
+  GemmSecondSource src2;
+  src2.K2 = K2;
+  src2.r = r2;
+  src2.n_sub = n_sub;
+  if (K2 > 0) {
+    if (bn == 512) bn = 256;   // the second source is implemented in the 1-CTA kernel
+    B200_REQUIRE(lda2 % 8 == 0 && ldb2 % 8 == 0, "gemm: lda2/ldb2 must be multiples of 8");
+    B200_REQUIRE(n_sub == 0 || n_sub % bn == 0, "gemm: n_sub (%d) must be a multiple of the N tile (%d)", n_sub, bn);
+  }
   CUtensorMap tmA, tmB;
   int rc = operand_tmap(&tmA, A, lda, a_mn_major != 0, M, K, GEMM_BM);
   if (rc) return rc;
   rc = operand_tmap(&tmB, B, ldb, b_mn_major != 0, N, K, bn == 512 ? 128 : bn);
   if (rc) return rc;
+  CUtensorMap tmA2 = tmA, tmB2 = tmB;
+  if (K2 > 0) {
+    // A2 spans all sub-linears' column blocks: its contraction extent is (N / n_sub) * r (forward) or K2 (dgrad)
+    const int a2_k = n_sub > 0 ? (N / n_sub) * r2 : K2;
+    rc = operand_tmap(&tmA2, A2, lda2, a_mn_major != 0, M, a2_k, GEMM_BM);
+    if (rc) return rc;
+    rc = operand_tmap(&tmB2, B2, ldb2, b_mn_major != 0, N, K2, bn);
+    if (rc) return rc;
+  }
   GemmEpilogue epi;
   epi.C = (bf16*)C;
   epi.ldc = ldc;
@@ -616,13 +657,13 @@ static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B
     return launch_gemm2<true, true>(tmA, tmB, M, N, K, epi, st);
   }
   if (!a_mn_major && !b_mn_major)
-    return bn == 256 ? launch_gemm<false, false, 256>(tmA, tmB, M, N, K, epi, st)
-                     : launch_gemm<false, false, 128>(tmA, tmB, M, N, K, epi, st);
+    return bn == 256 ? launch_gemm<false, false, 256>(tmA, tmB, tmA2, tmB2, M, N, K, src2, epi, st)
+                     : launch_gemm<false, false, 128>(tmA, tmB, tmA2, tmB2, M, N, K, src2, epi, st);
   if (!a_mn_major && b_mn_major)
-    return bn == 256 ? launch_gemm<false, true, 256>(tmA, tmB, M, N, K, epi, st)
-                     : launch_gemm<false, true, 128>(tmA, tmB, M, N, K, epi, st);
-  return bn == 256 ? launch_gemm<true, true, 256>(tmA, tmB, M, N, K, epi, st)
-                   : launch_gemm<true, true, 128>(tmA, tmB, M, N, K, epi, st);
+    return bn == 256 ? launch_gemm<false, true, 256>(tmA, tmB, tmA2, tmB2, M, N, K, src2, epi, st)
+                     : launch_gemm<false, true, 128>(tmA, tmB, tmA2, tmB2, M, N, K, src2, epi, st);
+  return bn == 256 ? launch_gemm<true, true, 256>(tmA, tmB, tmA2, tmB2, M, N, K, src2, epi, st)
+                   : launch_gemm<true, true, 128>(tmA, tmB, tmA2, tmB2, M, N, K, src2, epi, st);
 }
 
 extern "C" int rlaifv_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb,
@@ -639,4 +680,16 @@ extern "C" int rlaifv_gemm_bf16_scaled(const void* A, long long lda, int a_mn_ma
                                        int accumulate, int tile_n, float alpha, void* stream) {
   return gemm_impl(A, lda, a_mn_major, B, ldb, b_mn_major, C, ldc, M, N, K, bias, residual, ldr, act, accumulate,
                    tile_n, alpha, stream);
+}
+
+// C (+)= A*B^T + A2[:, koff:koff+K2] * B2^T (shared fp32 accumulator, one rounding), then bias/act/residual.
+// koff = (n0 / n_sub) * r when n_sub > 0 (forward over fused sub-linears), else 0. Same operand majors as A/B.
+extern "C" int rlaifv_gemm_bf16_dual(const void* A, long long lda, int a_mn_major, const void* B, long long ldb,
+                                     int b_mn_major, const void* A2, long long lda2, const void* B2, long long ldb2,
+                                     int K2, int r, int n_sub, void* C, long long ldc, int M, int N, int K,
+                                     const void* bias, const void* residual, long long ldr, int act, int accumulate,
+                                     void* stream) {
+  B200_REQUIRE(K2 > 0 && A2 && B2, "gemm_dual: second source missing");
+  return gemm_impl(A, lda, a_mn_major, B, ldb, b_mn_major, C, ldc, M, N, K, bias, residual, ldr, act, accumulate, 0,
+                   1.0f, stream, A2, lda2, B2, ldb2, K2, r, n_sub);
 }

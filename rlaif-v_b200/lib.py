@@ -23,6 +23,9 @@ _SIGNATURES = {
                          c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_void_p],
     "rlaifv_gemm_bf16_scaled": [c_void_p, c_ll, c_int, c_void_p, c_ll, c_int, c_void_p, c_ll, c_int, c_int, c_int,
                                 c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_float, c_void_p],
+    "rlaifv_gemm_bf16_dual": [c_void_p, c_ll, c_int, c_void_p, c_ll, c_int, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int,
+                              c_int, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_ll, c_int, c_int,
+                              c_void_p],
     "rlaifv_gemm_set_2cta": [c_int],
     "rlaifv_gemm_set_tuning": [c_int, c_int],
     "rlaifv_rmsnorm_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p],

@@ -210,9 +210,21 @@ class LoraStore:
                 n = math.prod(sg.shape)
                 self.p[sg.name] = self.flat[sg.offset:sg.offset + n].view(*sg.shape)
                 self.g[sg.name] = self.grad[sg.offset:sg.offset + n].view(*sg.shape)
+        for i in range(dims.num_layers):   # stacked lora_B views (adjacent segments) = second-source B operand
+            for src in (self.p, self.g):
+                q, gq = src[f"l{i}.B_q"], src[f"l{i}.B_g"]
+                base = self.flat if src is self.p else self.grad
+                oq = (q.data_ptr() - base.data_ptr()) // 2
+                og = (gq.data_ptr() - base.data_ptr()) // 2
+                src[f"l{i}.B_qkv"] = base[oq:oq + 3 * H * r].view(3 * H, r)
+                src[f"l{i}.B_gu"] = base[og:og + 2 * F * r].view(2 * F, r)
+                src[f"l{i}.B_o_cat"] = src[f"l{i}.B_o"]
+                src[f"l{i}.B_d_cat"] = src[f"l{i}.B_d"]
         # peft init: lora_A kaiming_uniform(a=sqrt(5)) = U(-1/sqrt(in), 1/sqrt(in)), lora_B = 0
         g = torch.Generator(device=device).manual_seed(seed)
-        for name, v in self.p.items():
+        for name, v in list(self.p.items()):
+            if name.endswith(("B_qkv", "B_gu", "B_o_cat", "B_d_cat")):
+                continue
             if ".A_" in name:
                 bound = 1.0 / math.sqrt(v.shape[1])
                 v.copy_((torch.rand(v.shape, generator=g, device=device) * 2 - 1) * bound)
@@ -345,26 +357,24 @@ class LlavaDPOPolicy:
         return f"layer{i}" if self.lora is None else f"lora{i}"
 
     # ---- one linear group = base GEMM (+ LoRA adapters sharing the input) ----
-    _GROUPS = {"qkv": ("A_qkv", ("B_q", "B_k", "B_v")), "o": ("A_o", ("B_o",)), "gu": ("A_gu", ("B_g", "B_u")),
-               "down": ("A_d", ("B_d",))}
+    _GROUPS = {"qkv": ("A_qkv", ("B_q", "B_k", "B_v"), "B_qkv"), "o": ("A_o", ("B_o",), "B_o_cat"),
+               "gu": ("A_gu", ("B_g", "B_u"), "B_gu"), "down": ("A_d", ("B_d",), "B_d_cat")}
 
     def _lin_fwd(self, i, group, x, out, residual=None, ls=None):
-        """out = x @ W^T (+ residual) (+ scaling * B(A(x)) per sub-linear when LoRA is on)."""
+        """out = x @ W^T (+ residual). LoRA: t = s * x @ A^T (all sub-linears' lora_A stacked), then ONE GEMM
+        accumulates x @ W^T and t_j @ B_j^T in the same TMEM tile (rlaifv_gemm_bf16_dual)."""
         W = self.store.p[f"l{i}.{group}"]
         if self.lora is None:
             return ops.gemm(x, W, out, residual=residual)
         L = self.lora
-        a_name, b_names = self._GROUPS[group]
+        a_name, b_names, bcat = self._GROUPS[group]
         A = L.p[f"l{i}.{a_name}"]
-        r, M = L.r, x.shape[0]
-        ops.gemm(x, W, out)
+        M = x.shape[0]
         t = torch.empty((M, A.shape[0]), dtype=_BF, device=self.device) if ls is not None else \
             self.buf("lora_t_" + group, (M, A.shape[0]))
-        ops.gemm(x, A, t)
-        n_out = out.shape[1] // len(b_names)
-        for j, bn in enumerate(b_names):
-            ops.gemm(t[:, j * r:(j + 1) * r], L.p[f"l{i}.{bn}"], out[:, j * n_out:(j + 1) * n_out],
-                     accumulate=True, alpha=L.scaling, residual=residual)
+        ops.gemm(x, A, t, alpha=L.scaling)
+        n_sub = out.shape[1] // len(b_names) if len(b_names) > 1 else 0
+        ops.gemm_dual(x, W, t, L.p[f"l{i}.{bcat}"], out, k2=L.r, r=L.r, n_sub=n_sub, residual=residual)
         if ls is not None:
             ls["t_" + group] = t
         return out
@@ -376,20 +386,19 @@ class LlavaDPOPolicy:
             ops.gemm(dy, x, self.store.g[f"l{i}.{group}"], a_mn=True, b_mn=True, accumulate=acc)
             return ops.gemm(dy, W, dx_out, b_mn=True)
         L = self.lora
-        a_name, b_names = self._GROUPS[group]
+        a_name, b_names, _ = self._GROUPS[group]
         A = L.p[f"l{i}.{a_name}"]
         r, M = L.r, x.shape[0]
-        t = ls["t_" + group]
+        t = ls["t_" + group]                      # already scaled by s
         dt = self.buf("lora_dt_" + group, (M, A.shape[0]))
         n_out = dy.shape[1] // len(b_names)
         for j, bn in enumerate(b_names):
             dy_j = dy[:, j * n_out:(j + 1) * n_out]
-            ops.gemm(dy_j, L.p[f"l{i}.{bn}"], dt[:, j * r:(j + 1) * r], b_mn=True, alpha=L.scaling)        # dt_j = s dy_j B_j
-            ops.gemm(dy_j, t[:, j * r:(j + 1) * r], L.g[f"l{i}.{bn}"], a_mn=True, b_mn=True, alpha=L.scaling,
-                     accumulate=acc)                                                                         # dB_j
-        ops.gemm(dt, x, L.g[f"l{i}.{a_name}"], a_mn=True, b_mn=True, accumulate=acc)                        # dA
-        ops.gemm(dy, W, dx_out, b_mn=True)
-        return ops.gemm(dt, A, dx_out, b_mn=True, accumulate=True)
+            ops.gemm(dy_j, L.p[f"l{i}.{bn}"], dt[:, j * r:(j + 1) * r], b_mn=True, alpha=L.scaling)   # dt_j = s dy_j B_j
+            ops.gemm(dy_j, t[:, j * r:(j + 1) * r], L.g[f"l{i}.{bn}"], a_mn=True, b_mn=True, accumulate=acc)  # dB_j
+        ops.gemm(dt, x, L.g[f"l{i}.{a_name}"], a_mn=True, b_mn=True, accumulate=acc)                  # dA = dt^T x
+        # dx = dy @ W + dt @ A in one pass (second source = stacked lora_A, MN-major like W)
+        return ops.gemm_dual(dy, W, dt, A, dx_out, k2=A.shape[0], r=r, n_sub=0, b_mn=True)
 
     # ------------------------------------------------------------------ init / buffers
     def _random_init(self, seed, std):

@@ -314,3 +314,17 @@ def adamw_step(master, exp_avg, exp_avg_sq, grad, param_bf16, lr, beta1, beta2, 
     _l.call("rlaifv_adamw_step", _l.ptr(master), _l.ptr(exp_avg), _l.ptr(exp_avg_sq), _l.ptr(grad),
             int(grad.dtype == torch.float32), _l.ptr(param_bf16), n, float(lr), float(beta1), float(beta2),
             float(eps), float(weight_decay), int(step), float(grad_scale), _l.stream_ptr())
+
+
+def gemm_dual(a, b, a2, b2, out, *, k2, r, n_sub=0, b_mn=False, residual=None, accumulate=False):
+    """out (+)= a @ op(b)^T + a2[:, koff:koff+k2] @ op(b2)^T (+ residual), one fp32 accumulator.
+    koff = (n0 // n_sub) * r per output tile when n_sub > 0, else 0."""
+    _chk(a), _chk(b), _chk(a2), _chk(b2), _chk(out)
+    M, K = a.shape
+    N = b.shape[1] if b_mn else b.shape[0]
+    assert out.shape == (M, N)
+    _l.call("rlaifv_gemm_bf16_dual", _l.ptr(a), a.stride(0), 0, _l.ptr(b), b.stride(0), int(b_mn), _l.ptr(a2),
+            a2.stride(0), _l.ptr(b2), b2.stride(0), int(k2), int(r), int(n_sub), _l.ptr(out), out.stride(0), M, N, K,
+            _l.ptr(None), _l.ptr(residual), residual.stride(0) if residual is not None else 0, 0, int(accumulate),
+            _l.stream_ptr())
+    return out

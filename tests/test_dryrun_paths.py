@@ -1,0 +1,54 @@
+"""CPU test: the Python orchestration (forward + backward launch sequences, full fine-tuning and LoRA)
+runs end to end against a recording stand-in for the C ABI — catches host-side breakage (shapes, views,
+missing methods, argument counts vs the ctypes table) without a GPU. No arithmetic is checked here."""
+import ctypes
+
+import pytest
+import torch
+
+from oracle import llava_dpo_oracle as O
+
+
+@pytest.mark.parametrize("use_lora", [False, True])
+def test_launch_sequence_dry_run(monkeypatch, use_lora):
+    from rlaifv_b200 import lib, ops
+    from rlaifv_b200.model import LlavaDims, LlavaDPOPolicy
+    c = O.TINY
+    dims = LlavaDims(vocab_size=c.vocab_size, hidden_size=c.hidden_size, intermediate_size=c.intermediate_size,
+                     num_layers=c.num_layers, num_heads=c.num_heads, clip_hidden=c.clip_hidden,
+                     clip_intermediate=c.clip_intermediate, clip_layers=c.clip_layers, clip_heads=c.clip_heads,
+                     image_size=c.image_size, patch_size=c.patch_size)
+    calls = []
+
+    def fake_call(name, *args):
+        assert len(args) == len(lib._SIGNATURES[name]), name       # argument count matches the ctypes table
+        calls.append(name)
+
+    monkeypatch.setattr(lib, "call", fake_call)
+    monkeypatch.setattr(lib, "stream_ptr", lambda: ctypes.c_void_p(0))
+    monkeypatch.setattr(lib, "load", lambda: type("L", (), {"rlaifv_rmsnorm_bwd_partials": staticmethod(lambda: 4)})())
+    monkeypatch.setattr(ops, "_chk", lambda t, dtype=None: t)
+    pol = LlavaDPOPolicy(dims, "cpu", hf_state=O.make_params(c, seed=0))
+    if use_lora:
+        pol.enable_lora(r=8, alpha=2.0)
+    batch = O.synthetic_pair_batch(c, 2, 24, 30, seed=31, image_pos=7, ragged=True)
+    T = 60
+    monkeypatch.setattr(pol, "splice", lambda ids, labels, rows, nb, idx, T_hint=None: (
+        torch.zeros(4 * T, dims.hidden_size, dtype=torch.bfloat16), torch.full((4, T), -100),
+        torch.zeros(4, T, dtype=torch.int32), T))
+    out = pol.forward_logps(batch["concatenated_input_ids"], batch["concatenated_labels"], batch["images"])
+    assert out["logp"].shape == (4,) and out["per_token_logps"].shape == (4, T - 1)
+    n_fwd = len(calls)
+    pol.backward_logps(torch.zeros(4))
+    pol.finalize_embed_grad()
+    assert len(calls) > 2 * n_fwd * 0.8
+    per_layer_gemm = 4
+    if use_lora:
+        assert calls.count("rlaifv_gemm_bf16_dual") == 2 * per_layer_gemm * dims.num_layers   # fwd + dgrad
+        assert "rlaifv_f32_to_bf16" in calls                # projected-image-row gradients still flow
+    else:
+        assert calls.count("rlaifv_gemm_bf16_dual") == 0
+    assert calls.count("rlaifv_attention_fwd") == dims.num_layers + dims.clip_layers_used
+    assert calls.count("rlaifv_attention_bwd") == dims.num_layers
+    names = {b.name for b in pol.trainable_buckets()}
+    assert ("projector" in names) and (("lora0" in names) == use_lora) and (("embed" in names) != use_lora)
