@@ -310,15 +310,24 @@ def main():
         gemm_events.append((s, e, 2.0 * r.shape[0] * r.shape[1] * K))
         return r
 
+    orig_dual = ops.gemm_dual
+
+    def timed_dual(a, b, a2, b2, out, **kw):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        r = orig_dual(a, b, a2, b2, out, **kw)
+        e.record()
+        gemm_events.append((s, e, 2.0 * r.shape[0] * r.shape[1] * (a.shape[1] + kw["k2"])))
+        return r
+
     ops.gemm = timed_gemm
+    ops.gemm_dual = timed_dual
     try:
-        import rlaifv_b200.model as _m
-        _m.ops.gemm = timed_gemm
         engine.train_step(dev_batches[0])
         torch.cuda.synchronize()
     finally:
         ops.gemm = orig_gemm
-        _m.ops.gemm = orig_gemm
+        ops.gemm_dual = orig_dual
     gemm_ms = sum(s.elapsed_time(e) for s, e, _ in gemm_events)
     gemm_flops = sum(f for _, _, f in gemm_events)
     peak_sus, peak_burst, peak_kind = measured_peaks()
@@ -330,11 +339,13 @@ def main():
     hb = host_batches[0]
     h2d = sum(v.numel() * v.element_size() for v in hb.values() if torch.is_tensor(v))
     f_pair = flops_per_pair(T)
-    if args.lora:   # base wgrad skipped, adapters added
+    if args.lora:   # base wgrad skipped, adapters (159 907 840 params) added
         n_dec = 32 * (4 * 4096 ** 2 + 3 * 4096 * 11008)
-        attn = 32 * 4 * T * T * 4096 * 0.5
-        f_pair = 2 * (2 * T * (4 * (n_dec + 4096 * 32000) + 6 * 159907840) + 3 * attn) + \
-            (flops_per_pair(T) - 6 * (2 * (n_dec + 4096 * 32000) * T + attn))
+        n_head = 4096 * 32000
+        attn_seq = 32 * 4 * T * T * 4096 * 0.5
+        f_clip = 2 * 23 * (4 * 1024 ** 2 + 2 * 1024 * 4096) * 577 + 23 * 4 * 577 ** 2 * 1024 + 2 * 588 * 1024 * 576
+        f_proj = 2 * (1024 * 4096 + 4096 ** 2) * 576
+        f_pair = 2 * T * (4 * (n_dec + n_head) + 6 * 159907840) + 3 * 2 * attn_seq + f_clip + 3 * f_proj
     line = {
         "metric": "preference-pairs/sec LLaVA-1.5-7B DPO step", "value": value, "unit": "pairs/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev,
