@@ -1,0 +1,274 @@
+"""-m gpu kernel-level parity tests through the C ABI: every row kernel, the GEMM operand forms / epilogues,
+attention forward / backward, splice edge cases (bit-exact), log-prob gather, DPO loss, AdamW.
+Floating-point kernels are compared with a plain fp32 torch evaluation of the same op on the same bf16
+inputs (tolerances in the asserts); integer / copy work must be bit-exact."""
+import math
+
+import pytest
+import torch
+
+from oracle import llava_dpo_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+BF = torch.bfloat16
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+@pytest.fixture(autouse=True)
+def _seed():
+    torch.manual_seed(0)
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True)])
+@pytest.mark.parametrize("tile_n", [128, 256, 512])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (304, 320, 200), (1136, 768, 1000)])
+def test_gemm_operand_forms(a_mn, b_mn, tile_n, M, N, K):
+    from rlaifv_b200 import ops
+    A = (torch.randn(K, M, device=DEV) if a_mn else torch.randn(M, K, device=DEV)).to(BF)
+    B = (torch.randn(K, N, device=DEV) if b_mn else torch.randn(N, K, device=DEV)).to(BF)
+    ref = (A.float().t() if a_mn else A.float()) @ (B.float() if b_mn else B.float().t())
+    got = ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn, tile_n=tile_n)
+    assert rel(got.float(), ref) <= 6e-3          # bf16 output rounding
+
+
+def test_gemm_epilogues_and_views():
+    from rlaifv_b200 import ops
+    M, N, K = 777, 512, 384
+    x = torch.randn(M, K, device=DEV).to(BF)
+    w = (torch.randn(N, K, device=DEV) * 0.05).to(BF)
+    bias = torch.randn(N, device=DEV).to(BF)
+    res = torch.randn(M, N, device=DEV).to(BF)
+    base = x.float() @ w.float().t()
+    assert rel(ops.gemm(x, w, bias=bias).float(), base + bias.float()) <= 6e-3
+    g = ops.gemm(x, w, bias=bias, act=ops.ACT_GELU).float()
+    assert rel(g, torch.nn.functional.gelu((base + bias.float()).to(BF).float())) <= 8e-3
+    q = ops.gemm(x, w, bias=bias, act=ops.ACT_QUICK_GELU).float()
+    pre = (base + bias.float()).to(BF).float()
+    assert rel(q, pre * torch.sigmoid(1.702 * pre)) <= 8e-3
+    r = ops.gemm(x, w, residual=res).float()
+    assert rel(r, base.to(BF).float() + res.float()) <= 6e-3
+    acc = torch.randn(M, N, device=DEV).to(BF)
+    want = base + acc.float()
+    assert rel(ops.gemm(x, w, acc.clone(), accumulate=True).float(), want) <= 6e-3
+    # alpha-scaled (LoRA) + column-block output view of a wider buffer
+    wide = torch.zeros(M, 3 * N, device=DEV, dtype=BF)
+    ops.gemm(x, w, wide[:, N:2 * N], alpha=0.25)
+    assert rel(wide[:, N:2 * N].float(), 0.25 * base) <= 6e-3
+    assert float(wide[:, :N].abs().max()) == 0.0 and float(wide[:, 2 * N:].abs().max()) == 0.0
+
+
+def test_gemm_dual_source_matches_two_products():
+    from rlaifv_b200 import ops
+    M, K, r, nsub = 500, 256, 8, 256
+    x = torch.randn(M, K, device=DEV).to(BF)
+    W = (torch.randn(2 * nsub, K, device=DEV) * 0.05).to(BF)
+    t = torch.randn(M, 2 * r, device=DEV).to(BF)
+    Bc = (torch.randn(2 * nsub, r, device=DEV) * 0.1).to(BF)
+    out = torch.empty(M, 2 * nsub, device=DEV, dtype=BF)
+    ops.gemm_dual(x, W, t, Bc, out, k2=r, r=r, n_sub=nsub)
+    ref = x.float() @ W.float().t()
+    ref[:, :nsub] += t[:, :r].float() @ Bc[:nsub].float().t()
+    ref[:, nsub:] += t[:, r:].float() @ Bc[nsub:].float().t()
+    assert rel(out.float(), ref) <= 6e-3
+    # dgrad form: dy [M,N] @ W [N,K] (MN-major) + dt [M,2r] @ A [2r,K]
+    dy = torch.randn(M, 2 * nsub, device=DEV).to(BF)
+    A = (torch.randn(2 * r, K, device=DEV) * 0.1).to(BF)
+    dx = torch.empty(M, K, device=DEV, dtype=BF)
+    ops.gemm_dual(dy, W, t, A, dx, k2=2 * r, r=r, n_sub=0, b_mn=True)
+    assert rel(dx.float(), dy.float() @ W.float() + t.float() @ A.float()) <= 6e-3
+
+
+# ------------------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize("nseq,S,nh,D,causal", [(2, 300, 2, 128, True), (1, 1135, 2, 128, True), (2, 577, 4, 64, False),
+                                                (3, 5, 2, 64, False)])
+def test_attention_forward(nseq, S, nh, D, causal):
+    from rlaifv_b200 import ops
+    H = nh * D
+    qkv = torch.randn(nseq * S, 3 * H, device=DEV).to(BF)
+    scale = D ** -0.5
+    out, lse = ops.attention_fwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], nseq, S, nh, D, causal, scale)
+
+    def split(t):
+        return t.float().reshape(nseq, S, nh, D).permute(0, 2, 1, 3)
+    q, k, v = split(qkv[:, :H]), split(qkv[:, H:2 * H]), split(qkv[:, 2 * H:])
+    s = q @ k.transpose(-1, -2) * scale
+    if causal:
+        s = s.masked_fill(~torch.ones(S, S, device=DEV, dtype=torch.bool).tril(), float("-inf"))
+    assert rel(split(out), torch.softmax(s, -1) @ v) <= 2e-2
+    assert rel(lse, torch.logsumexp(s, -1)) <= 1e-3
+
+
+def test_attention_backward():
+    from rlaifv_b200 import ops
+    nseq, S, nh, D = 2, 687, 2, 128
+    H = nh * D
+    qkv = torch.randn(nseq * S, 3 * H, device=DEV).to(BF)
+    scale = D ** -0.5
+    out, lse = ops.attention_fwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], nseq, S, nh, D, True, scale)
+    d_out = torch.randn(nseq * S, H, device=DEV).to(BF)
+    dq32 = torch.zeros(nseq * S, H, device=DEV)
+    dqkv = torch.zeros(nseq * S, 3 * H, device=DEV, dtype=BF)
+    ops.attention_bwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], out, d_out, lse, nseq, S, nh, D, scale, dq32,
+                      dqkv[:, H:2 * H], dqkv[:, 2 * H:])
+
+    def split(t):
+        return t.float().reshape(nseq, S, nh, D).permute(0, 2, 1, 3).contiguous()
+    q, k, v = (split(qkv[:, i * H:(i + 1) * H]).requires_grad_() for i in range(3))
+    s = (q @ k.transpose(-1, -2) * scale).masked_fill(~torch.ones(S, S, device=DEV, dtype=torch.bool).tril(), float("-inf"))
+    (torch.softmax(s, -1) @ v).backward(split(d_out))
+    assert rel(split(dq32), q.grad) <= 3e-2
+    assert rel(split(dqkv[:, H:2 * H]), k.grad) <= 3e-2
+    assert rel(split(dqkv[:, 2 * H:]), v.grad) <= 3e-2
+
+
+# ------------------------------------------------------------------------------------------------ row kernels
+def test_rmsnorm_forward_backward():
+    from rlaifv_b200 import ops
+    M, H = 333, 4096
+    x = torch.randn(M, H, device=DEV).to(BF)
+    w = (1 + 0.1 * torch.randn(H, device=DEV)).to(BF)
+    rstd = torch.empty(M, device=DEV)
+    y = ops.rmsnorm_fwd(x, w, 1e-5, rstd=rstd)
+    xf = x.float().requires_grad_()
+    wf = w.float().requires_grad_()
+    ref = O.rms_norm(xf, wf, 1e-5)
+    assert rel(y.float(), ref) <= 8e-3
+    dy = torch.randn(M, H, device=DEV).to(BF)
+    dres = torch.randn(M, H, device=DEV).to(BF)
+    dx = torch.empty_like(x)
+    dw = torch.zeros(H, device=DEV, dtype=BF)
+    ops.rmsnorm_bwd(dy, x, w, rstd, dx, dw, dres=dres, dw_accumulate=False)
+    ref.backward(dy.float())
+    assert rel(dx.float(), xf.grad + dres.float()) <= 1e-2
+    assert rel(dw.float(), wf.grad) <= 1e-2
+
+
+def test_layernorm_rope_swiglu_gelu_colsum():
+    from rlaifv_b200 import ops
+    M, H = 577, 1024
+    x = torch.randn(M, H, device=DEV).to(BF)
+    w, b = torch.randn(H, device=DEV).to(BF), torch.randn(H, device=DEV).to(BF)
+    assert rel(ops.layernorm_fwd(x, w, b, 1e-5).float(),
+               torch.nn.functional.layer_norm(x.float(), (H,), w.float(), b.float(), 1e-5)) <= 8e-3
+    # RoPE forward == oracle formula; backward == transpose
+    T, nh, D = 45, 2, 128
+    nseq = 3
+    qkv = torch.randn(nseq * T, 3 * nh * D, device=DEV).to(BF)
+    cos, sin = O.rope_cos_sin(T, D, 10000.0, BF)
+    cosd, sind = cos.to(DEV).contiguous(), sin.to(DEV).contiguous()
+    ref_q = qkv[:, :nh * D].float().reshape(nseq, T, nh, D)
+    want = (ref_q.to(BF) * cosd[None, :, None, :] + O.rotate_half(ref_q.to(BF)) * sind[None, :, None, :])
+    got = ops.rope_fwd(qkv.clone(), cosd, sind, T, nh, D)
+    assert torch.equal(got[:, :nh * D].reshape(nseq, T, nh, D), want)          # same bf16 rounding order: bit-exact
+    assert torch.equal(got[:, 2 * nh * D:], qkv[:, 2 * nh * D:])               # v untouched
+    # SwiGLU
+    F_ = 512
+    gu = torch.randn(M, 2 * F_, device=DEV).to(BF)
+    act = ops.swiglu_fwd(gu)
+    g, u = gu[:, :F_], gu[:, F_:]
+    assert rel(act.float(), (torch.nn.functional.silu(g) * u).float()) <= 8e-3      # 1 bf16 ulp (fast exp)
+    dact = torch.randn(M, F_, device=DEV).to(BF)
+    dgu = ops.swiglu_bwd(gu, dact)
+    gf, uf = g.float().requires_grad_(), u.float().requires_grad_()
+    (torch.nn.functional.silu(gf) * uf).backward(dact.float())
+    assert rel(dgu[:, :F_].float(), gf.grad) <= 8e-3 and rel(dgu[:, F_:].float(), uf.grad) <= 8e-3
+    # GELU fwd/bwd, column sums
+    pre = torch.randn(M, H, device=DEV).to(BF)
+    assert rel(ops.gelu_fwd(pre).float(), torch.nn.functional.gelu(pre.float())) <= 8e-3
+    pf = pre.float().requires_grad_()
+    torch.nn.functional.gelu(pf).backward(x.float())
+    assert rel(ops.gelu_bwd(pre, x).float(), pf.grad) <= 8e-3
+    db = torch.zeros(H, device=DEV, dtype=BF)
+    ops.colsum(x, db, accumulate=False)
+    assert rel(db.float(), x.float().sum(0)) <= 8e-3
+
+
+# ------------------------------------------------------------------------------------------------ splice (bit-exact)
+@pytest.mark.parametrize("max_len", [2048, 30])
+def test_splice_index_map_and_rows_bit_exact(max_len):
+    from rlaifv_b200 import ops
+    P, H, V = 16, 64, 100
+    ids = torch.tensor([[1, 5, -200, 7, 8, 0, 0, 0], [1, -200, 9, 10, 11, 12, 13, 2], [1, 4, 5, 6, 7, 2, 0, 0],
+                        [-200, 3, 4, 5, 6, 7, 8, 9]])
+    labs = torch.tensor([[-100, -100, -100, 7, 8, -100, -100, -100], [-100, -100, 9, 10, 11, 12, 13, 2],
+                         [-100, 4, 5, 6, 7, 2, -100, -100], [-100, 3, 4, 5, 6, 7, 8, 9]])
+    src_ref, lab_ref, T = O.splice_index_map(ids, labs, P, max_len)
+    idc, labc = ids.to(DEV), labs.to(DEV)
+    n_img, lens = ops.splice_count(idc, P, max_len)
+    assert int(lens.max()) == T and n_img.tolist() == [1, 1, 0, 1]
+    img_index = torch.arange(4, dtype=torch.int32, device=DEV)
+    src, new_labels = ops.splice_map(idc, labc, n_img, img_index, P, T, max_len)
+    assert torch.equal(new_labels.cpu(), lab_ref)
+    assert torch.equal(src.cpu().long(), src_ref)
+    embed = torch.randn(V, H, device=DEV).to(BF)
+    feat = torch.randn(4 * P, H, device=DEV).to(BF)
+    rows = ops.splice_gather(src, idc, embed, feat).reshape(4, T, H)
+    ref = O.splice_embeds({"model.embed_tokens.weight": embed.cpu()}, ids, src_ref, feat.cpu().reshape(4, P, H))
+    assert torch.equal(rows.cpu(), ref)
+    # backward scatter = transpose of the gather
+    dx = torch.randn(4 * T, H, device=DEV).to(BF)
+    d_embed = torch.zeros(V, H, device=DEV)
+    d_feat = torch.zeros(4 * P, H, device=DEV)
+    ops.splice_scatter(src, idc, dx, d_embed, d_feat)
+    e = embed.cpu().float().requires_grad_()
+    f = feat.cpu().float().requires_grad_()
+    O.splice_embeds({"model.embed_tokens.weight": e}, ids, src_ref, f.reshape(4, P, H)).backward(dx.cpu().float().reshape(4, T, H))
+    assert rel(d_embed, e.grad) <= 1e-6 and rel(d_feat, f.grad) <= 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ logp / loss / optimizer
+def test_logp_gather_forward_backward():
+    from rlaifv_b200 import ops
+    nseq, T, V = 3, 37, 32000
+    logits = (torch.randn(nseq * T, V, device=DEV) * 2).to(BF)
+    labels = torch.randint(0, V, (nseq, T), device=DEV)
+    labels[:, :10] = -100
+    labels[1, 20:] = -100
+    per_tok, lse, s, a, cnt = ops.logp_fwd(logits, labels, nseq, T)
+    lf = logits.float().reshape(nseq, T, V).requires_grad_()
+    rp, rs, ra = O.get_batch_logps(lf, labels)
+    mask = labels[:, 1:] != -100
+    assert rel(per_tok[mask], rp[mask]) <= 1e-5 and rel(s, rs) <= 1e-5 and rel(a, ra) <= 1e-5
+    assert torch.equal(cnt.long(), mask.sum(-1))
+    g = torch.randn(nseq, device=DEV)
+    (rs * g).sum().backward()
+    d = ops.logp_bwd(logits.clone(), labels, lse, g, nseq, T)
+    assert rel(d.float().reshape(nseq, T, V), lf.grad) <= 1e-2
+
+
+def test_dpo_loss_kernel_matches_reference_formula():
+    from rlaifv_b200 import ops
+    B = 37
+    pw, pr, rw, rr = (torch.randn(B, device=DEV) * 20 - 100 for _ in range(4))
+    losses, cr, rj, dpw, dpr, out9 = ops.dpo_loss(pw, pr, rw, rr, 0.1, dpo_weight=1.0, sft_weight=0.3)
+    pwf, prf = pw.clone().requires_grad_(), pr.clone().requires_grad_()
+    rl, rc, rrj = O.dpo_loss(pwf, prf, rw, rr, 0.1)
+    loss = rl.mean() - 0.3 * pwf.mean()
+    loss.backward()
+    assert rel(losses, rl.detach()) <= 1e-5 and rel(cr, rc) <= 1e-5 and rel(rj, rrj) <= 1e-5
+    assert rel(dpw, pwf.grad) <= 1e-4 and rel(dpr, prf.grad) <= 1e-4
+    assert abs(float(out9[0]) - float(loss)) <= 1e-4 * abs(float(loss))
+    assert abs(float(out9[3]) - float((rc > rrj).float().mean())) <= 1e-6
+
+
+def test_fused_adamw_matches_torch():
+    from rlaifv_b200 import ops
+    n = 4096 * 3
+    p0 = torch.randn(n, device=DEV)
+    ref_p = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([ref_p], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
+    master, m, v = p0.clone(), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    pbf = torch.empty(n, device=DEV, dtype=BF)
+    for step in range(1, 4):
+        g = (torch.randn(n, device=DEV) * 0.1).to(BF)
+        ref_p.grad = g.float()
+        opt.step()
+        ops.adamw_step(master, m, v, g, pbf, 1e-3, 0.9, 0.999, 1e-8, 0.01, step)
+        assert rel(master, ref_p.detach()) <= 1e-5
+        assert torch.equal(pbf, master.to(BF))
