@@ -332,6 +332,16 @@ def main():
     gemm_flops = sum(f for _, _, f in gemm_events)
     peak_sus, peak_burst, peak_kind = measured_peaks()
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
+    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (bytes per launch of the
+    # forward qkv GEMM; the same capture lists dgrad / wgrad) — profiles/ncu_gemm_traffic.json
+    traffic, traffic_note = None, None
+    tp = os.path.join(REPO, "profiles", "ncu_gemm_traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            tj = json.load(f)["gemm"][0]
+        traffic = tj["dram_bytes_per_launch"]
+        traffic_note = "%s: %.3g B DRAM per launch vs %.3g B algorithmic (ncu)" % (
+            tj["launch"], tj["dram_bytes_per_launch"], tj["algorithmic_bytes"])
 
     total_pairs = B * world
     value = total_pairs / (ms_dev * 1e-3)
@@ -366,7 +376,7 @@ def main():
                               "measured_burst_%g" % peak_burst: value / world * f_pair / 1e12 / peak_burst,
                               "datasheet_2250": value / world * f_pair / 1e12 / 2250.0},
         "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05)", "achieved": achieved,
-                     "peak": peak_sus, "unit": "TFLOP/s", "frac": achieved / peak_sus, "traffic": None,
+                     "peak": peak_sus, "unit": "TFLOP/s", "frac": achieved / peak_sus, "traffic": traffic, "traffic_note": traffic_note,
                      "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step); burst %g"
                                     % (peak_kind, peak_burst),
                      "gemm_launches": len(gemm_events), "gemm_ms_per_step": gemm_ms,

@@ -47,6 +47,7 @@ class DPOStepEngine:
             _lib.load().rlaifv_gemm_set_2cta(0)
         self._metrics = torch.zeros(9, dtype=_F32, device=policy.device)
         self._last_micro = False
+        self._stepping = False
         # ZeRO-2 overlap: reduce a layer's bucket as soon as its backward finished (last micro-batch only)
         policy.on_layer_grads_ready = self._layer_ready
         policy.on_head_grads_ready = self._head_ready
@@ -54,11 +55,16 @@ class DPOStepEngine:
 
     def _layer_ready(self, layer):
         if self._last_micro:
-            self.opt.reduce_bucket(self.policy.layer_bucket_name(layer))
+            name = self.policy.layer_bucket_name(layer)
+            self.opt.reduce_bucket(name)
+            if self._stepping:            # gradients final, weights no longer read this step: update now,
+                self.opt.step_bucket(name)    # overlapped with the rest of the backward
 
     def _head_ready(self):
-        if self._last_micro and self.world > 1:
+        if self._last_micro:
             self.opt.reduce_bucket("head")      # head bucket: final right after its backward
+            if self._stepping:
+                self.opt.step_bucket("head")
 
     def _h2d(self, t, dtype=None):
         if not t.is_cuda:
@@ -94,6 +100,11 @@ class DPOStepEngine:
         sft_w = float(os.environ.get("SFT_weight", 0.0))     # muffin/train/trainers.py:299-300
         dpo_w = float(os.environ.get("DPO_weight", 1.0))
         self._metrics.zero_()
+        self._stepping = bool(optimizer_step)
+        if optimizer_step:
+            lr = self.base_lr if self.constant_lr else cosine_lr(self.global_step, self.total_steps, self.base_lr,
+                                                                 self.warmup_ratio)
+            self.opt.begin_step(lr)
         n_micro = (B + mp - 1) // mp
         for mi in range(n_micro):
             lo, hi = mi * mp, min(B, (mi + 1) * mp)
@@ -114,9 +125,7 @@ class DPOStepEngine:
             self.opt.reduce_bucket("embed")
             self.opt.reduce_bucket("projector")
         if optimizer_step:
-            lr = self.base_lr if self.constant_lr else cosine_lr(self.global_step, self.total_steps, self.base_lr,
-                                                                 self.warmup_ratio)
-            self.opt.step(lr)
+            self.opt.finish_step()
             self.global_step += 1
         return self._metrics
 

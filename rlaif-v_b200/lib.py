@@ -140,7 +140,28 @@ def bind_stream(stream=None):
     _bound_stream = None if stream is None else c_void_p(stream.cuda_stream)
 
 
+_override_stream = None
+
+
+class use_stream:
+    """Context manager: launches inside go to `stream` (side streams for overlapped optimizer work)."""
+
+    def __init__(self, stream):
+        self.stream = stream
+
+    def __enter__(self):
+        global _override_stream
+        self._prev = _override_stream
+        _override_stream = c_void_p(self.stream.cuda_stream)
+
+    def __exit__(self, *exc):
+        global _override_stream
+        _override_stream = self._prev
+
+
 def stream_ptr():
+    if _override_stream is not None:
+        return _override_stream
     if _bound_stream is not None:
         return _bound_stream
     return c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -16,6 +16,7 @@ import math
 import torch
 import torch.distributed as dist
 
+from . import lib as _lib
 from . import ops
 
 _F32 = torch.float32
@@ -74,7 +75,10 @@ class Zero2AdamW:
         for b, s0, s1, o in self.slices:
             self.master[o:o + (s1 - s0)].copy_(b.flat[s0:s1])
         self.comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+        self.opt_stream = None
         self._gathered = {}
+        self._reduced = {}
+        self._done = set()
         # order in which the next forward needs the parameters (default: as given)
         self.gather_order = [self.index[n] for n in gather_order if n in self.index] if gather_order else \
             list(range(len(self.buckets)))
@@ -93,46 +97,77 @@ class Zero2AdamW:
         with torch.cuda.stream(self.comm_stream):
             self.comm_stream.wait_event(ev)
             dist.reduce_scatter_tensor(b.grad[s0:s1], b.grad, op=dist.ReduceOp.SUM, group=self.group)
+            done = torch.cuda.Event()
+            done.record(self.comm_stream)
+        self._reduced[bucket_index] = done
 
     def reduce_all(self):
         for i in range(len(self.slices)):
             self.reduce_bucket(i)
 
     # ---- optimizer step ----
-    def step(self, lr=None):
-        """Fused AdamW on the owned slices, then (world > 1) the in-place parameter all-gather.
-        Buckets are processed in the order the next forward needs them (projector, embed, layer 0..,
-        head); each bucket's all-gather runs on the comm stream as soon as its AdamW kernels are done
-        and is awaited lazily by `wait_bucket` — so the gathers overlap the remaining AdamW work and the
-        beginning of the next step (frozen CLIP tower first) instead of sitting exposed at the step end."""
-        lr = self.lr if lr is None else lr
-        self.step_count += 1
-        cur = torch.cuda.current_stream()
-        if self.world > 1:
-            cur.wait_stream(self.comm_stream)        # all gradient reduce-scatters have landed
+    def _adamw_bucket(self, bi, lr):
+        b, s0, s1, o = self.slices[bi]
         b1, b2 = self.betas
-        for bi in self.gather_order:
-            b, s0, s1, o = self.slices[bi]
-            dec_end = min(s1, b.decay_size)
-            if dec_end > s0:
-                n = dec_end - s0
-                ops.adamw_step(self.master[o:o + n], self.exp_avg[o:o + n], self.exp_avg_sq[o:o + n],
-                               b.grad[s0:dec_end], b.flat[s0:dec_end], lr, b1, b2, self.eps, self.wd, self.step_count)
-            nd0 = max(s0, b.decay_size)
-            if s1 > nd0:
-                n = s1 - nd0
-                oo = o + (nd0 - s0)
-                ops.adamw_step(self.master[oo:oo + n], self.exp_avg[oo:oo + n], self.exp_avg_sq[oo:oo + n],
-                               b.grad[nd0:s1], b.flat[nd0:s1], lr, b1, b2, self.eps, 0.0, self.step_count)
+        dec_end = min(s1, b.decay_size)
+        if dec_end > s0:
+            n = dec_end - s0
+            ops.adamw_step(self.master[o:o + n], self.exp_avg[o:o + n], self.exp_avg_sq[o:o + n],
+                           b.grad[s0:dec_end], b.flat[s0:dec_end], lr, b1, b2, self.eps, self.wd, self.step_count)
+        nd0 = max(s0, b.decay_size)
+        if s1 > nd0:
+            n = s1 - nd0
+            oo = o + (nd0 - s0)
+            ops.adamw_step(self.master[oo:oo + n], self.exp_avg[oo:oo + n], self.exp_avg_sq[oo:oo + n],
+                           b.grad[nd0:s1], b.flat[nd0:s1], lr, b1, b2, self.eps, 0.0, self.step_count)
+
+    def begin_step(self, lr=None):
+        """Open an optimizer step whose buckets are updated one by one (`step_bucket`) while the backward
+        is still running; `finish_step` updates whatever is left and closes the step."""
+        self._lr = self.lr if lr is None else lr
+        self.step_count += 1
+        self._done = set()
+        if self.opt_stream is None:
+            self.opt_stream = torch.cuda.Stream(device=self.buckets[0].flat.device)
+
+    def step_bucket(self, name):
+        """AdamW (+ parameter all-gather) of one bucket on the optimizer side stream, ordered after everything
+        enqueued so far on the current stream and after this bucket's gradient reduce-scatter. The caller
+        guarantees the bucket's gradients are final and its parameters are no longer read this step."""
+        bi = self.index.get(name, -1)
+        if bi < 0 or bi in self._done:
+            return
+        self._done.add(bi)
+        cur = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self.opt_stream.wait_event(ev)
+        if self.world > 1:
+            rs = self._reduced.pop(bi, None)
+            if rs is not None:
+                self.opt_stream.wait_event(rs)
+        with torch.cuda.stream(self.opt_stream), _lib.use_stream(self.opt_stream):
+            self._adamw_bucket(bi, self._lr)
             if self.world > 1:
-                ev = torch.cuda.Event()
-                ev.record(cur)
-                with torch.cuda.stream(self.comm_stream):
-                    self.comm_stream.wait_event(ev)
-                    dist.all_gather_into_tensor(b.flat, b.flat[s0:s1], group=self.group)
-                    done = torch.cuda.Event()
-                    done.record(self.comm_stream)
-                self._gathered[bi] = done
+                b, s0, s1, _ = self.slices[bi]
+                dist.all_gather_into_tensor(b.flat, b.flat[s0:s1], group=self.group)
+            done = torch.cuda.Event()
+            done.record(self.opt_stream)
+        self._gathered[bi] = done
+
+    def finish_step(self):
+        for bi in self.gather_order:
+            self.step_bucket(self.buckets[bi].name)
+        # single-GPU callers read the parameters right away on the main stream: order it after the side stream
+        if self.world == 1:
+            self.wait_all()
+
+    def step(self, lr=None):
+        """Whole optimizer step at once (no overlap with the backward)."""
+        self.begin_step(lr)
+        if self.world > 1:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        self.finish_step()
 
     def wait_bucket(self, bucket_index):
         """Make the current stream wait for bucket's parameter all-gather of the last step (no-op if none)."""

@@ -89,6 +89,7 @@ GLOO_WORKER = textwrap.dedent('''
     class Ev:
         def record(self, *a): pass
     class St:
+        cuda_stream = 0
         def wait_stream(self, *a): pass
         def wait_event(self, *a): pass
     import contextlib
