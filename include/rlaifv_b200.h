@@ -74,6 +74,22 @@ int rlaifv_attention_bwd(const void* q, const void* k, const void* v, long long 
                          float* dq_f32, void* dk, void* dv, long long ld_dkv, float* delta_ws, int nseq,
                          int S, int n_heads, int head_dim, float scale, void* stream);
 
+/* Grouped-query variants (Mistral-7B decoder of OmniLMM-12B, omnilmm/model/omnilmm.py:259-265 -> HF
+ * MistralForCausalLM: 32 query / 8 key-value heads): k/v (and dk/dv) hold n_kv_heads heads; query head h uses
+ * kv head h / (n_heads / n_kv_heads); the backward sums the group's dK/dV contributions in TMEM. */
+int rlaifv_attention_fwd_gqa(const void* q, const void* k, const void* v, long long ld_qkv, void* out,
+                             long long ld_out, float* lse, int nseq, int S, int n_heads, int n_kv_heads,
+                             int head_dim, int causal, float scale, void* stream);
+int rlaifv_attention_bwd_gqa(const void* q, const void* k, const void* v, long long ld_qkv, const void* out,
+                             long long ld_out, const void* d_out, long long ld_dout, const float* lse, float* dq_f32,
+                             void* dk, void* dv, long long ld_dkv, float* delta_ws, int nseq, int S, int n_heads,
+                             int n_kv_heads, int head_dim, float scale, void* stream);
+/* RoPE on a fused row [q: n_heads*D | k: n_kv_heads*D | v: n_kv_heads*D] */
+int rlaifv_rope_fwd_gqa(void* qkv, const void* cos_tab, const void* sin_tab, long long M, int T, int n_heads,
+                        int n_kv_heads, int head_dim, long long ld, void* stream);
+int rlaifv_rope_bwd_gqa(void* dqkv, const float* dq_f32, const void* cos_tab, const void* sin_tab, long long M,
+                        int T, int n_heads, int n_kv_heads, int head_dim, long long ld, void* stream);
+
 /* ---- norms (HF:llama/modeling_llama.py:62-67; HF:clip LayerNorm) -------------------------------- */
 int rlaifv_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd_or_null, int M, int H, float eps,
                        void* stream);

@@ -51,7 +51,7 @@ def build_reference_model(R, cfg, params):
     """SURVEY.md Appendix A recipe: random-init model, CLIP tower attached without network."""
     lc = R["LlavaConfig"](vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size,
                           intermediate_size=cfg.intermediate_size, num_hidden_layers=cfg.num_layers,
-                          num_attention_heads=cfg.num_heads, num_key_value_heads=cfg.num_heads,
+                          num_attention_heads=cfg.num_heads, num_key_value_heads=cfg.kv_heads,
                           rms_norm_eps=cfg.rms_eps, rope_theta=cfg.rope_theta, max_position_embeddings=4096,
                           attn_implementation="eager", tie_word_embeddings=False, pad_token_id=0,
                           bos_token_id=1, eos_token_id=2)
@@ -107,6 +107,9 @@ CASES = {
     # cooler weights: logits of the magnitude a real checkpoint produces, so the strict 1e-3 bf16 gate applies
     "cool_ragged_b2": (2, 24, 40, 14, 9, True, 0.4),
     "cool_long_b1": (1, 30, 150, 15, 20, False, 0.4),
+    # grouped-query decoder (4 query / 2 kv heads): reference = the same LlavaLlamaForCausalLM with
+    # num_key_value_heads=2 (HF Llama's repeat_kv path, the arithmetic of the Mistral LLM in OmniLMM-12B)
+    "gqa_ragged_b2": (2, 24, 40, 16, 9, True, 0.4, "TINY_GQA"),
 }
 
 
@@ -126,13 +129,16 @@ def main():
         dpo_token_weighted = False
         task = "DPO"
 
-    for name, (B, P, Rl, seed, ipos, ragged, pscale) in CASES.items():
-        if pscale not in models:
+    for name, case in CASES.items():
+        B, P, Rl, seed, ipos, ragged, pscale = case[:7]
+        cfg_name = case[7] if len(case) > 7 else "TINY"
+        cfg = O.CONFIGS[cfg_name]
+        if (pscale, cfg_name) not in models:
             prm = O.make_params(cfg, seed=0, scale=pscale)
             mdl = build_reference_model(R, cfg, prm)
             mdl.train()
-            models[pscale] = (prm, mdl)
-        params, model = models[pscale]
+            models[(pscale, cfg_name)] = (prm, mdl)
+        params, model = models[(pscale, cfg_name)]
         batch = O.synthetic_pair_batch(cfg, B, P, Rl, seed, image_pos=ipos, ragged=ragged)
         g = torch.Generator().manual_seed(seed + 100)
         ref = {k: (-40.0 + 3.0 * torch.randn(B, generator=g)) for k in ("ref_win_logp", "ref_rej_logp")}
@@ -191,6 +197,7 @@ def main():
             B=np.int64(B), prompt_len=np.int64(P), resp_len=np.int64(Rl), seed=np.int64(seed),
             image_pos=np.int64(-1 if ipos is None else ipos), ragged=np.int64(int(ragged)),
             params_checksum=np.float64(O.params_checksum(params)), param_scale=np.float64(pscale),
+            cfg_name=np.array(cfg_name),
             concatenated_input_ids=keep_ids.numpy(), concatenated_labels=keep_labels.numpy(),
             images=data["images"].numpy().astype(np.float32),
             ref_win_logp=ref["ref_win_logp"].numpy(), ref_rej_logp=ref["ref_rej_logp"].numpy(),

@@ -39,6 +39,7 @@ class OracleConfig:
     intermediate_size: int = 11008
     num_layers: int = 32
     num_heads: int = 32
+    num_kv_heads: int = 0          # 0 = num_heads (MHA); < num_heads = grouped-query attention (Mistral-7B: 32/8)
     rms_eps: float = 1e-5          # llava-v1.5-7b config.json rms_norm_eps
     rope_theta: float = 10000.0
     max_len: int = 2048            # tokenizer_model_max_length (muffin/train/train_llava15.py:249)
@@ -57,6 +58,10 @@ class OracleConfig:
         return self.hidden_size // self.num_heads
 
     @property
+    def kv_heads(self):
+        return self.num_kv_heads or self.num_heads
+
+    @property
     def num_patches(self):
         return (self.image_size // self.patch_size) ** 2
 
@@ -69,6 +74,12 @@ class OracleConfig:
 TINY = OracleConfig(vocab_size=512, hidden_size=256, intermediate_size=512, num_layers=2, num_heads=2,
                     clip_hidden=128, clip_intermediate=256, clip_layers=3, clip_heads=2,
                     image_size=56, patch_size=14)
+# grouped-query decoder (4 query heads share 2 key/value heads), the attention layout of the Mistral-7B LLM inside
+# OmniLMM-12B (omnilmm/model/omnilmm.py:259-265); HF Llama implements the same repeat_kv arithmetic.
+TINY_GQA = OracleConfig(vocab_size=512, hidden_size=512, intermediate_size=512, num_layers=2, num_heads=4,
+                        num_kv_heads=2, clip_hidden=128, clip_intermediate=256, clip_layers=3, clip_heads=2,
+                        image_size=56, patch_size=14)
+CONFIGS = {"TINY": TINY, "TINY_GQA": TINY_GQA}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -90,8 +101,11 @@ def make_params(cfg: OracleConfig, seed: int = 0, std: float = 0.02, dtype=torch
     rnd("model.embed_tokens.weight", V, H)
     for i in range(cfg.num_layers):
         pre = f"model.layers.{i}."
-        for nm in ("q_proj", "k_proj", "v_proj", "o_proj"):
-            rnd(pre + f"self_attn.{nm}.weight", H, H, s=0.05)
+        Hkv = cfg.kv_heads * cfg.head_dim
+        rnd(pre + "self_attn.q_proj.weight", H, H, s=0.05)
+        rnd(pre + "self_attn.k_proj.weight", Hkv, H, s=0.05)
+        rnd(pre + "self_attn.v_proj.weight", Hkv, H, s=0.05)
+        rnd(pre + "self_attn.o_proj.weight", H, H, s=0.05)
         rnd(pre + "mlp.gate_proj.weight", F_, H, s=0.05)
         rnd(pre + "mlp.up_proj.weight", F_, H, s=0.05)
         rnd(pre + "mlp.down_proj.weight", H, F_, s=0.05)
@@ -339,11 +353,15 @@ def llama_logits(p, inputs_embeds, cfg: OracleConfig, lora_scaling=0.25):
         pre = f"model.layers.{i}."
         r = x
         h = rms_norm(x, p[pre + "input_layernorm.weight"], cfg.rms_eps)
+        nkv = cfg.kv_heads
         q = lora_linear(p, pre + "self_attn.q_proj", h, lora_scaling).view(nseq, T, nh, hd).transpose(1, 2)
-        k = lora_linear(p, pre + "self_attn.k_proj", h, lora_scaling).view(nseq, T, nh, hd).transpose(1, 2)
-        v = lora_linear(p, pre + "self_attn.v_proj", h, lora_scaling).view(nseq, T, nh, hd).transpose(1, 2)
+        k = lora_linear(p, pre + "self_attn.k_proj", h, lora_scaling).view(nseq, T, nkv, hd).transpose(1, 2)
+        v = lora_linear(p, pre + "self_attn.v_proj", h, lora_scaling).view(nseq, T, nkv, hd).transpose(1, 2)
         q = q * cos + rotate_half(q) * sin
         k = k * cos + rotate_half(k) * sin
+        if nkv != nh:   # HF repeat_kv (llama/modeling_llama.py:171-180): kv head j serves query heads j*g .. j*g+g-1
+            k = k.repeat_interleave(nh // nkv, dim=1)
+            v = v.repeat_interleave(nh // nkv, dim=1)
         w = torch.matmul(q, k.transpose(2, 3)) * (hd ** -0.5) + causal
         w = F.softmax(w, dim=-1, dtype=torch.float32).to(q.dtype)
         a = torch.matmul(w, v).transpose(1, 2).reshape(nseq, T, H)

@@ -47,7 +47,9 @@ template <int D, bool CAUSAL>
 __global__ void __launch_bounds__(160, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ out, long long ld_out,
-                     float* __restrict__ lse_out, int S, int n_heads, float scale) {
+                     float* __restrict__ lse_out, int S, int n_heads, int kv_group, float scale) {
+  // kv_group = query heads per key/value head (1 = MHA; 4 = Mistral-7B's 32/8 GQA,
+  // omnilmm/model/omnilmm.py -> HF MistralForCausalLM): K/V tiles come from head / kv_group.
   using Cfg = AttFwdCfg<D>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -65,6 +67,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const int num_q_tiles = (S + ATT_BQ - 1) / ATT_BQ;
   const int q_tile = num_q_tiles - 1 - blockIdx.x;  // heavy (late) tiles first
   const int head = blockIdx.y, seq = blockIdx.z;
+  const int kv_head = head / kv_group;
   const int q0 = q_tile * ATT_BQ;
   const int n_kv = CAUSAL ? (q_tile + 1) : (S + ATT_BKV - 1) / ATT_BKV;
 
@@ -102,9 +105,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
         for (int a = 0; a < D / 64; ++a) {
           tma_load_3d(smem + Cfg::OFF_K + s * Cfg::KV_BYTES + a * (ATT_BKV * 128), &tmK, &kv_full[s],
-                      head * D + a * 64, j * ATT_BKV, seq);
+                      kv_head * D + a * 64, j * ATT_BKV, seq);
           tma_load_3d(smem + Cfg::OFF_V + s * Cfg::KV_BYTES + a * (ATT_BKV * 128), &tmV, &kv_full[s],
-                      head * D + a * 64, j * ATT_BKV, seq);
+                      kv_head * D + a * 64, j * ATT_BKV, seq);
         }
       };
       auto issue_s = [&](int j) {
@@ -311,7 +314,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                      const float* __restrict__ lse, const float* __restrict__ delta,
                      float* __restrict__ dq_f32, bf16* __restrict__ dk, bf16* __restrict__ dv,
-                     long long ld_dkv, int S, int n_heads, float scale) {
+                     long long ld_dkv, int S, int n_heads, int kv_group, float scale) {
+  // grid.y = key/value heads; the CTA loops over the kv_group query heads that share its K/V tile.
   using Cfg = AttBwdCfg;
   constexpr int D = Cfg::D;
   extern __shared__ uint8_t smem_raw[];
@@ -331,9 +335,10 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = (S + 127) / 128;
   const int kv_tile = blockIdx.x;
-  const int head = blockIdx.y, seq = blockIdx.z;
+  const int kv_head = blockIdx.y, seq = blockIdx.z;
   const int kv0 = kv_tile * 128;
-  const int n_q = num_tiles - kv_tile;  // q tiles kv_tile .. num_tiles-1
+  const int n_qt = num_tiles - kv_tile;     // q tiles kv_tile .. num_tiles-1 (per query head)
+  const int n_q = n_qt * kv_group;          // iterations: (query head of the group) x (q tile)
 
   if (warp == 4) {
     if (lane == 0) {
@@ -367,11 +372,12 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       constexpr uint32_t idesc_mnmn = make_idesc_bf16(128, 128, true, true);  // both MN-major
       mbar_arrive_expect_tx(kv_full, 2 * Cfg::TILE_BYTES);
       for (int a = 0; a < 2; ++a) {
-        tma_load_3d(smem + Cfg::OFF_K + a * 16384, &tmK, kv_full, head * D + a * 64, kv0, seq);
-        tma_load_3d(smem + Cfg::OFF_V + a * 16384, &tmV, kv_full, head * D + a * 64, kv0, seq);
+        tma_load_3d(smem + Cfg::OFF_K + a * 16384, &tmK, kv_full, kv_head * D + a * 64, kv0, seq);
+        tma_load_3d(smem + Cfg::OFF_V + a * 16384, &tmV, kv_full, kv_head * D + a * 64, kv0, seq);
       }
       auto load_q = [&](int it) {
-        const int q0 = (kv_tile + it) * 128;
+        const int q0 = (kv_tile + it % n_qt) * 128;
+        const int head = kv_head * kv_group + it / n_qt;
         mbar_arrive_expect_tx(q_full, 2 * Cfg::TILE_BYTES);
         for (int a = 0; a < 2; ++a) {
           tma_load_3d(smem + Cfg::OFF_Q + a * 16384, &tmQ, q_full, head * D + a * 64, q0, seq);
@@ -429,7 +435,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
     const float c = scale * LOG2E;
     for (int it = 0; it < n_q; ++it) {
-      const int q_tile = kv_tile + it;
+      const int q_tile = kv_tile + it % n_qt;
+      const int head = kv_head * kv_group + it / n_qt;
       const int q0 = q_tile * 128;
       // stage LSE / delta of this q tile (previous readers finished before last pt_full arrive;
       // named barrier among the 128 compute threads keeps it simple)
@@ -508,8 +515,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     tc_fence_after();
     {
       const bool row_ok = kv_idx < S;  // loads stay warp-convergent; only the stores are predicated
-      bf16* dv_row = dv + ((long long)seq * S + kv_idx) * ld_dkv + head * D;
-      bf16* dk_row = dk + ((long long)seq * S + kv_idx) * ld_dkv + head * D;
+      bf16* dv_row = dv + ((long long)seq * S + kv_idx) * ld_dkv + kv_head * D;
+      bf16* dk_row = dk + ((long long)seq * S + kv_idx) * ld_dkv + kv_head * D;
 #pragma unroll 1
       for (int ch = 0; ch < 4; ++ch) {
         uint32_t a[32], b[32];
@@ -552,7 +559,7 @@ static int make_qkv_tmap(CUtensorMap* tm, const void* ptr, long long ld, int nse
 
 template <int D, bool CAUSAL>
 static int launch_att_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, bf16* out,
-                          long long ld_out, float* lse, int nseq, int S, int n_heads, float scale,
+                          long long ld_out, float* lse, int nseq, int S, int n_heads, int kv_group, float scale,
                           cudaStream_t st) {
   using Cfg = AttFwdCfg<D>;
   auto kern = attention_fwd_kernel<D, CAUSAL>;
@@ -562,7 +569,7 @@ static int launch_att_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CU
     configured = true;
   }
   dim3 grid((S + ATT_BQ - 1) / ATT_BQ, n_heads, nseq);
-  kern<<<grid, 160, Cfg::SMEM_BYTES, st>>>(tq, tk, tv, out, ld_out, lse, S, n_heads, scale);
+  kern<<<grid, 160, Cfg::SMEM_BYTES, st>>>(tq, tk, tv, out, ld_out, lse, S, n_heads, kv_group, scale);
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -571,33 +578,49 @@ static int launch_att_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CU
 
 using namespace b200;
 
+static int attention_fwd_impl(const void* q, const void* k, const void* v, long long ld_qkv, void* out,
+                              long long ld_out, float* lse, int nseq, int S, int n_heads, int n_kv_heads,
+                              int head_dim, int causal, float scale, void* stream) {
+  B200_REQUIRE(head_dim == 128 || head_dim == 64, "attention_fwd: head_dim %d not in {64,128}", head_dim);
+  B200_REQUIRE(ld_qkv % 8 == 0 && ld_out % 8 == 0, "attention_fwd: ld must be a multiple of 8");
+  B200_REQUIRE(n_kv_heads > 0 && n_heads % n_kv_heads == 0, "attention_fwd: n_heads %d not a multiple of n_kv_heads %d",
+               n_heads, n_kv_heads);
+  CUtensorMap tq, tk, tv;
+  int rc;
+  if ((rc = make_qkv_tmap(&tq, q, ld_qkv, nseq, S, n_heads * head_dim))) return rc;
+  if ((rc = make_qkv_tmap(&tk, k, ld_qkv, nseq, S, n_kv_heads * head_dim))) return rc;
+  if ((rc = make_qkv_tmap(&tv, v, ld_qkv, nseq, S, n_kv_heads * head_dim))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int g = n_heads / n_kv_heads;
+  if (head_dim == 128) {
+    return causal ? launch_att_fwd<128, true>(tq, tk, tv, (bf16*)out, ld_out, lse, nseq, S, n_heads, g, scale, st)
+                  : launch_att_fwd<128, false>(tq, tk, tv, (bf16*)out, ld_out, lse, nseq, S, n_heads, g, scale, st);
+  }
+  return causal ? launch_att_fwd<64, true>(tq, tk, tv, (bf16*)out, ld_out, lse, nseq, S, n_heads, g, scale, st)
+                : launch_att_fwd<64, false>(tq, tk, tv, (bf16*)out, ld_out, lse, nseq, S, n_heads, g, scale, st);
+}
+
 extern "C" int rlaifv_attention_fwd(const void* q, const void* k, const void* v, long long ld_qkv, void* out,
                                     long long ld_out, float* lse, int nseq, int S, int n_heads, int head_dim,
                                     int causal, float scale, void* stream) {
-  B200_REQUIRE(head_dim == 128 || head_dim == 64, "attention_fwd: head_dim %d not in {64,128}", head_dim);
-  B200_REQUIRE(ld_qkv % 8 == 0 && ld_out % 8 == 0, "attention_fwd: ld must be a multiple of 8");
-  CUtensorMap tq, tk, tv;
-  const int cols = n_heads * head_dim;
-  int rc;
-  if ((rc = make_qkv_tmap(&tq, q, ld_qkv, nseq, S, cols))) return rc;
-  if ((rc = make_qkv_tmap(&tk, k, ld_qkv, nseq, S, cols))) return rc;
-  if ((rc = make_qkv_tmap(&tv, v, ld_qkv, nseq, S, cols))) return rc;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (head_dim == 128) {
-    return causal ? launch_att_fwd<128, true>(tq, tk, tv, (bf16*)out, ld_out, lse, nseq, S, n_heads, scale, st)
-                  : launch_att_fwd<128, false>(tq, tk, tv, (bf16*)out, ld_out, lse, nseq, S, n_heads, scale, st);
-  }
-  return causal ? launch_att_fwd<64, true>(tq, tk, tv, (bf16*)out, ld_out, lse, nseq, S, n_heads, scale, st)
-                : launch_att_fwd<64, false>(tq, tk, tv, (bf16*)out, ld_out, lse, nseq, S, n_heads, scale, st);
+  return attention_fwd_impl(q, k, v, ld_qkv, out, ld_out, lse, nseq, S, n_heads, n_heads, head_dim, causal, scale,
+                            stream);
+}
+// grouped-query attention: k/v hold n_kv_heads heads, query head h reads kv head h / (n_heads / n_kv_heads)
+extern "C" int rlaifv_attention_fwd_gqa(const void* q, const void* k, const void* v, long long ld_qkv, void* out,
+                                        long long ld_out, float* lse, int nseq, int S, int n_heads, int n_kv_heads,
+                                        int head_dim, int causal, float scale, void* stream) {
+  return attention_fwd_impl(q, k, v, ld_qkv, out, ld_out, lse, nseq, S, n_heads, n_kv_heads, head_dim, causal, scale,
+                            stream);
 }
 
-// dq_f32 [nseq*S][n_heads*128] must be zeroed by the caller; delta_ws fp32 [nseq*n_heads*S].
-extern "C" int rlaifv_attention_bwd(const void* q, const void* k, const void* v, long long ld_qkv,
-                                    const void* out, long long ld_out, const void* d_out, long long ld_dout,
-                                    const float* lse, float* dq_f32, void* dk, void* dv, long long ld_dkv,
-                                    float* delta_ws, int nseq, int S, int n_heads, int head_dim, float scale,
-                                    void* stream) {
+static int attention_bwd_impl(const void* q, const void* k, const void* v, long long ld_qkv, const void* out,
+                              long long ld_out, const void* d_out, long long ld_dout, const float* lse, float* dq_f32,
+                              void* dk, void* dv, long long ld_dkv, float* delta_ws, int nseq, int S, int n_heads,
+                              int n_kv_heads, int head_dim, float scale, void* stream) {
   B200_REQUIRE(head_dim == 128, "attention_bwd: head_dim must be 128 (got %d)", head_dim);
+  B200_REQUIRE(n_kv_heads > 0 && n_heads % n_kv_heads == 0, "attention_bwd: bad head counts %d / %d", n_heads,
+               n_kv_heads);
   cudaStream_t st = (cudaStream_t)stream;
   {
     const long long total = (long long)nseq * S * n_heads;
@@ -608,21 +631,40 @@ extern "C" int rlaifv_attention_bwd(const void* q, const void* k, const void* v,
     B200_CHECK_CUDA(cudaGetLastError());
   }
   CUtensorMap tq, tk, tv, tdo;
-  const int cols = n_heads * head_dim;
   int rc;
-  if ((rc = make_qkv_tmap(&tq, q, ld_qkv, nseq, S, cols))) return rc;
-  if ((rc = make_qkv_tmap(&tk, k, ld_qkv, nseq, S, cols))) return rc;
-  if ((rc = make_qkv_tmap(&tv, v, ld_qkv, nseq, S, cols))) return rc;
-  if ((rc = make_qkv_tmap(&tdo, d_out, ld_dout, nseq, S, cols))) return rc;
+  if ((rc = make_qkv_tmap(&tq, q, ld_qkv, nseq, S, n_heads * head_dim))) return rc;
+  if ((rc = make_qkv_tmap(&tk, k, ld_qkv, nseq, S, n_kv_heads * head_dim))) return rc;
+  if ((rc = make_qkv_tmap(&tv, v, ld_qkv, nseq, S, n_kv_heads * head_dim))) return rc;
+  if ((rc = make_qkv_tmap(&tdo, d_out, ld_dout, nseq, S, n_heads * head_dim))) return rc;
   static bool configured = false;
   if (!configured) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)AttBwdCfg::SMEM_BYTES));
     configured = true;
   }
-  dim3 grid((S + 127) / 128, n_heads, nseq);
-  attention_bwd_kernel<<<grid, 160, AttBwdCfg::SMEM_BYTES, st>>>(tq, tk, tv, tdo, lse, delta_ws, dq_f32,
-                                                                 (bf16*)dk, (bf16*)dv, ld_dkv, S, n_heads, scale);
+  dim3 grid((S + 127) / 128, n_kv_heads, nseq);
+  attention_bwd_kernel<<<grid, 160, AttBwdCfg::SMEM_BYTES, st>>>(tq, tk, tv, tdo, lse, delta_ws, dq_f32, (bf16*)dk,
+                                                                 (bf16*)dv, ld_dkv, S, n_heads, n_heads / n_kv_heads,
+                                                                 scale);
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+// dq_f32 [nseq*S][n_heads*128] must be zeroed by the caller; delta_ws fp32 [nseq*n_heads*S].
+extern "C" int rlaifv_attention_bwd(const void* q, const void* k, const void* v, long long ld_qkv,
+                                    const void* out, long long ld_out, const void* d_out, long long ld_dout,
+                                    const float* lse, float* dq_f32, void* dk, void* dv, long long ld_dkv,
+                                    float* delta_ws, int nseq, int S, int n_heads, int head_dim, float scale,
+                                    void* stream) {
+  return attention_bwd_impl(q, k, v, ld_qkv, out, ld_out, d_out, ld_dout, lse, dq_f32, dk, dv, ld_dkv, delta_ws, nseq,
+                            S, n_heads, n_heads, head_dim, scale, stream);
+}
+// GQA: dk/dv hold n_kv_heads heads (sum over the query heads of each group is formed in TMEM).
+extern "C" int rlaifv_attention_bwd_gqa(const void* q, const void* k, const void* v, long long ld_qkv,
+                                        const void* out, long long ld_out, const void* d_out, long long ld_dout,
+                                        const float* lse, float* dq_f32, void* dk, void* dv, long long ld_dkv,
+                                        float* delta_ws, int nseq, int S, int n_heads, int n_kv_heads, int head_dim,
+                                        float scale, void* stream) {
+  return attention_bwd_impl(q, k, v, ld_qkv, out, ld_out, d_out, ld_dout, lse, dq_f32, dk, dv, ld_dkv, delta_ws, nseq,
+                            S, n_heads, n_kv_heads, head_dim, scale, stream);
 }

@@ -238,22 +238,21 @@ layernorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
 // of the fused qkv buffer [M][3*nh*D]; token m has position m % T.
 // ------------------------------------------------------------------------------------------------
 __global__ void rope_fwd_kernel(bf16* __restrict__ qkv, const bf16* __restrict__ cosb,
-                                const bf16* __restrict__ sinb, long long M, int T, int nh, int D,
+                                const bf16* __restrict__ sinb, long long M, int T, int nrot, int D,
                                 long long ld) {
-  // one thread handles 8 consecutive i in [0, D/2) for one (row, q|k, head)
+  // one thread handles 8 consecutive i in [0, D/2) for one (row, rotated head); the nrot = n_heads + n_kv_heads
+  // rotated heads (q block then k block) are contiguous in the fused qkv row
   const int half = D >> 1;
   const int per_head = half >> 3;
-  const long long total = M * 2 * nh * per_head;
+  const long long total = M * nrot * per_head;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int c8 = (int)(idx % per_head);
     long long r = idx / per_head;
-    const int head = (int)(r % nh);
-    r /= nh;
-    const int which = (int)(r % 2);
-    const long long row = r / 2;
+    const int head = (int)(r % nrot);
+    const long long row = r / nrot;
     const int pos = (int)(row % T);
-    bf16* p = qkv + row * ld + (long long)which * nh * D + head * D + c8 * 8;
+    bf16* p = qkv + row * ld + (long long)head * D + c8 * 8;
     float x1[8], x2[8], c1[8], s1[8], c2[8], s2[8];
     load8(p, x1);
     load8(p + half, x2);
@@ -276,22 +275,21 @@ __global__ void rope_fwd_kernel(bf16* __restrict__ qkv, const bf16* __restrict__
 //   dx1 = dy1*cos1 + dy2*sin2 ; dx2 = dy2*cos2 - dy1*sin1
 __global__ void rope_bwd_kernel(bf16* __restrict__ dqkv, const float* __restrict__ dq_f32,
                                 const bf16* __restrict__ cosb, const bf16* __restrict__ sinb,
-                                long long M, int T, int nh, int D, long long ld) {
+                                long long M, int T, int nh, int nkv, int D, long long ld) {
   const int half = D >> 1;
   const int per_head = half >> 3;
-  const long long total = M * 2 * nh * per_head;
+  const int nrot = nh + nkv;
+  const long long total = M * nrot * per_head;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int c8 = (int)(idx % per_head);
     long long r = idx / per_head;
-    const int head = (int)(r % nh);
-    r /= nh;
-    const int which = (int)(r % 2);
-    const long long row = r / 2;
+    const int head = (int)(r % nrot);
+    const long long row = r / nrot;
     const int pos = (int)(row % T);
-    bf16* p = dqkv + row * ld + (long long)which * nh * D + head * D + c8 * 8;
+    bf16* p = dqkv + row * ld + (long long)head * D + c8 * 8;
     float y1[8], y2[8], c1[8], s1[8], c2[8], s2[8];
-    if (which == 0) {
+    if (head < nh) {
       const float* q = dq_f32 + row * (long long)nh * D + head * D + c8 * 8;
       float4 a = *reinterpret_cast<const float4*>(q), b = *reinterpret_cast<const float4*>(q + 4);
       float4 c = *reinterpret_cast<const float4*>(q + half), d = *reinterpret_cast<const float4*>(q + half + 4);
@@ -853,23 +851,42 @@ extern "C" int rlaifv_layernorm_fwd(const void* x, const void* w, const void* b,
   return 0;
 }
 
-extern "C" int rlaifv_rope_fwd(void* qkv, const void* cos_tab, const void* sin_tab, long long M, int T,
-                               int n_heads, int head_dim, long long ld, void* stream) {
+static int rope_fwd_impl(void* qkv, const void* cos_tab, const void* sin_tab, long long M, int T, int n_heads,
+                         int n_kv_heads, int head_dim, long long ld, void* stream) {
   B200_REQUIRE(head_dim % 16 == 0, "rope: head_dim %% 16 != 0");
-  const long long total = M * 2 * n_heads * (head_dim / 16);
+  const int nrot = n_heads + n_kv_heads;
+  const long long total = M * nrot * (head_dim / 16);
   rope_fwd_kernel<<<grid_for(total, 256), 256, 0, ST>>>((bf16*)qkv, (const bf16*)cos_tab, (const bf16*)sin_tab,
-                                                        M, T, n_heads, head_dim, ld);
+                                                        M, T, nrot, head_dim, ld);
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
-extern "C" int rlaifv_rope_bwd(void* dqkv, const float* dq_f32, const void* cos_tab, const void* sin_tab,
-                               long long M, int T, int n_heads, int head_dim, long long ld, void* stream) {
+static int rope_bwd_impl(void* dqkv, const float* dq_f32, const void* cos_tab, const void* sin_tab, long long M,
+                         int T, int n_heads, int n_kv_heads, int head_dim, long long ld, void* stream) {
   B200_REQUIRE(head_dim % 16 == 0, "rope: head_dim %% 16 != 0");
-  const long long total = M * 2 * n_heads * (head_dim / 16);
+  const long long total = M * (n_heads + n_kv_heads) * (head_dim / 16);
   rope_bwd_kernel<<<grid_for(total, 256), 256, 0, ST>>>((bf16*)dqkv, dq_f32, (const bf16*)cos_tab,
-                                                        (const bf16*)sin_tab, M, T, n_heads, head_dim, ld);
+                                                        (const bf16*)sin_tab, M, T, n_heads, n_kv_heads, head_dim, ld);
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+extern "C" int rlaifv_rope_fwd(void* qkv, const void* cos_tab, const void* sin_tab, long long M, int T,
+                               int n_heads, int head_dim, long long ld, void* stream) {
+  return rope_fwd_impl(qkv, cos_tab, sin_tab, M, T, n_heads, n_heads, head_dim, ld, stream);
+}
+extern "C" int rlaifv_rope_bwd(void* dqkv, const float* dq_f32, const void* cos_tab, const void* sin_tab,
+                               long long M, int T, int n_heads, int head_dim, long long ld, void* stream) {
+  return rope_bwd_impl(dqkv, dq_f32, cos_tab, sin_tab, M, T, n_heads, n_heads, head_dim, ld, stream);
+}
+// grouped-query layout: row = [q: n_heads*D | k: n_kv_heads*D | v: n_kv_heads*D]
+extern "C" int rlaifv_rope_fwd_gqa(void* qkv, const void* cos_tab, const void* sin_tab, long long M, int T,
+                                   int n_heads, int n_kv_heads, int head_dim, long long ld, void* stream) {
+  return rope_fwd_impl(qkv, cos_tab, sin_tab, M, T, n_heads, n_kv_heads, head_dim, ld, stream);
+}
+extern "C" int rlaifv_rope_bwd_gqa(void* dqkv, const float* dq_f32, const void* cos_tab, const void* sin_tab,
+                                   long long M, int T, int n_heads, int n_kv_heads, int head_dim, long long ld,
+                                   void* stream) {
+  return rope_bwd_impl(dqkv, dq_f32, cos_tab, sin_tab, M, T, n_heads, n_kv_heads, head_dim, ld, stream);
 }
 
 extern "C" int rlaifv_swiglu_fwd(const void* gu, void* act, long long M, int F, void* stream) {

@@ -58,6 +58,13 @@ _SIGNATURES = {
                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "rlaifv_adamw_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_ll, c_float, c_float,
                           c_float, c_float, c_float, c_int, c_float, c_void_p],
+    "rlaifv_attention_fwd_gqa": [c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_int, c_int,
+                                 c_int, c_int, c_int, c_int, c_float, c_void_p],
+    "rlaifv_attention_bwd_gqa": [c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                 c_float, c_void_p],
+    "rlaifv_rope_fwd_gqa": [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_ll, c_void_p],
+    "rlaifv_rope_bwd_gqa": [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_ll, c_void_p],
     "rlaifv_attention_fwd": [c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_int, c_int,
                              c_int, c_int, c_int, c_float, c_void_p],
     "rlaifv_attention_bwd": [c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_void_p,

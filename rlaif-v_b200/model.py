@@ -34,6 +34,7 @@ class LlavaDims:
     intermediate_size: int = 11008
     num_layers: int = 32
     num_heads: int = 32
+    num_kv_heads: int = 0          # 0 = num_heads; fewer = grouped-query attention (Mistral-7B: 32 / 8)
     rms_eps: float = 1e-5
     rope_theta: float = 10000.0
     max_len: int = 2048
@@ -49,6 +50,14 @@ class LlavaDims:
     @property
     def head_dim(self):
         return self.hidden_size // self.num_heads
+
+    @property
+    def kv_heads(self):
+        return self.num_kv_heads or self.num_heads
+
+    @property
+    def kv_size(self):
+        return self.kv_heads * self.head_dim
 
     @property
     def num_patches(self):
@@ -101,6 +110,7 @@ class ParamStore:
         self.dims = dims
         d = dims
         H, F, V, C = d.hidden_size, d.intermediate_size, d.vocab_size, d.clip_hidden
+        KV = d.kv_size
         self.buckets = []
         off = 0
 
@@ -122,7 +132,7 @@ class ParamStore:
         add_bucket("embed", [("embed", (V, H))], [])
         for i in range(d.num_layers):
             add_bucket(f"layer{i}",
-                       [(f"l{i}.qkv", (3 * H, H)), (f"l{i}.o", (H, H)), (f"l{i}.gu", (2 * F, H)),
+                       [(f"l{i}.qkv", (H + 2 * KV, H)), (f"l{i}.o", (H, H)), (f"l{i}.gu", (2 * F, H)),
                         (f"l{i}.down", (H, F))],
                        [(f"l{i}.ln1", (H,)), (f"l{i}.ln2", (H,))])
         add_bucket("head", [("lm_head", (V, H))], [("norm", (H,))])
@@ -141,7 +151,7 @@ class ParamStore:
     def hf_views(self):
         """HF state-dict name -> view into the fused storage (LlavaLlamaForCausalLM naming)."""
         d = self.dims
-        H, F = d.hidden_size, d.intermediate_size
+        H, F, KV = d.hidden_size, d.intermediate_size, d.kv_size
         out = {"model.embed_tokens.weight": self.p["embed"], "model.norm.weight": self.p["norm"],
                "lm_head.weight": self.p["lm_head"],
                "model.mm_projector.0.weight": self.p["proj.w0"], "model.mm_projector.0.bias": self.p["proj.b0"],
@@ -150,8 +160,8 @@ class ParamStore:
             pre = f"model.layers.{i}."
             qkv, gu = self.p[f"l{i}.qkv"], self.p[f"l{i}.gu"]
             out[pre + "self_attn.q_proj.weight"] = qkv[0:H]
-            out[pre + "self_attn.k_proj.weight"] = qkv[H:2 * H]
-            out[pre + "self_attn.v_proj.weight"] = qkv[2 * H:3 * H]
+            out[pre + "self_attn.k_proj.weight"] = qkv[H:H + KV]
+            out[pre + "self_attn.v_proj.weight"] = qkv[H + KV:H + 2 * KV]
             out[pre + "self_attn.o_proj.weight"] = self.p[f"l{i}.o"]
             out[pre + "mlp.gate_proj.weight"] = gu[0:F]
             out[pre + "mlp.up_proj.weight"] = gu[F:2 * F]
@@ -337,6 +347,8 @@ class LlavaDPOPolicy:
         self.lora = None             # LoraStore: base weights frozen, adapters + mm_projector trainable
 
     def enable_lora(self, r=64, alpha=16, seed=7, init_b_zero=True):
+        if self.dims.kv_heads != self.dims.num_heads:
+            raise NotImplementedError("LoRA adapters on a grouped-query decoder (unequal q/k/v widths)")
         self.lora = LoraStore(self.dims, self.device, r=r, alpha=alpha, seed=seed, init_b_zero=init_b_zero)
         return self.lora
 
@@ -489,8 +501,9 @@ class LlavaDPOPolicy:
         """32 x [RMSNorm -> fused qkv GEMM -> RoPE -> causal attention -> o GEMM(+res) -> RMSNorm ->
         fused gate|up GEMM -> SwiGLU -> down GEMM(+res)]; st (dict or None) receives the per-layer stash."""
         d, P, dev = self.dims, self.store.p, self.device
-        H, F = d.hidden_size, d.intermediate_size
-        nh, hd = d.num_heads, d.head_dim
+        H, F, KV = d.hidden_size, d.intermediate_size, d.kv_size
+        nh, hd, nkv = d.num_heads, d.head_dim, d.kv_heads
+        QKV = H + 2 * KV
         M = nseq * T
         cos, sin = self.rope_tables(T)
         scale = hd ** -0.5
@@ -500,7 +513,7 @@ class LlavaDPOPolicy:
             ls = None
             if keep_stash:
                 ls = {"x": x}
-                qkv = torch.empty((M, 3 * H), dtype=_BF, device=dev)
+                qkv = torch.empty((M, QKV), dtype=_BF, device=dev)
                 att = torch.empty((M, H), dtype=_BF, device=dev)
                 x2 = torch.empty((M, H), dtype=_BF, device=dev)
                 gu = torch.empty((M, 2 * F), dtype=_BF, device=dev)
@@ -509,7 +522,7 @@ class LlavaDPOPolicy:
                 rstd2 = torch.empty(M, dtype=_F32, device=dev)
                 lse = torch.empty((nseq, nh, T), dtype=_F32, device=dev)
             else:
-                qkv, att = self.buf("qkv", (M, 3 * H)), self.buf("att", (M, H))
+                qkv, att = self.buf("qkv", (M, QKV)), self.buf("att", (M, H))
                 x2, gu = self.buf("x2", (M, H)), self.buf("gu", (M, 2 * F))
                 x3 = self.buf("x3_%d" % (i & 1), (M, H))
                 rstd1 = rstd2 = None
@@ -519,8 +532,9 @@ class LlavaDPOPolicy:
                                  out=torch.empty((M, H), dtype=_BF, device=dev) if extra else self.buf("n", (M, H)),
                                  rstd=rstd1)
             self._lin_fwd(i, "qkv", n1, qkv, ls=ls if keep_stash else None)
-            ops.rope_fwd(qkv, cos, sin, T, nh, hd)
-            ops.attention_fwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], nseq, T, nh, hd, True, scale, out=att, lse=lse)
+            ops.rope_fwd(qkv, cos, sin, T, nh, hd, n_kv_heads=nkv)
+            ops.attention_fwd(qkv[:, :H], qkv[:, H:H + KV], qkv[:, H + KV:], nseq, T, nh, hd, True, scale, out=att,
+                              lse=lse, n_kv_heads=nkv)
             self._lin_fwd(i, "o", att, x2, residual=x, ls=ls if keep_stash else None)
             n2 = ops.rmsnorm_fwd(x2, P[f"l{i}.ln2"], d.rms_eps,
                                  out=torch.empty((M, H), dtype=_BF, device=dev) if extra else self.buf("n", (M, H)),
@@ -598,8 +612,8 @@ class LlavaDPOPolicy:
         dev = self.device
         nseq, T, b = st["nseq"], st["T"], st["b"]
         M = nseq * T
-        H, F, V = d.hidden_size, d.intermediate_size, d.vocab_size
-        nh, hd = d.num_heads, d.head_dim
+        H, F, V, KV = d.hidden_size, d.intermediate_size, d.vocab_size, d.kv_size
+        nh, hd, nkv = d.num_heads, d.head_dim, d.kv_heads
         scale = hd ** -0.5
         cos, sin = self.rope_tables(T)
         acc = bool(accumulate)
@@ -631,10 +645,11 @@ class LlavaDPOPolicy:
             qkv = ls["qkv"]
             dq32 = self.buf("dq32", (M, H), _F32)
             dq32.zero_()
-            dqkv = self.buf("dqkv", (M, 3 * H))
-            ops.attention_bwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], ls["att"], datt, ls["lse"], nseq, T, nh, hd,
-                              scale, dq32, dqkv[:, H:2 * H], dqkv[:, 2 * H:], self.buf("delta", (nseq, nh, T), _F32))
-            ops.rope_bwd(dqkv, dq32, cos, sin, T, nh, hd)
+            dqkv = self.buf("dqkv", (M, H + 2 * KV))
+            ops.attention_bwd(qkv[:, :H], qkv[:, H:H + KV], qkv[:, H + KV:], ls["att"], datt, ls["lse"], nseq, T, nh, hd,
+                              scale, dq32, dqkv[:, H:H + KV], dqkv[:, H + KV:], self.buf("delta", (nseq, nh, T), _F32),
+                              n_kv_heads=nkv)
+            ops.rope_bwd(dqkv, dq32, cos, sin, T, nh, hd, n_kv_heads=nkv)
             n1 = ls["n1"] if "n1" in ls else ops.rmsnorm_fwd(ls["x"], P[f"l{i}.ln1"], d.rms_eps,
                                                              out=self.buf("n", (M, H)))             # recompute
             dn1 = self._lin_bwd(i, "qkv", dqkv, n1, self.buf("dn", (M, H)), ls, acc)

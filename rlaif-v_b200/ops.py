@@ -59,8 +59,9 @@ def gemm(a, b, out=None, *, a_mn=False, b_mn=False, bias=None, residual=None, ac
     return out
 
 
-def attention_fwd(q, k, v, nseq, S, n_heads, head_dim, causal, scale, out=None, lse=None):
-    """q/k/v: [nseq*S, ld] views (column blocks allowed) sharing one row stride."""
+def attention_fwd(q, k, v, nseq, S, n_heads, head_dim, causal, scale, out=None, lse=None, n_kv_heads=None):
+    """q/k/v: [nseq*S, ld] views (column blocks allowed) sharing one row stride.
+    n_kv_heads < n_heads: grouped-query attention (k/v hold n_kv_heads heads)."""
     _chk(q), _chk(k), _chk(v)
     assert q.stride(0) == k.stride(0) == v.stride(0) and q.stride(1) == 1
     M = nseq * S
@@ -68,18 +69,28 @@ def attention_fwd(q, k, v, nseq, S, n_heads, head_dim, causal, scale, out=None, 
         out = torch.empty((M, n_heads * head_dim), dtype=torch.bfloat16, device=q.device)
     if lse is None:
         lse = torch.empty((nseq, n_heads, S), dtype=torch.float32, device=q.device)
+    if n_kv_heads is not None and n_kv_heads != n_heads:
+        _l.call("rlaifv_attention_fwd_gqa", _l.ptr(q), _l.ptr(k), _l.ptr(v), q.stride(0), _l.ptr(out), out.stride(0),
+                _l.ptr(lse), nseq, S, n_heads, n_kv_heads, head_dim, int(causal), float(scale), _l.stream_ptr())
+        return out, lse
     _l.call("rlaifv_attention_fwd", _l.ptr(q), _l.ptr(k), _l.ptr(v), q.stride(0), _l.ptr(out), out.stride(0),
             _l.ptr(lse), nseq, S, n_heads, head_dim, int(causal), float(scale), _l.stream_ptr())
     return out, lse
 
 
-def attention_bwd(q, k, v, out, d_out, lse, nseq, S, n_heads, head_dim, scale, dq_f32, dk, dv, delta_ws=None):
+def attention_bwd(q, k, v, out, d_out, lse, nseq, S, n_heads, head_dim, scale, dq_f32, dk, dv, delta_ws=None,
+                  n_kv_heads=None):
     """dq_f32 [M, n_heads*head_dim] fp32 must be zeroed; dk/dv bf16 views with a shared row stride."""
     _chk(q), _chk(k), _chk(v), _chk(out), _chk(d_out), _chk(dk), _chk(dv)
     _chk(dq_f32, torch.float32), _chk(lse, torch.float32)
     assert dk.stride(0) == dv.stride(0)
     if delta_ws is None:
         delta_ws = torch.empty((nseq, n_heads, S), dtype=torch.float32, device=q.device)
+    if n_kv_heads is not None and n_kv_heads != n_heads:
+        _l.call("rlaifv_attention_bwd_gqa", _l.ptr(q), _l.ptr(k), _l.ptr(v), q.stride(0), _l.ptr(out), out.stride(0),
+                _l.ptr(d_out), d_out.stride(0), _l.ptr(lse), _l.ptr(dq_f32), _l.ptr(dk), _l.ptr(dv), dk.stride(0),
+                _l.ptr(delta_ws), nseq, S, n_heads, n_kv_heads, head_dim, float(scale), _l.stream_ptr())
+        return dq_f32, dk, dv
     _l.call("rlaifv_attention_bwd", _l.ptr(q), _l.ptr(k), _l.ptr(v), q.stride(0), _l.ptr(out), out.stride(0),
             _l.ptr(d_out), d_out.stride(0), _l.ptr(lse), _l.ptr(dq_f32), _l.ptr(dk), _l.ptr(dv), dk.stride(0),
             _l.ptr(delta_ws), nseq, S, n_heads, head_dim, float(scale), _l.stream_ptr())
@@ -134,17 +145,17 @@ def layernorm_fwd(x, w, b, eps, out=None):
     return out
 
 
-def rope_fwd(qkv, cos, sin, T, n_heads, head_dim):
+def rope_fwd(qkv, cos, sin, T, n_heads, head_dim, n_kv_heads=None):
     _chk(qkv), _chk(cos), _chk(sin)
-    _l.call("rlaifv_rope_fwd", _l.ptr(qkv), _l.ptr(cos), _l.ptr(sin), qkv.shape[0], T, n_heads, head_dim,
-            qkv.stride(0), _l.stream_ptr())
+    _l.call("rlaifv_rope_fwd_gqa", _l.ptr(qkv), _l.ptr(cos), _l.ptr(sin), qkv.shape[0], T, n_heads,
+            n_heads if n_kv_heads is None else n_kv_heads, head_dim, qkv.stride(0), _l.stream_ptr())
     return qkv
 
 
-def rope_bwd(dqkv, dq_f32, cos, sin, T, n_heads, head_dim):
+def rope_bwd(dqkv, dq_f32, cos, sin, T, n_heads, head_dim, n_kv_heads=None):
     _chk(dqkv), _chk(dq_f32, _f32)
-    _l.call("rlaifv_rope_bwd", _l.ptr(dqkv), _l.ptr(dq_f32), _l.ptr(cos), _l.ptr(sin), dqkv.shape[0], T,
-            n_heads, head_dim, dqkv.stride(0), _l.stream_ptr())
+    _l.call("rlaifv_rope_bwd_gqa", _l.ptr(dqkv), _l.ptr(dq_f32), _l.ptr(cos), _l.ptr(sin), dqkv.shape[0], T,
+            n_heads, n_heads if n_kv_heads is None else n_kv_heads, head_dim, dqkv.stride(0), _l.stream_ptr())
     return dqkv
 
 

@@ -9,13 +9,14 @@ import torch
 from oracle import llava_dpo_oracle as O
 
 
-@pytest.mark.parametrize("use_lora", [False, True])
-def test_launch_sequence_dry_run(monkeypatch, use_lora):
+@pytest.mark.parametrize("use_lora,cfg_name", [(False, "TINY"), (True, "TINY"), (False, "TINY_GQA")])
+def test_launch_sequence_dry_run(monkeypatch, use_lora, cfg_name):
     from rlaifv_b200 import lib, ops
     from rlaifv_b200.model import LlavaDims, LlavaDPOPolicy
-    c = O.TINY
+    c = O.CONFIGS[cfg_name]
     dims = LlavaDims(vocab_size=c.vocab_size, hidden_size=c.hidden_size, intermediate_size=c.intermediate_size,
-                     num_layers=c.num_layers, num_heads=c.num_heads, clip_hidden=c.clip_hidden,
+                     num_layers=c.num_layers, num_heads=c.num_heads, num_kv_heads=c.num_kv_heads,
+                     clip_hidden=c.clip_hidden,
                      clip_intermediate=c.clip_intermediate, clip_layers=c.clip_layers, clip_heads=c.clip_heads,
                      image_size=c.image_size, patch_size=c.patch_size)
     calls = []
@@ -29,6 +30,10 @@ def test_launch_sequence_dry_run(monkeypatch, use_lora):
     monkeypatch.setattr(lib, "load", lambda: type("L", (), {"rlaifv_rmsnorm_bwd_partials": staticmethod(lambda: 4)})())
     monkeypatch.setattr(ops, "_chk", lambda t, dtype=None: t)
     pol = LlavaDPOPolicy(dims, "cpu", hf_state=O.make_params(c, seed=0))
+    if cfg_name == "TINY_GQA":
+        assert pol.store.p["l0.qkv"].shape == (512 + 2 * 256, 512)
+        with pytest.raises(NotImplementedError):
+            pol.enable_lora()
     if use_lora:
         pol.enable_lora(r=8, alpha=2.0)
     batch = O.synthetic_pair_batch(c, 2, 24, 30, seed=31, image_pos=7, ragged=True)
@@ -48,7 +53,10 @@ def test_launch_sequence_dry_run(monkeypatch, use_lora):
         assert "rlaifv_f32_to_bf16" in calls                # projected-image-row gradients still flow
     else:
         assert calls.count("rlaifv_gemm_bf16_dual") == 0
-    assert calls.count("rlaifv_attention_fwd") == dims.num_layers + dims.clip_layers_used
-    assert calls.count("rlaifv_attention_bwd") == dims.num_layers
+    gqa = dims.kv_heads != dims.num_heads
+    assert calls.count("rlaifv_attention_fwd") + calls.count("rlaifv_attention_fwd_gqa") == \
+        dims.num_layers + dims.clip_layers_used
+    assert calls.count("rlaifv_attention_fwd_gqa") == (dims.num_layers if gqa else 0)
+    assert calls.count("rlaifv_attention_bwd_gqa" if gqa else "rlaifv_attention_bwd") == dims.num_layers
     names = {b.name for b in pol.trainable_buckets()}
     assert ("projector" in names) and (("lora0" in names) == use_lora) and (("embed" in names) != use_lora)

@@ -272,3 +272,31 @@ def test_fused_adamw_matches_torch():
         ops.adamw_step(master, m, v, g, pbf, 1e-3, 0.9, 0.999, 1e-8, 0.01, step)
         assert rel(master, ref_p.detach()) <= 1e-5
         assert torch.equal(pbf, master.to(BF))
+
+
+def test_attention_grouped_query_forward_backward():
+    """GQA (4 query heads share 2 kv heads): forward and backward vs fp32 torch with repeat_interleave."""
+    from rlaifv_b200 import ops
+    nseq, S, nh, nkv, D = 2, 300, 4, 2, 128
+    H, KV = nh * D, nkv * D
+    qkv = torch.randn(nseq * S, H + 2 * KV, device=DEV).to(BF)
+    q_, k_, v_ = qkv[:, :H], qkv[:, H:H + KV], qkv[:, H + KV:]
+    scale = D ** -0.5
+    out, lse = ops.attention_fwd(q_, k_, v_, nseq, S, nh, D, True, scale, n_kv_heads=nkv)
+
+    def split(t, n):
+        return t.float().reshape(nseq, S, n, D).permute(0, 2, 1, 3).contiguous()
+    q, k, v = split(q_, nh).requires_grad_(), split(k_, nkv).requires_grad_(), split(v_, nkv).requires_grad_()
+    kk, vv = k.repeat_interleave(nh // nkv, dim=1), v.repeat_interleave(nh // nkv, dim=1)
+    s = (q @ kk.transpose(-1, -2) * scale).masked_fill(~torch.ones(S, S, device=DEV, dtype=torch.bool).tril(), float("-inf"))
+    ref = torch.softmax(s, -1) @ vv
+    assert rel(split(out, nh), ref) <= 2e-2 and rel(lse, torch.logsumexp(s, -1)) <= 1e-3
+    d_out = torch.randn(nseq * S, H, device=DEV).to(BF)
+    dq32 = torch.zeros(nseq * S, H, device=DEV)
+    dqkv = torch.zeros(nseq * S, H + 2 * KV, device=DEV, dtype=BF)
+    ops.attention_bwd(q_, k_, v_, out, d_out, lse, nseq, S, nh, D, scale, dq32, dqkv[:, H:H + KV], dqkv[:, H + KV:],
+                      n_kv_heads=nkv)
+    ref.backward(split(d_out, nh))
+    assert rel(split(dq32, nh), q.grad) <= 3e-2
+    assert rel(split(dqkv[:, H:H + KV], nkv), k.grad) <= 3e-2
+    assert rel(split(dqkv[:, H + KV:], nkv), v.grad) <= 3e-2

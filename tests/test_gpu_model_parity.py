@@ -19,11 +19,15 @@ pytestmark = pytest.mark.gpu
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
 
 
-def tiny_dims():
+def cfg_of(fx):
+    return O.CONFIGS[str(fx["cfg_name"])] if "cfg_name" in fx.files else O.TINY
+
+
+def tiny_dims(c=O.TINY):
     from rlaifv_b200.model import LlavaDims
-    c = O.TINY
     return LlavaDims(vocab_size=c.vocab_size, hidden_size=c.hidden_size, intermediate_size=c.intermediate_size,
-                     num_layers=c.num_layers, num_heads=c.num_heads, clip_hidden=c.clip_hidden,
+                     num_layers=c.num_layers, num_heads=c.num_heads, num_kv_heads=c.num_kv_heads,
+                     clip_hidden=c.clip_hidden,
                      clip_intermediate=c.clip_intermediate, clip_layers=c.clip_layers, clip_heads=c.clip_heads,
                      image_size=c.image_size, patch_size=c.patch_size)
 
@@ -31,12 +35,13 @@ def tiny_dims():
 _POL = {}
 
 
-def policy_for(scale):
+def policy_for(scale, cfg=O.TINY):
     from rlaifv_b200.model import LlavaDPOPolicy
-    if scale not in _POL:
-        params = O.make_params(O.TINY, seed=0, scale=scale)
-        _POL[scale] = (LlavaDPOPolicy(tiny_dims(), "cuda", hf_state=params), params)
-    return _POL[scale]
+    key = (scale, id(cfg))
+    if key not in _POL:
+        params = O.make_params(cfg, seed=0, scale=scale)
+        _POL[key] = (LlavaDPOPolicy(tiny_dims(cfg), "cuda", hf_state=params), params)
+    return _POL[key]
 
 
 def rel(a, b):
@@ -48,7 +53,8 @@ def rel(a, b):
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
 def test_forward_matches_reference_fixture(path):
     fx = np.load(path)
-    pol, params = policy_for(float(fx["param_scale"]))
+    cfg = cfg_of(fx)
+    pol, params = policy_for(float(fx["param_scale"]), cfg)
     assert abs(O.params_checksum(params) - float(fx["params_checksum"])) < 1e-6 * float(fx["params_checksum"])
     ids = torch.from_numpy(fx["concatenated_input_ids"])
     labels = torch.from_numpy(fx["concatenated_labels"])
@@ -59,7 +65,7 @@ def test_forward_matches_reference_fixture(path):
     assert torch.equal(out["labels"].cpu(), torch.from_numpy(fx["spliced_labels"]))
     # bf16-op-order oracle on the same bf16-rounded parameters
     pb = {k: v.to(torch.bfloat16) for k, v in params.items()}
-    ob = O.policy_logps(pb, O.TINY, ids, labels, images.to(torch.bfloat16))
+    ob = O.policy_logps(pb, cfg, ids, labels, images.to(torch.bfloat16))
     B = ids.shape[0] // 2
     logp = out["logp"].cpu()
     print("logp cuda", logp.tolist(), "oracle bf16", ob["logp"].tolist(),
@@ -96,7 +102,7 @@ def test_forward_matches_reference_fixture(path):
 def test_dpo_loss_and_grads_match_reference_fixture(path):
     from rlaifv_b200 import ops
     fx = np.load(path)
-    pol, params = policy_for(float(fx["param_scale"]))
+    pol, params = policy_for(float(fx["param_scale"]), cfg_of(fx))
     ids = torch.from_numpy(fx["concatenated_input_ids"])
     labels = torch.from_numpy(fx["concatenated_labels"])
     images = torch.from_numpy(fx["images"])

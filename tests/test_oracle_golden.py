@@ -22,10 +22,15 @@ def rel(a, b):
 _PARAMS = {}
 
 
-def params_for(scale):
-    if scale not in _PARAMS:
-        _PARAMS[scale] = O.make_params(O.TINY, seed=0, scale=scale)
-    return _PARAMS[scale]
+def cfg_of(fx):
+    return O.CONFIGS[str(fx["cfg_name"])] if "cfg_name" in fx.files else O.TINY
+
+
+def params_for(scale, cfg=O.TINY):
+    key = (scale, id(cfg))
+    if key not in _PARAMS:
+        _PARAMS[key] = O.make_params(cfg, seed=0, scale=scale)
+    return _PARAMS[key]
 
 
 @pytest.fixture(scope="module")
@@ -40,14 +45,15 @@ def test_fixtures_exist():
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
 def test_oracle_matches_reference_outputs(path):
     fx = np.load(path)
-    params = params_for(float(fx["param_scale"]))
+    cfg = cfg_of(fx)
+    params = params_for(float(fx["param_scale"]), cfg)
     assert abs(O.params_checksum(params) - float(fx["params_checksum"])) <= 1e-9 * float(fx["params_checksum"])
     p = {k: v.clone().requires_grad_(k.startswith(O.TRAINABLE_PREFIXES)) for k, v in params.items()}
     batch = dict(concatenated_input_ids=torch.from_numpy(fx["concatenated_input_ids"]),
                  concatenated_labels=torch.from_numpy(fx["concatenated_labels"]),
                  images=torch.from_numpy(fx["images"]),
                  ref_win_logp=torch.from_numpy(fx["ref_win_logp"]), ref_rej_logp=torch.from_numpy(fx["ref_rej_logp"]))
-    out = O.dpo_step(p, O.TINY, batch, beta=float(fx["beta"]))
+    out = O.dpo_step(p, cfg, batch, beta=float(fx["beta"]))
     # integer / copy work: bit exact
     assert torch.equal(out["labels"], torch.from_numpy(fx["spliced_labels"]))
     assert np.array_equal(out["inputs_embeds"].detach().double().sum(-1).numpy(), fx["spliced_embeds_rowsum"])
