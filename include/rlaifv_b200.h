@@ -115,6 +115,11 @@ int rlaifv_gelu_bwd(const void* pre, const void* dpost, void* dpre, long long n,
 int rlaifv_colsum(const void* x, long long M, int N, void* db, int accumulate, float* workspace_64xN,
                   void* stream);
 
+/* Dropout on the LoRA adapter input (peft lora.Linear, lora_dropout = 0.05, train_llava15_lora.py:115). The keep
+ * bit of element i is a stateless hash of (seed, i): dropout_bwd_add regenerates the mask (dx += keep ? g/(1-p) : 0). */
+int rlaifv_dropout_fwd(const void* x, void* out, long long n, float p, unsigned long long seed, void* stream);
+int rlaifv_dropout_bwd_add(void* dx, const void* g, long long n, float p, unsigned long long seed, void* stream);
+
 /* ---- CLIP embedding helpers (HF:clip/modeling_clip.py:202-219; clip_encoder.py:36-44) ----------- */
 int rlaifv_clip_im2col(const void* images, void* out, int n_img, int channels, int size, int patch,
                        int k_pad, void* stream);

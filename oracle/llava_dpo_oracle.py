@@ -309,7 +309,7 @@ LORA_TARGETS = ("self_attn.q_proj", "self_attn.k_proj", "self_attn.v_proj", "sel
                 "mlp.gate_proj", "mlp.up_proj", "mlp.down_proj")   # find_all_linear_names, train_llava15_lora.py:121-134
 
 
-def lora_linear(p, name, x, lora_scaling):
+def lora_linear(p, name, x, lora_scaling, x_adapter=None):
     """y = W x (+ (alpha/r) * B(A(x))) — peft 0.10.0 lora.Linear.forward with dropout p=0
     (muffin/train/train_llava15_lora.py:304-318: r=64, alpha=16; adapters live next to the base
     weight as `<name>.lora_A.weight` [r,in] / `<name>.lora_B.weight` [out,r]).
@@ -318,7 +318,8 @@ def lora_linear(p, name, x, lora_scaling):
     y = F.linear(x, p[name + ".weight"])
     a = p.get(name + ".lora_A.weight")
     if a is not None:
-        y = y + F.linear(F.linear(x, a), p[name + ".lora_B.weight"]) * lora_scaling
+        xa = x if x_adapter is None else x_adapter       # dropout(x) when a mask is supplied
+        y = y + F.linear(F.linear(xa, a), p[name + ".lora_B.weight"]) * lora_scaling
     return y
 
 
@@ -338,7 +339,7 @@ def make_lora_params(cfg: OracleConfig, r=8, seed=3, dtype=torch.float32, b_std=
     return out
 
 
-def llama_logits(p, inputs_embeds, cfg: OracleConfig, lora_scaling=0.25):
+def llama_logits(p, inputs_embeds, cfg: OracleConfig, lora_scaling=0.25, lora_drop=None):
     """inputs_embeds [nseq,T,H] -> logits [nseq,T,V] in fp32 (4.35.0 `logits.float()`).
 
     HF: llama/modeling_llama.py:303-333 (layer), :251-290 + :199-222 (attention: eager, causal mask
@@ -354,9 +355,15 @@ def llama_logits(p, inputs_embeds, cfg: OracleConfig, lora_scaling=0.25):
         r = x
         h = rms_norm(x, p[pre + "input_layernorm.weight"], cfg.rms_eps)
         nkv = cfg.kv_heads
-        q = lora_linear(p, pre + "self_attn.q_proj", h, lora_scaling).view(nseq, T, nh, hd).transpose(1, 2)
-        k = lora_linear(p, pre + "self_attn.k_proj", h, lora_scaling).view(nseq, T, nkv, hd).transpose(1, 2)
-        v = lora_linear(p, pre + "self_attn.v_proj", h, lora_scaling).view(nseq, T, nkv, hd).transpose(1, 2)
+
+        def dropped(t, group):
+            # lora_drop["<layer>.<group>"] = keep mask already scaled by 1/(1-p) (shape of t); None = no dropout
+            m = None if lora_drop is None else lora_drop.get(f"{i}.{group}")
+            return None if m is None else t * m.to(t.dtype)
+        hq = dropped(h, "qkv")
+        q = lora_linear(p, pre + "self_attn.q_proj", h, lora_scaling, hq).view(nseq, T, nh, hd).transpose(1, 2)
+        k = lora_linear(p, pre + "self_attn.k_proj", h, lora_scaling, hq).view(nseq, T, nkv, hd).transpose(1, 2)
+        v = lora_linear(p, pre + "self_attn.v_proj", h, lora_scaling, hq).view(nseq, T, nkv, hd).transpose(1, 2)
         q = q * cos + rotate_half(q) * sin
         k = k * cos + rotate_half(k) * sin
         if nkv != nh:   # HF repeat_kv (llama/modeling_llama.py:171-180): kv head j serves query heads j*g .. j*g+g-1
@@ -365,12 +372,14 @@ def llama_logits(p, inputs_embeds, cfg: OracleConfig, lora_scaling=0.25):
         w = torch.matmul(q, k.transpose(2, 3)) * (hd ** -0.5) + causal
         w = F.softmax(w, dim=-1, dtype=torch.float32).to(q.dtype)
         a = torch.matmul(w, v).transpose(1, 2).reshape(nseq, T, H)
-        x = r + lora_linear(p, pre + "self_attn.o_proj", a, lora_scaling)
+        x = r + lora_linear(p, pre + "self_attn.o_proj", a, lora_scaling, dropped(a, "o"))
         r = x
         h = rms_norm(x, p[pre + "post_attention_layernorm.weight"], cfg.rms_eps)
-        g = lora_linear(p, pre + "mlp.gate_proj", h, lora_scaling)
-        u = lora_linear(p, pre + "mlp.up_proj", h, lora_scaling)
-        x = r + lora_linear(p, pre + "mlp.down_proj", F.silu(g) * u, lora_scaling)
+        hg = dropped(h, "gu")
+        g = lora_linear(p, pre + "mlp.gate_proj", h, lora_scaling, hg)
+        u = lora_linear(p, pre + "mlp.up_proj", h, lora_scaling, hg)
+        act = F.silu(g) * u
+        x = r + lora_linear(p, pre + "mlp.down_proj", act, lora_scaling, dropped(act, "down"))
     x = rms_norm(x, p["model.norm.weight"], cfg.rms_eps)
     return F.linear(x, p["lm_head.weight"]).float()
 
@@ -402,7 +411,7 @@ def dpo_loss(policy_chosen_logps, policy_rejected_logps, reference_chosen_logps,
     return losses, chosen_rewards, rejected_rewards
 
 
-def policy_logps(p, cfg, concatenated_input_ids, concatenated_labels, images, dedup_images=True):
+def policy_logps(p, cfg, concatenated_input_ids, concatenated_labels, images, dedup_images=True, lora_drop=None):
     """get_beta_and_logps' llava15 branch (muffin/train/trainers.py:185-231): images are repeated for
     the win and rej halves (identical copies, so encoding them once is exact)."""
     feats = clip_features(p, images, cfg)                       # [B, P, C]  (no grad)
@@ -411,7 +420,7 @@ def policy_logps(p, cfg, concatenated_input_ids, concatenated_labels, images, de
     src, new_labels, T = splice_index_map(concatenated_input_ids, concatenated_labels, cfg.num_patches,
                                           cfg.max_len)
     embeds = splice_embeds(p, concatenated_input_ids, src, image_features)
-    logits = llama_logits(p, embeds, cfg)
+    logits = llama_logits(p, embeds, cfg, lora_drop=lora_drop)
     per_tok, logp, avg = get_batch_logps(logits, new_labels)
     return dict(src=src, labels=new_labels, per_token_logps=per_tok, logp=logp, avg_logp=avg,
                 inputs_embeds=embeds, logits=logits)

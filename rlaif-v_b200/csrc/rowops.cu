@@ -803,6 +803,52 @@ __global__ void adamw_kernel(float* __restrict__ master, float* __restrict__ m, 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Dropout for the LoRA adapter input (peft lora.Linear: lora_B(lora_A(dropout(x))), p = 0.05 in
+// muffin/train/train_llava15_lora.py:115). Stateless counter-based RNG: the keep bit of element i
+// is a hash of (seed, i), so the backward regenerates the mask instead of storing it.
+//   fwd : out = keep ? bf16(x / (1-p)) : 0
+//   bwd : dx += keep ? g / (1-p) : 0
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mix32(uint64_t z) {   // splitmix64 finaliser, high word
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (uint32_t)(z >> 32);
+}
+__device__ __forceinline__ void keep_bits8(unsigned long long seed, long long chunk, uint32_t thresh, bool (&keep)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) keep[j] = mix32(seed ^ ((unsigned long long)(chunk * 8 + j) * 0xD1B54A32D192ED03ull)) >= thresh;
+}
+__global__ void dropout_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, long long n8, uint32_t thresh,
+                                   float inv_keep, unsigned long long seed) {
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n8;
+       idx += (long long)gridDim.x * blockDim.x) {
+    float v[8];
+    bool keep[8];
+    load8(x + idx * 8, v);
+    keep_bits8(seed, idx, thresh, keep);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = keep[j] ? v[j] * inv_keep : 0.f;
+    store8(out + idx * 8, v);
+  }
+}
+__global__ void dropout_bwd_add_kernel(bf16* __restrict__ dx, const bf16* __restrict__ g, long long n8, uint32_t thresh,
+                                       float inv_keep, unsigned long long seed) {
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n8;
+       idx += (long long)gridDim.x * blockDim.x) {
+    float a[8], b[8];
+    bool keep[8];
+    load8(dx + idx * 8, a);
+    load8(g + idx * 8, b);
+    keep_bits8(seed, idx, thresh, keep);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += keep[j] ? b[j] * inv_keep : 0.f;
+    store8(dx + idx * 8, a);
+  }
+}
+
 static inline int grid_for(long long work_items, int threads, int max_blocks_per_sm = 8) {
   long long blocks = (work_items + threads - 1) / threads;
   long long cap = (long long)num_sms() * max_blocks_per_sm;
@@ -1039,6 +1085,27 @@ extern "C" int rlaifv_adamw_step(float* master, float* exp_avg, float* exp_avg_s
   else
     adamw_kernel<false><<<grid, 256, 0, ST>>>(master, exp_avg, exp_avg_sq, grad, (bf16*)param_bf16, n, lr, beta1,
                                               beta2, eps, weight_decay, bc1, bc2_sqrt, grad_scale);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static inline uint32_t dropout_threshold(float p) {
+  double t = (double)p * 4294967296.0;
+  if (t < 0) t = 0;
+  if (t > 4294967295.0) t = 4294967295.0;
+  return (uint32_t)t;
+}
+extern "C" int rlaifv_dropout_fwd(const void* x, void* out, long long n, float p, unsigned long long seed, void* stream) {
+  B200_REQUIRE(n % 8 == 0 && p >= 0.f && p < 1.f, "dropout_fwd: n %% 8 != 0 or p outside [0,1)");
+  dropout_fwd_kernel<<<grid_for(n / 8, 256), 256, 0, ST>>>((const bf16*)x, (bf16*)out, n / 8, dropout_threshold(p),
+                                                           1.f / (1.f - p), seed);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int rlaifv_dropout_bwd_add(void* dx, const void* g, long long n, float p, unsigned long long seed, void* stream) {
+  B200_REQUIRE(n % 8 == 0 && p >= 0.f && p < 1.f, "dropout_bwd_add: n %% 8 != 0 or p outside [0,1)");
+  dropout_bwd_add_kernel<<<grid_for(n / 8, 256), 256, 0, ST>>>((bf16*)dx, (const bf16*)g, n / 8, dropout_threshold(p),
+                                                               1.f / (1.f - p), seed);
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -127,6 +127,8 @@ class DPOStepEngine:
         if optimizer_step:
             self.opt.finish_step()
             self.global_step += 1
+            if pol.lora is not None:
+                pol.lora.step = self.global_step
         return self._metrics
 
     def metrics_dict(self, metrics=None):

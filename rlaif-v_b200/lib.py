@@ -38,6 +38,8 @@ _SIGNATURES = {
     "rlaifv_swiglu_bwd": [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p],
     "rlaifv_gelu_fwd": [c_void_p, c_void_p, c_ll, c_void_p],
     "rlaifv_gelu_bwd": [c_void_p, c_void_p, c_void_p, c_ll, c_void_p],
+    "rlaifv_dropout_fwd": [c_void_p, c_void_p, c_ll, c_float, ctypes.c_ulonglong, c_void_p],
+    "rlaifv_dropout_bwd_add": [c_void_p, c_void_p, c_ll, c_float, ctypes.c_ulonglong, c_void_p],
     "rlaifv_colsum": [c_void_p, c_ll, c_int, c_void_p, c_int, c_void_p, c_void_p],
     "rlaifv_clip_im2col": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "rlaifv_clip_embed": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],

@@ -193,8 +193,11 @@ class LoraStore:
     A_o [r,H], B_o [H,r], A_gu [2r,H], B_g/B_u [F,r], A_d [r,F], B_d [H,r]. Adapters get weight decay like any
     other matrix (HF decay groups exclude only norms and biases)."""
 
-    def __init__(self, dims: LlavaDims, device, r=64, alpha=16, seed=7, init_b_zero=True):
+    def __init__(self, dims: LlavaDims, device, r=64, alpha=16, seed=7, init_b_zero=True, dropout=0.0):
         self.dims, self.r, self.scaling = dims, r, alpha / r
+        self.dropout = float(dropout)      # applied to the adapter input while training (peft lora_dropout)
+        self.rng_seed = 0x5EED0000 + seed
+        self.step = 0                      # advanced by the engine once per optimisation step
         H, F = dims.hidden_size, dims.intermediate_size
         self.buckets = []
         off = 0
@@ -346,11 +349,22 @@ class LlavaDPOPolicy:
         self._stash = None
         self.lora = None             # LoraStore: base weights frozen, adapters + mm_projector trainable
 
-    def enable_lora(self, r=64, alpha=16, seed=7, init_b_zero=True):
+    def enable_lora(self, r=64, alpha=16, seed=7, init_b_zero=True, dropout=0.0):
         if self.dims.kv_heads != self.dims.num_heads:
             raise NotImplementedError("LoRA adapters on a grouped-query decoder (unequal q/k/v widths)")
-        self.lora = LoraStore(self.dims, self.device, r=r, alpha=alpha, seed=seed, init_b_zero=init_b_zero)
+        self.lora = LoraStore(self.dims, self.device, r=r, alpha=alpha, seed=seed, init_b_zero=init_b_zero,
+                              dropout=dropout)
         return self.lora
+
+    training = True
+
+    def _lora_seed(self, i, group):
+        """One dropout stream per (optimisation step, micro-batch forward, layer, linear group)."""
+        L = self.lora
+        g = ("qkv", "o", "gu", "down").index(group)
+        return (L.rng_seed * 1000003 + L.step) * 4099 + (self._fwd_count * 131 + i) * 4 + g
+
+    _fwd_count = 0
 
     # ---- what the optimizer trains / in which order the forward needs it ----
     def trainable_buckets(self):
@@ -384,7 +398,13 @@ class LlavaDPOPolicy:
         M = x.shape[0]
         t = torch.empty((M, A.shape[0]), dtype=_BF, device=self.device) if ls is not None else \
             self.buf("lora_t_" + group, (M, A.shape[0]))
-        ops.gemm(x, A, t, alpha=L.scaling)
+        xa = x
+        if L.dropout > 0.0 and self.training and ls is not None:
+            # the sub-linears of a fused group share one mask (peft draws one per adapter; same marginal law)
+            seed = self._lora_seed(i, group)
+            xa = ops.dropout_fwd(x, L.dropout, seed, out=self.buf("lora_xd_%d" % x.shape[1], tuple(x.shape)))
+            ls["seed_" + group] = seed
+        ops.gemm(xa, A, t, alpha=L.scaling)
         n_sub = out.shape[1] // len(b_names) if len(b_names) > 1 else 0
         ops.gemm_dual(x, W, t, L.p[f"l{i}.{bcat}"], out, k2=L.r, r=L.r, n_sub=n_sub, residual=residual)
         if ls is not None:
@@ -408,6 +428,14 @@ class LlavaDPOPolicy:
             dy_j = dy[:, j * n_out:(j + 1) * n_out]
             ops.gemm(dy_j, L.p[f"l{i}.{bn}"], dt[:, j * r:(j + 1) * r], b_mn=True, alpha=L.scaling)   # dt_j = s dy_j B_j
             ops.gemm(dy_j, t[:, j * r:(j + 1) * r], L.g[f"l{i}.{bn}"], a_mn=True, b_mn=True, accumulate=acc)  # dB_j
+        seed = ls.get("seed_" + group)
+        if seed is not None:
+            # dropout on the adapter input: dA sees the dropped input, and the adapter's dx passes through the mask
+            xd = ops.dropout_fwd(x, L.dropout, seed, out=self.buf("lora_xd_%d" % x.shape[1], tuple(x.shape)))
+            ops.gemm(dt, xd, L.g[f"l{i}.{a_name}"], a_mn=True, b_mn=True, accumulate=acc)             # dA = dt^T drop(x)
+            ops.gemm(dy, W, dx_out, b_mn=True)
+            pa = ops.gemm(dt, A, self.buf("lora_xd_%d" % x.shape[1], tuple(x.shape)), b_mn=True)                       # dt @ A
+            return ops.dropout_bwd_add(dx_out, pa, L.dropout, seed)
         ops.gemm(dt, x, L.g[f"l{i}.{a_name}"], a_mn=True, b_mn=True, accumulate=acc)                  # dA = dt^T x
         # dx = dy @ W + dt @ A in one pass (second source = stacked lora_A, MN-major like W)
         return ops.gemm_dual(dy, W, dt, A, dx_out, k2=A.shape[0], r=r, n_sub=0, b_mn=True)
@@ -574,6 +602,7 @@ class LlavaDPOPolicy:
         H, F, V = d.hidden_size, d.intermediate_size, d.vocab_size
         nh, hd = d.num_heads, d.head_dim
         st = {"layers": []} if keep_stash else None
+        self._fwd_count += 1
 
         feats = self.encode_images(images)                                   # [b*Pn, C]
         self._need("projector")

@@ -339,3 +339,20 @@ def gemm_dual(a, b, a2, b2, out, *, k2, r, n_sub=0, b_mn=False, residual=None, a
             _l.ptr(None), _l.ptr(residual), residual.stride(0) if residual is not None else 0, 0, int(accumulate),
             _l.stream_ptr())
     return out
+
+
+def dropout_fwd(x, p, seed, out=None):
+    _chk(x)
+    assert x.is_contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    _l.call("rlaifv_dropout_fwd", _l.ptr(x), _l.ptr(out), x.numel(), float(p), int(seed), _l.stream_ptr())
+    return out
+
+
+def dropout_bwd_add(dx, g, p, seed):
+    """dx += mask(seed) * g / (1 - p), the mask of dropout_fwd with the same seed."""
+    _chk(dx), _chk(g)
+    assert dx.is_contiguous() and g.is_contiguous() and dx.numel() == g.numel()
+    _l.call("rlaifv_dropout_bwd_add", _l.ptr(dx), _l.ptr(g), dx.numel(), float(p), int(seed), _l.stream_ptr())
+    return dx

@@ -155,7 +155,7 @@ def safe_save_model_for_hf_trainer(trainer, output_dir):
             torch.save(ad, os.path.join(output_dir, "adapter_model.bin"))
             with open(os.path.join(output_dir, "adapter_config.json"), "w") as f:
                 json.dump({"peft_type": "LORA", "r": pol.lora.r, "lora_alpha": pol.lora.scaling * pol.lora.r,
-                           "lora_dropout": 0.0, "bias": "none", "task_type": "CAUSAL_LM",
+                           "lora_dropout": pol.lora.dropout, "bias": "none", "task_type": "CAUSAL_LM",
                            "target_modules": ["q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj",
                                               "down_proj"]}, f)
             non_lora = {"base_model.model." + k: v.cpu() for k, v in trainer.model.state_dict().items()
@@ -187,10 +187,8 @@ def init_model(model_args, data_args, training_args, attn_implementation=None):
     model = LlavaLlamaForCausalLM(dims, torch.device("cuda", local_rank), hf_state=state)
     model.config.use_cache = False
     if training_args.lora_enable:
-        if training_args.lora_dropout != 0.0:
-            print("note: lora_dropout=%g requested; the B200 adapter path runs dropout-free (p=0)" %
-                  training_args.lora_dropout)
-        model.policy.enable_lora(r=training_args.lora_r, alpha=training_args.lora_alpha)
+        model.policy.enable_lora(r=training_args.lora_r, alpha=training_args.lora_alpha,
+                                 dropout=training_args.lora_dropout)
     tokenizer = load_tokenizer(model_args.model_name_or_path, training_args.model_max_length)
     data_args.is_multimodal = True
     data_args.image_token_len = dims.num_patches

@@ -97,3 +97,60 @@ def test_lora_engine_step_updates_only_adapters_and_projector():
     assert bool(changed[proj.start:proj.start + proj.size].any())
     changed[proj.start:proj.start + proj.size] = False
     assert not bool(changed.any())                      # base weights, embeddings, norms, lm_head frozen
+
+
+def test_lora_dropout_kernels():
+    from rlaifv_b200 import ops
+    x = torch.randn(1 << 16, 64, device="cuda").to(torch.bfloat16)
+    p = 0.05
+    a = ops.dropout_fwd(x, p, seed=1234)
+    b = ops.dropout_fwd(x, p, seed=1234)
+    c = ops.dropout_fwd(x, p, seed=1235)
+    assert torch.equal(a, b) and not torch.equal(a, c)                     # deterministic per seed
+    dropped = (a == 0) & (x != 0)
+    frac = float(dropped.float().mean())
+    assert abs(frac - p) < 2e-3                                            # 4M samples: sigma ~ 1e-4
+    kept = ~dropped
+    assert torch.equal(a[kept], (x.float()[kept] / (1 - p)).to(torch.bfloat16))
+    g = torch.randn_like(x)
+    dx = torch.zeros_like(x)
+    ops.dropout_bwd_add(dx, g, p, seed=1234)
+    assert torch.equal(dx != 0, kept & (g != 0))                           # same mask as the forward
+    assert torch.equal(dx[kept], (g.float()[kept] / (1 - p)).to(torch.bfloat16))
+
+
+def test_lora_with_dropout_matches_oracle_given_the_same_masks():
+    """p = 0.25: the CUDA path regenerates its masks from seeds; feed exactly those masks to the oracle."""
+    from rlaifv_b200 import ops
+    pol, params, lora = setup()
+    pol.lora.dropout = 0.25
+    c = O.TINY
+    batch = O.synthetic_pair_batch(c, 2, 24, 30, seed=41, image_pos=7, ragged=True)
+    ids, labels, images = batch["concatenated_input_ids"], batch["concatenated_labels"], batch["images"]
+    out = pol.forward_logps(ids, labels, images, keep_stash=True)
+    nseq, T = ids.shape[0], out["T"]
+    H, F_ = c.hidden_size, c.intermediate_size
+    masks = {}
+    for i, ls in enumerate(pol._stash["layers"]):
+        for group, width in (("qkv", H), ("o", H), ("gu", H), ("down", F_)):
+            ones = torch.ones(nseq * T, width, device="cuda", dtype=torch.bfloat16)
+            masks[f"{i}.{group}"] = ops.dropout_fwd(ones, 0.25, ls["seed_" + group]).float().cpu().reshape(nseq, T, width)
+    assert 0.2 < float((masks["0.qkv"] == 0).float().mean()) < 0.3
+    pf = {k: v.clone().float().requires_grad_(True) for k, v in {**params, **lora}.items()}
+    of = O.policy_logps(pf, c, ids, labels, images, lora_drop=masks)
+    assert rel(out["logp"], of["logp"].detach()) <= 2e-3
+    nodrop = O.policy_logps({k: v.detach() for k, v in pf.items()}, c, ids, labels, images)
+    assert rel(of["logp"].detach(), nodrop["logp"]) > 1e-4                 # the masks matter
+    g = torch.tensor([0.02, -0.01, -0.02, 0.01])
+    (of["logp"] * g).sum().backward()
+    pol.backward_logps(g.cuda().contiguous())
+    torch.cuda.synchronize()
+    gl = pol.lora.hf_views(grads=True)
+    for name in ("model.layers.0.self_attn.q_proj.lora_A.weight", "model.layers.1.self_attn.o_proj.lora_B.weight",
+                 "model.layers.0.mlp.up_proj.lora_A.weight", "model.layers.1.mlp.down_proj.lora_A.weight",
+                 "model.layers.0.mlp.down_proj.lora_B.weight"):
+        ref, got = pf[name].grad, gl[name].float().cpu()
+        nr = float((got.double().norm() - ref.double().norm()).abs() / (ref.double().norm() + 1e-30))
+        print(f"{name}: rel max err {rel(got, ref):.3e}, norm diff {nr:.3e}")
+        assert nr <= 5e-2 and rel(got, ref) <= 1e-1, name
+    assert rel(pol.store.hf_grad_views()["model.mm_projector.0.weight"].float(), pf["model.mm_projector.0.weight"].grad) <= 1e-1
