@@ -342,7 +342,7 @@ constexpr int GEMM2_STAGES = 6;
 constexpr uint32_t GEMM2_A_BYTES = 128 * GEMM_BK * 2;
 constexpr uint32_t GEMM2_B_BYTES = 128 * GEMM_BK * 2;
 constexpr uint32_t GEMM2_STAGE_BYTES = GEMM2_A_BYTES + GEMM2_B_BYTES;
-constexpr uint32_t GEMM2_SMEM_BYTES = GEMM2_STAGES * GEMM2_STAGE_BYTES + 256 + 1024;
+constexpr uint32_t GEMM2_SMEM_BYTES = GEMM2_STAGES * GEMM2_STAGE_BYTES + 512 + 1024;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -362,7 +362,7 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t cta) 
 template <bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  int M, int N, int K, GemmEpilogue epi) {
+                  int M, int N, int K, GemmEpilogue epi, TileCounter* ctr) {
   constexpr int STAGES = GEMM2_STAGES;
   constexpr int BN = 256;
   extern __shared__ uint8_t smem_raw[];
@@ -372,12 +372,14 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* tq_full = tempty + 2;            // tile index landed in this CTA's queue slot
+  uint64_t* tq_empty = tq_full + GEMM_TQ;    // (leader's copy) every consumer of both CTAs has read the slot
+  volatile int* tile_q = reinterpret_cast<volatile int*>(tq_empty + GEMM_TQ);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(const_cast<int*>(tile_q) + GEMM_TQ);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = cluster_ctarank();
-  const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
   const int num_m = (M + 255) / 256;
   const int num_n = (N + BN - 1) / BN;
@@ -398,6 +400,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_init(&tfull[i], 1);   // multicast tcgen05.commit
         mbar_init(&tempty[i], 8);  // 4 epilogue warps of each CTA arrive on the leader's barrier
       }
+      for (int i = 0; i < GEMM_TQ; ++i) {
+        mbar_init(&tq_full[i], 1);    // one arrive by the leader's producer (local / remote)
+        mbar_init(&tq_empty[i], 10);  // leader: MMA + 4 epilogue warps; peer: producer + 4 epilogue warps
+      }
       fence_barrier_init();
     }
     __syncwarp();
@@ -409,11 +415,29 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------ TMA producer (both CTAs) ------------------------------
+    // ------------------------------ TMA producer (both CTAs); the leader's also schedules tiles ------------------
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+      int qs = 0;
+      uint32_t qph = 0;
+      for (int iter = 0;; ++iter) {
+        int t;
+        if (cta_rank == 0) {
+          t = epi.dynamic ? (int)atomicAdd(&ctr->next, 1u) : (int)((blockIdx.x >> 1) + iter * num_clusters);
+          if (t >= num_tiles) t = -1;
+          mbar_wait_cluster(&tq_empty[qs], qph ^ 1);
+          tile_q[qs] = t;
+          st_shared_cluster_u32(const_cast<int*>(&tile_q[qs]), 1, (uint32_t)t);
+          mbar_arrive(&tq_full[qs]);
+          mbar_arrive_cluster_release(&tq_full[qs], 1);
+        } else {
+          mbar_wait_cluster(&tq_full[qs], qph);
+          t = tile_q[qs];
+          mbar_arrive_cluster_release(&tq_empty[qs], 0);
+        }
+        if (++qs == GEMM_TQ) { qs = 0; qph ^= 1; }
+        if (t < 0) break;
         int m_blk, n_blk;
         tile_coords(t, num_m, num_n, epi.group_m, m_blk, n_blk);
         const int m0 = m_blk * 256 + (int)cta_rank * 128;
@@ -450,8 +474,14 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       constexpr uint32_t idesc = make_idesc_bf16(256, BN, A_MN, B_MN);
       int s = 0;
       uint32_t ph = 0;
-      int it = 0;
-      for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+      int qs = 0;
+      uint32_t qph = 0;
+      for (int it = 0;; ++it) {
+        mbar_wait(&tq_full[qs], qph);
+        const int t = tile_q[qs];
+        mbar_arrive(&tq_empty[qs]);
+        if (++qs == GEMM_TQ) { qs = 0; qph ^= 1; }
+        if (t < 0) break;
         const int acc = it & 1;
         const uint32_t acc_ph = (it >> 1) & 1;
         mbar_wait(&tempty[acc], acc_ph ^ 1);
@@ -478,8 +508,19 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ------------------------------ epilogue (both CTAs) ------------------------------
     const int quad = warp & 3;
     const int row_in_tile = (int)cta_rank * 128 + quad * 32 + lane;
-    int it = 0;
-    for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+    int qs = 0;
+    uint32_t qph = 0;
+    for (int it = 0;; ++it) {
+      if (cta_rank == 0) mbar_wait(&tq_full[qs], qph);
+      else mbar_wait_cluster(&tq_full[qs], qph);
+      const int t = tile_q[qs];
+      __syncwarp();
+      if (lane == 0) {
+        if (cta_rank == 0) mbar_arrive(&tq_empty[qs]);
+        else mbar_arrive_cluster_release(&tq_empty[qs], 0);
+      }
+      if (++qs == GEMM_TQ) { qs = 0; qph ^= 1; }
+      if (t < 0) break;
       int m_blk, n_blk;
       tile_coords(t, num_m, num_n, epi.group_m, m_blk, n_blk);
       const int acc = it & 1;
@@ -515,6 +556,14 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tc_fence_after();
     tmem_dealloc_2sm<512>(tmem_base);
   }
+  if (threadIdx.x == 0 && cta_rank == 0) {
+    const unsigned int d = atomicAdd(&ctr->done, 1u);
+    if (d == (unsigned int)num_clusters - 1) {
+      ctr->next = 0;
+      ctr->done = 0;
+      __threadfence();
+    }
+  }
 }
 
 template <bool A_MN, bool B_MN>
@@ -530,7 +579,9 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, i
   const int num_tiles = ((M + 255) / 256) * ((N + 255) / 256);
   int clusters = num_sms() / 2;
   if (num_tiles < clusters) clusters = num_tiles;
-  kern<<<clusters * 2, GEMM_THREADS, GEMM2_SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, epi);
+  if (!g_counter_pool) B200_CHECK_CUDA(cudaGetSymbolAddress((void**)&g_counter_pool, g_tile_counters));
+  TileCounter* ctr = g_counter_pool + (g_launch_seq++ & 63);
+  kern<<<clusters * 2, GEMM_THREADS, GEMM2_SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, epi, ctr);
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -607,11 +658,10 @@ static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B
   if (bn == 0) {
     const long long tiles256 = (long long)((M + 127) / 128) * ((N + 255) / 256);
     const long long tiles2 = (long long)((M + 255) / 256) * ((N + 255) / 256);
-    // measured on B200 (profiles/r01_gemm_1cta_vs_2cta.log): the CTA-pair kernel wins for long-K
-    // forward/dgrad shapes (down_proj, K=11008: +6%) and the very wide lm_head (+4%); elsewhere the
-    // 1-CTA 128x256 kernel is equal or better.
-    const bool pair_wins = !a_mn_major && tiles2 >= 64 && (K >= 8192 || N >= 30000);
-    if (N >= 256 && (g_enable_2cta == 1 ? tiles2 >= 64 : (g_enable_2cta == 2 && pair_wins))) bn = 512;
+    // measured on B200 in one process (tools/gpu_gemm_pair_ab.py, profiles/r01_gemm_pair_ab.log): the CTA-pair
+    // kernel is 5-10% faster than the 1-CTA kernel on every layer shape (the part is power-limited and the
+    // pair halves the B-operand shared-memory traffic), so policy 2 (default) takes it for any large problem.
+    if (N >= 256 && g_enable_2cta != 0 && tiles2 >= 64) bn = 512;
     else bn = (N >= 256 && tiles256 >= 120) ? 256 : 128;
   }
   B200_REQUIRE(bn == 128 || bn == 256 || bn == 512, "gemm: tile_n must be 0, 128, 256 or 512 (2-CTA 256x256)");

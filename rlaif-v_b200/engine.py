@@ -41,10 +41,6 @@ class DPOStepEngine:
         # engine itself takes get_beta_and_logps' inputs as they are.
         self.hf_deepspeed_input_cast = hf_deepspeed_input_cast
         self.global_step = 0
-        if world > 1:
-            # the CTA-pair GEMM still uses a static tile assignment; next to overlapped NCCL kernels only the
-            # dynamically scheduled 1-CTA kernel degrades gracefully
-            _lib.load().rlaifv_gemm_set_2cta(0)
         self._metrics = torch.zeros(9, dtype=_F32, device=policy.device)
         self._last_micro = False
         self._stepping = False
