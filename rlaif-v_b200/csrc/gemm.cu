@@ -362,7 +362,8 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t cta) 
 template <bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  int M, int N, int K, GemmEpilogue epi, TileCounter* ctr) {
+                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+                  int M, int N, int K, GemmSecondSource src2, GemmEpilogue epi, TileCounter* ctr) {
   constexpr int STAGES = GEMM2_STAGES;
   constexpr int BN = 256;
   extern __shared__ uint8_t smem_raw[];
@@ -384,7 +385,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int num_m = (M + 255) / 256;
   const int num_n = (N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
-  const int num_k = (K + GEMM_BK - 1) / GEMM_BK;
+  const int num_k1 = (K + GEMM_BK - 1) / GEMM_BK;
+  const int num_k = num_k1 + (src2.K2 + GEMM_BK - 1) / GEMM_BK;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -449,20 +451,24 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint32_t leader_full = mapa_u32(smem_u32(&full[s]), 0);
           if (cta_rank == 0) mbar_arrive_expect_tx(&full[s], 2 * GEMM2_STAGE_BYTES);
           else mbar_arrive_cluster(&full[s], 0);
-          const int k0 = kb * GEMM_BK;
+          const bool second = kb >= num_k1;
+          const CUtensorMap* mA = second ? &tmA2 : &tmA;
+          const CUtensorMap* mB = second ? &tmB2 : &tmB;
+          const int kB = (second ? kb - num_k1 : kb) * GEMM_BK;
+          const int kA = second ? kB + (src2.n_sub > 0 ? ((n_blk * BN) / src2.n_sub) * src2.r : 0) : kB;
           if (A_MN) {
 #pragma unroll
             for (int a = 0; a < 2; ++a)
-              tma_load_2d_2sm(a_dst + a * (GEMM_BK * 128), &tmA, leader_full, m0 + a * 64, k0);
+              tma_load_2d_2sm(a_dst + a * (GEMM_BK * 128), mA, leader_full, m0 + a * 64, kA);
           } else {
-            tma_load_2d_2sm(a_dst, &tmA, leader_full, k0, m0);
+            tma_load_2d_2sm(a_dst, mA, leader_full, kA, m0);
           }
           if (B_MN) {
 #pragma unroll
             for (int a = 0; a < 2; ++a)
-              tma_load_2d_2sm(b_dst + a * (GEMM_BK * 128), &tmB, leader_full, n0 + a * 64, k0);
+              tma_load_2d_2sm(b_dst + a * (GEMM_BK * 128), mB, leader_full, n0 + a * 64, kB);
           } else {
-            tma_load_2d_2sm(b_dst, &tmB, leader_full, k0, n0);
+            tma_load_2d_2sm(b_dst, mB, leader_full, kB, n0);
           }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
@@ -567,7 +573,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 }
 
 template <bool A_MN, bool B_MN>
-static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K,
+static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA2,
+                        const CUtensorMap& tmB2, int M, int N, int K, const GemmSecondSource& src2,
                         const GemmEpilogue& epi, cudaStream_t stream) {
   auto kern = gemm2_bf16_kernel<A_MN, B_MN>;
   static bool configured = false;
@@ -581,7 +588,7 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, i
   if (num_tiles < clusters) clusters = num_tiles;
   if (!g_counter_pool) B200_CHECK_CUDA(cudaGetSymbolAddress((void**)&g_counter_pool, g_tile_counters));
   TileCounter* ctr = g_counter_pool + (g_launch_seq++ & 63);
-  kern<<<clusters * 2, GEMM_THREADS, GEMM2_SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, epi, ctr);
+  kern<<<clusters * 2, GEMM_THREADS, GEMM2_SMEM_BYTES, stream>>>(tmA, tmB, tmA2, tmB2, M, N, K, src2, epi, ctr);
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -670,9 +677,10 @@ static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B
   src2.r = r2;
   src2.n_sub = n_sub;
   if (K2 > 0) {
-    if (bn == 512) bn = 256;   // the second source is implemented in the 1-CTA kernel
     B200_REQUIRE(lda2 % 8 == 0 && ldb2 % 8 == 0, "gemm: lda2/ldb2 must be multiples of 8");
-    B200_REQUIRE(n_sub == 0 || n_sub % bn == 0, "gemm: n_sub (%d) must be a multiple of the N tile (%d)", n_sub, bn);
+    const int ntile = bn == 512 ? 256 : bn;
+    B200_REQUIRE(n_sub == 0 || n_sub % ntile == 0, "gemm: n_sub (%d) must be a multiple of the N tile (%d)", n_sub,
+                 ntile);
   }
   CUtensorMap tmA, tmB;
   int rc = operand_tmap(&tmA, A, lda, a_mn_major != 0, M, K, GEMM_BM);
@@ -685,7 +693,7 @@ static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B
     const int a2_k = n_sub > 0 ? (N / n_sub) * r2 : K2;
     rc = operand_tmap(&tmA2, A2, lda2, a_mn_major != 0, M, a2_k, GEMM_BM);
     if (rc) return rc;
-    rc = operand_tmap(&tmB2, B2, ldb2, b_mn_major != 0, N, K2, bn);
+    rc = operand_tmap(&tmB2, B2, ldb2, b_mn_major != 0, N, K2, bn == 512 ? 128 : bn);
     if (rc) return rc;
   }
   GemmEpilogue epi;
@@ -702,9 +710,9 @@ static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B
   epi.dynamic = (g_debug & 4) ? 0 : 1;
   cudaStream_t st = (cudaStream_t)stream;
   if (bn == 512) {
-    if (!a_mn_major && !b_mn_major) return launch_gemm2<false, false>(tmA, tmB, M, N, K, epi, st);
-    if (!a_mn_major && b_mn_major) return launch_gemm2<false, true>(tmA, tmB, M, N, K, epi, st);
-    return launch_gemm2<true, true>(tmA, tmB, M, N, K, epi, st);
+    if (!a_mn_major && !b_mn_major) return launch_gemm2<false, false>(tmA, tmB, tmA2, tmB2, M, N, K, src2, epi, st);
+    if (!a_mn_major && b_mn_major) return launch_gemm2<false, true>(tmA, tmB, tmA2, tmB2, M, N, K, src2, epi, st);
+    return launch_gemm2<true, true>(tmA, tmB, tmA2, tmB2, M, N, K, src2, epi, st);
   }
   if (!a_mn_major && !b_mn_major)
     return bn == 256 ? launch_gemm<false, false, 256>(tmA, tmB, tmA2, tmB2, M, N, K, src2, epi, st)

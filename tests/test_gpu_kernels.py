@@ -63,9 +63,10 @@ def test_gemm_epilogues_and_views():
     assert float(wide[:, :N].abs().max()) == 0.0 and float(wide[:, 2 * N:].abs().max()) == 0.0
 
 
-def test_gemm_dual_source_matches_two_products():
+@pytest.mark.parametrize("M", [500, 4200])          # 4200 rows: enough tiles for the CTA-pair kernel
+def test_gemm_dual_source_matches_two_products(M):
     from rlaifv_b200 import ops
-    M, K, r, nsub = 500, 256, 8, 256
+    K, r, nsub = 256, 8, 2048 if M > 1000 else 256
     x = torch.randn(M, K, device=DEV).to(BF)
     W = (torch.randn(2 * nsub, K, device=DEV) * 0.05).to(BF)
     t = torch.randn(M, 2 * r, device=DEV).to(BF)
