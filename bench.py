@@ -125,7 +125,46 @@ def synthetic_batch(rank, step, B):
 # ------------------------------------------------------------------------------------------------
 # CPU arm: oracle port of the reference path on the host cores, bounded sample
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_pairs_per_sec(dtype_name="float32"):
+def gpu_full_width_parity(p, cfg, batch, out):
+    """Checker leg: the CUDA path on the SAME full-width 1-layer model / batch the oracle port just ran
+    (h=4096, ffn=11008, vocab=32000, CLIP-L 23 layers; config (a) shape) — log-probs, loss and gradients."""
+    from rlaifv_b200 import ops
+    from rlaifv_b200.model import LlavaDims, LlavaDPOPolicy
+    pol = LlavaDPOPolicy(LlavaDims(num_layers=cfg.num_layers), "cuda", hf_state={k: v.detach() for k, v in p.items()})
+    o = pol.forward_logps(batch["concatenated_input_ids"], batch["concatenated_labels"], batch["images"].float(),
+                          keep_stash=True)
+    B = batch["images"].shape[0]
+    lp = o["logp"]
+    losses, _, _, dpw, dpr, out9 = ops.dpo_loss(lp[:B].contiguous(), lp[B:].contiguous(), batch["ref_win_logp"].cuda(),
+                                                batch["ref_rej_logp"].cuda(), 0.1)
+    pol.backward_logps(torch.cat([dpw, dpr]).contiguous())
+    pol.finalize_embed_grad()
+    torch.cuda.synchronize()
+    ref_lp = out["logp"].detach().double()
+    mask = (out["labels"][:, 1:] != -100)
+    pt_ref = out["per_token_logps"].detach().double()[mask]
+    pt_gpu = o["per_token_logps"].double().cpu()[mask]
+    grads = pol.store.hf_grad_views()
+    gerr = {}
+    for name in ("model.mm_projector.0.weight", "model.mm_projector.2.weight", "model.layers.0.self_attn.q_proj.weight",
+                 "model.layers.0.self_attn.o_proj.weight", "model.layers.0.mlp.gate_proj.weight",
+                 "model.layers.0.mlp.down_proj.weight", "model.layers.0.input_layernorm.weight", "model.norm.weight",
+                 "lm_head.weight"):
+        ref = p[name].grad.detach().double()
+        got = grads[name].double().cpu().view_as(ref)
+        gerr[name] = float((got - ref).norm() / (ref.norm() + 1e-300))
+    res = {"shape": "1 decoder layer at full width, 1 pair, R=64 (T=687)",
+           "logp_oracle": ref_lp.tolist(), "logp_gpu": lp.double().cpu().tolist(),
+           "logp_rel_err": float(((lp.double().cpu() - ref_lp).abs() / ref_lp.abs()).max()),
+           "per_token_logp_max_rel_err": float(((pt_gpu - pt_ref).abs() / pt_ref.abs().clamp_min(1e-6)).max()),
+           "loss_oracle": float(out["loss"]), "loss_gpu": float(out9[0]),
+           "grad_rel_l2_err": gerr}
+    del pol
+    torch.cuda.empty_cache()
+    return res
+
+
+def cpu_reference_pairs_per_sec(dtype_name="float32", check=None):
     """Times oracle.dpo_step fwd + bwd + AdamW at FULL WIDTH (h=4096, ffn=11008, vocab=32000,
     CLIP-L 23 layers, 336 px) on config (a) shape (1 pair, 64-token responses, T=687) with 1 and 2
     decoder layers, and extrapolates linearly to 32 layers."""
@@ -149,6 +188,10 @@ def cpu_reference_pairs_per_sec(dtype_name="float32"):
         t0 = time.perf_counter()
         out = O.dpo_step(p, cfg, batch, beta=0.1)
         out["loss"].backward()
+        if check is not None and nl == 1:
+            t_pause = time.perf_counter()
+            check(p, cfg, batch, out)
+            t0 += time.perf_counter() - t_pause
         with torch.no_grad():
             for k in names:
                 new_p, m, v = O.adamw_update(p[k].float(), p[k].grad.float(), state[k][0], state[k][1], 1, 5e-7)
@@ -396,7 +439,7 @@ def main():
         "step_frac_of_peak": {"measured_sustained_%g" % peak_sus: value / world * f_pair / 1e12 / peak_sus,
                               "measured_burst_%g" % peak_burst: value / world * f_pair / 1e12 / peak_burst,
                               "datasheet_2250": value / world * f_pair / 1e12 / 2250.0},
-        "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05)", "achieved": achieved,
+        "roofline": {"bound": "tensor", "kernel": "gemm2_bf16_kernel / gemm_bf16_kernel (tcgen05, all GEMM launches of a step)", "achieved": achieved,
                      "peak": peak_sus, "unit": "TFLOP/s", "frac": achieved / peak_sus, "traffic": traffic, "traffic_note": traffic_note,
                      "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step); burst %g"
                                     % (peak_kind, peak_burst),
@@ -410,8 +453,20 @@ def main():
     }
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
-            v, cores, sample = cpu_reference_pairs_per_sec()
+            policy._stash = None
+            policy._bufs.clear()
+            torch.cuda.empty_cache()
+            parity = {}
+
+            def check(*a):
+                try:
+                    parity.update(gpu_full_width_parity(*a))
+                except Exception as exc:                      # the checker must never take the bench line down
+                    parity["error"] = "%s: %s" % (type(exc).__name__, exc)
+
+            v, cores, sample = cpu_reference_pairs_per_sec(check=check)
             line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample}
+            line["parity_full_width"] = parity
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
