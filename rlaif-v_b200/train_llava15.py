@@ -150,17 +150,7 @@ def safe_save_model_for_hf_trainer(trainer, output_dir):
     pol = trainer.model.policy
     if pol.lora is not None:
         if trainer.args.should_save:
-            os.makedirs(output_dir, exist_ok=True)
-            ad = {"base_model.model." + k: v.cpu() for k, v in pol.lora.hf_views().items()}
-            torch.save(ad, os.path.join(output_dir, "adapter_model.bin"))
-            with open(os.path.join(output_dir, "adapter_config.json"), "w") as f:
-                json.dump({"peft_type": "LORA", "r": pol.lora.r, "lora_alpha": pol.lora.scaling * pol.lora.r,
-                           "lora_dropout": pol.lora.dropout, "bias": "none", "task_type": "CAUSAL_LM",
-                           "target_modules": ["q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj",
-                                              "down_proj"]}, f)
-            non_lora = {"base_model.model." + k: v.cpu() for k, v in trainer.model.state_dict().items()
-                        if "mm_projector" in k}
-            torch.save(non_lora, os.path.join(output_dir, "non_lora_trainables.bin"))
+            trainer.save_adapter(output_dir)
         return
     if trainer.args.should_save:
         trainer._save(output_dir, state_dict={k: v.cpu() for k, v in trainer.model.state_dict().items()})
@@ -187,8 +177,13 @@ def init_model(model_args, data_args, training_args, attn_implementation=None):
     model = LlavaLlamaForCausalLM(dims, torch.device("cuda", local_rank), hf_state=state)
     model.config.use_cache = False
     if training_args.lora_enable:
+        if training_args.lora_bias != "none":
+            raise NotImplementedError("lora_bias=%r (the shipped recipe uses 'none')" % training_args.lora_bias)
         model.policy.enable_lora(r=training_args.lora_r, alpha=training_args.lora_alpha,
                                  dropout=training_args.lora_dropout)
+        if training_args.lora_weight_path:                    # continue from a saved adapter
+            ad = torch.load(os.path.join(training_args.lora_weight_path, "adapter_model.bin"), map_location="cpu")
+            model.policy.lora.load_hf({k[len("base_model.model."):]: v for k, v in ad.items()})
     tokenizer = load_tokenizer(model_args.model_name_or_path, training_args.model_max_length)
     data_args.is_multimodal = True
     data_args.image_token_len = dims.num_patches
@@ -208,6 +203,7 @@ def train(attn_implementation=None, argv=None):
     if training_args.task != "DPO":
         raise NotImplementedError
     from .trainers import LLaVA15DPOTrainer
+    training_args.model_name_or_path = model_args.model_name_or_path
     trainer = LLaVA15DPOTrainer(model=model, tokenizer=tokenizer, args=training_args, **data_module)
     if list(pathlib.Path(training_args.output_dir).glob("checkpoint-*")):
         print("Resume from checkpoint.")

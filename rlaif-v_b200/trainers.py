@@ -202,16 +202,27 @@ class LLaVA15DPOTrainer:
         """Fused path: forward + DPO loss/grad kernel + backward + reduce-scatter + AdamW."""
         return self.engine.train_step(inputs)
 
-    def _dataloader(self):
+    def _dataloader(self, epoch=0):
+        """One epoch's loader; the shuffle is a pure function of (seed, epoch) so that a resumed run replays the
+        order of the interrupted one."""
         a = self.args
         sampler = self._get_train_sampler()
+        seed = int(getattr(a, "seed", 42)) + epoch
         if self.world > 1 and sampler is not None:
             sampler = torch.utils.data.distributed.DistributedSampler(self.train_dataset, self.world, self.rank,
-                                                                      shuffle=True, seed=int(getattr(a, "seed", 42)))
+                                                                      shuffle=True, seed=seed)
+        elif isinstance(sampler, torch.utils.data.RandomSampler):
+            sampler.generator = torch.Generator().manual_seed(seed)
         return torch.utils.data.DataLoader(self.train_dataset, batch_size=a.per_device_train_batch_size,
                                            sampler=sampler, collate_fn=self.data_collator,
                                            num_workers=getattr(a, "dataloader_num_workers", 0), drop_last=True,
                                            pin_memory=True)
+
+    def _steps_per_epoch(self):
+        if not hasattr(self.train_dataset, "__len__"):
+            return 1 << 60
+        n = len(self.train_dataset) // max(1, self.world)
+        return n // self.args.per_device_train_batch_size
 
     def train(self, resume_from_checkpoint=None):
         a = self.args
@@ -222,7 +233,11 @@ class LLaVA15DPOTrainer:
         self.engine.global_step = step
         t0 = time.time()
         while step < a.max_steps:
-            for batch in self._dataloader():
+            loader = self._dataloader(epoch=step // max(1, self._steps_per_epoch()))
+            skip = step % max(1, self._steps_per_epoch())       # batches of this epoch consumed before a resume
+            for bi, batch in enumerate(loader):
+                if bi < skip:
+                    continue
                 m = self.training_step(self.model, batch)
                 step += 1
                 self.state["global_step"] = step
@@ -238,10 +253,54 @@ class LLaVA15DPOTrainer:
         return self.state
 
     # ---- checkpoints ----
+    def _write_config(self, output_dir):
+        """`config.json` next to the weights (HF `save_pretrained` does this for the reference; the LoRA run script
+        copies it into every checkpoint dir, script/train/llava15_train_lora.sh:51-69)."""
+        cfg = dict(vars(self.model.config))
+        cfg.update(model_type="llava_llama", architectures=["LlavaLlamaForCausalLM"], torch_dtype="bfloat16")
+        with open(os.path.join(output_dir, "config.json"), "w") as f:
+            json.dump(cfg, f, indent=1)
+
+    def save_adapter(self, output_dir):
+        """LoRA run: peft-layout adapter (`adapter_model.bin` + `adapter_config.json`) and the non-LoRA trainables
+        (`non_lora_trainables.bin` = mm_projector), muffin/train/train_llava15_lora.py:184-197 — what
+        llava/model/builder.py:52-86 loads back."""
+        pol = self.model.policy
+        os.makedirs(output_dir, exist_ok=True)
+        if pol.param_ready is not None:                       # pending ZeRO-2 all-gathers of the last step
+            for b in pol.lora.buckets:
+                pol.param_ready(b.name)
+        torch.cuda.synchronize()
+        ad = {"base_model.model." + k: v.cpu() for k, v in pol.lora.hf_views().items()}
+        torch.save(ad, os.path.join(output_dir, "adapter_model.bin"))
+        with open(os.path.join(output_dir, "adapter_config.json"), "w") as f:
+            json.dump({"peft_type": "LORA", "r": pol.lora.r, "lora_alpha": pol.lora.scaling * pol.lora.r,
+                       "lora_dropout": pol.lora.dropout, "bias": "none", "task_type": "CAUSAL_LM",
+                       "base_model_name_or_path": getattr(self.args, "model_name_or_path", None),
+                       "target_modules": ["q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj",
+                                          "down_proj"]}, f, indent=1)
+        non_lora = {"base_model.model." + k: v.cpu() for k, v in self.model.state_dict().items()
+                    if "mm_projector" in k}
+        torch.save(non_lora, os.path.join(output_dir, "non_lora_trainables.bin"))
+        self._write_config(output_dir)
+
+    def load_adapter(self, path):
+        pol = self.model.policy
+        ad = torch.load(os.path.join(path, "adapter_model.bin"), map_location="cpu")
+        pol.lora.load_hf({k[len("base_model.model."):]: v for k, v in ad.items()})
+        nl = torch.load(os.path.join(path, "non_lora_trainables.bin"), map_location="cpu")
+        views = pol.store.hf_views()
+        for k, v in nl.items():
+            views[k[len("base_model.model."):]].copy_(v)
+
     def _save(self, output_dir, state_dict=None):
         os.makedirs(output_dir, exist_ok=True)
+        if self.model.policy.lora is not None and state_dict is None:
+            self.save_adapter(output_dir)                      # frozen base weights are not rewritten
+            return
         sd = state_dict if state_dict is not None else {k: v.cpu() for k, v in self.model.state_dict().items()}
         torch.save(sd, os.path.join(output_dir, "pytorch_model.bin"))
+        self._write_config(output_dir)
 
     def save_state(self):
         if self.args.should_save:
@@ -270,7 +329,10 @@ class LLaVA15DPOTrainer:
         if not ck:
             return
         path = ck[-1]
-        self.model.load_state_dict(torch.load(os.path.join(path, "pytorch_model.bin"), map_location="cpu"))
+        if self.model.policy.lora is not None:
+            self.load_adapter(path)
+        else:
+            self.model.load_state_dict(torch.load(os.path.join(path, "pytorch_model.bin"), map_location="cpu"))
         self.engine.opt.load_state_dict(torch.load(os.path.join(path, f"optimizer_rank{self.rank}.pt"),
                                                    map_location=self.model.device))
         with open(os.path.join(path, "trainer_state.json")) as f:

@@ -154,3 +154,50 @@ def test_lora_with_dropout_matches_oracle_given_the_same_masks():
         print(f"{name}: rel max err {rel(got, ref):.3e}, norm diff {nr:.3e}")
         assert nr <= 5e-2 and rel(got, ref) <= 1e-1, name
     assert rel(pol.store.hf_grad_views()["model.mm_projector.0.weight"].float(), pf["model.mm_projector.0.weight"].grad) <= 1e-1
+
+
+def test_lora_trainer_checkpoint_layout_and_resume(tmp_path):
+    """LoRA run through the trainer: checkpoints hold the peft-layout adapter + non_lora_trainables.bin + config.json
+    (muffin/train/train_llava15_lora.py:184-197; what llava/model/builder.py:52-86 loads), the frozen base is never
+    rewritten, and resuming restores adapters, projector and optimizer state exactly."""
+    import json
+    import os
+    from test_gpu_trainer_compat import Tok, dims, instances, make_args
+    from rlaifv_b200.collator import DataCollatorForDPODataset
+    from rlaifv_b200.llava_model import LlavaLlamaForCausalLM
+    from rlaifv_b200.trainers import LLaVA15DPOTrainer
+    params = O.make_params(O.TINY, seed=0, scale=0.4)
+    data = instances(8, seed=11)
+    coll = DataCollatorForDPODataset(tokenizer=Tok(), beta=0.1, mod_token_weight=1.0)
+
+    def run(max_steps, resume):
+        model = LlavaLlamaForCausalLM(dims(), "cuda", hf_state=params)
+        model.policy.enable_lora(r=R, alpha=ALPHA, dropout=0.0)
+        tr = LLaVA15DPOTrainer(model=model, tokenizer=Tok(), args=make_args(tmp_path, max_steps=max_steps),
+                               train_dataset=data, data_collator=coll)
+        tr.train(resume_from_checkpoint=resume)
+        torch.cuda.synchronize()
+        return model, tr
+
+    m_full, _ = run(4, False)                                   # uninterrupted 4 steps (also writes checkpoint-2/-4)
+    ck = tmp_path / "checkpoint-2"
+    assert sorted(os.listdir(ck)) == ["adapter_config.json", "adapter_model.bin", "config.json",
+                                      "non_lora_trainables.bin", "optimizer_rank0.pt", "trainer_state.json"]
+    cfg = json.load(open(ck / "adapter_config.json"))
+    assert cfg["r"] == R and cfg["lora_alpha"] == ALPHA and cfg["peft_type"] == "LORA"
+    ad = torch.load(ck / "adapter_model.bin")
+    assert "base_model.model.model.layers.0.self_attn.q_proj.lora_A.weight" in ad
+    assert ad["base_model.model.model.layers.1.mlp.down_proj.lora_B.weight"].shape == (O.TINY.hidden_size, R)
+    assert set(torch.load(ck / "non_lora_trainables.bin")) == {
+        "base_model.model.model.mm_projector.%d.%s" % (i, n) for i in (0, 2) for n in ("weight", "bias")}
+    assert json.load(open(ck / "config.json"))["model_type"] == "llava_llama"
+    want = m_full.policy.lora.flat.clone()
+    # drop checkpoint-4 so the second run resumes from step 2 and must land on the same adapters
+    for fn in os.listdir(tmp_path / "checkpoint-4"):
+        os.remove(tmp_path / "checkpoint-4" / fn)
+    os.rmdir(tmp_path / "checkpoint-4")
+    m_res, t_res = run(4, True)
+    assert t_res.state["global_step"] == 4
+    # same data order, same optimizer state => same adapters (fp32 atomics in the backward may flip a last bit)
+    assert float((m_res.policy.lora.flat == want).float().mean()) > 0.99
+    assert float((m_res.policy.store.flat == m_full.policy.store.flat).float().mean()) > 0.999
