@@ -84,6 +84,19 @@ int rlaifv_attention_bwd_gqa(const void* q, const void* k, const void* v, long l
                              long long ld_out, const void* d_out, long long ld_dout, const float* lse, float* dq_f32,
                              void* dk, void* dv, long long ld_dkv, float* delta_ws, int nseq, int S, int n_heads,
                              int n_kv_heads, int head_dim, float scale, void* stream);
+/* Cross-attention of the perceiver resampler (OmniLMM-12B, omnilmm/model/resampler.py:149-168: the core of
+ * nn.MultiheadAttention called at :158-163 — 64 learned queries over the Skv vision tokens, non-causal, no mask).
+ * q [(q_shared ? 1 : nseq)*Sq][ld_q], k/v [nseq*Skv][ld_kv], out [nseq*Sq][ld_out], lse fp32 [nseq][n_heads][Sq].
+ * q_shared != 0: one query block serves every image (resampler.py:160 `_repeat`), so it is read from sequence 0 and
+ * the backward's fp32 dQ reduction also sums over the batch. head_dim 64 or 128 forward, 128 backward. */
+int rlaifv_cross_attention_fwd(const void* q, long long ld_q, const void* k, const void* v, long long ld_kv, void* out,
+                               long long ld_out, float* lse, int nseq, int Sq, int Skv, int n_heads, int head_dim,
+                               int q_shared, float scale, void* stream);
+int rlaifv_cross_attention_bwd(const void* q, long long ld_q, const void* k, const void* v, long long ld_kv,
+                               const void* out, long long ld_out, const void* d_out, long long ld_dout,
+                               const float* lse, float* dq_f32, void* dk, void* dv, long long ld_dkv, float* delta_ws,
+                               int nseq, int Sq, int Skv, int n_heads, int head_dim, int q_shared, float scale,
+                               void* stream);
 /* RoPE on a fused row [q: n_heads*D | k: n_kv_heads*D | v: n_kv_heads*D] */
 int rlaifv_rope_fwd_gqa(void* qkv, const void* cos_tab, const void* sin_tab, long long M, int T, int n_heads,
                         int n_kv_heads, int head_dim, long long ld, void* stream);
@@ -99,6 +112,14 @@ int rlaifv_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float
                        int M, int H, void* stream);
 int rlaifv_layernorm_fwd(const void* x, const void* w, const void* b, void* y, int M, int H, float eps,
                          void* stream);
+/* LayerNorm backward for the resampler's trainable ln_q / ln_kv / ln_post (omnilmm/model/resampler.py:137-141;
+ * eps 1e-6, :110): statistics recomputed from x; dw/db bf16 [H] overwritten or accumulated; workspace fp32
+ * [2 * rlaifv_rmsnorm_bwd_partials() * H]. */
+int rlaifv_layernorm_bwd(const void* dy, const void* x, const void* w, void* dx, void* dw, void* db, int accumulate,
+                         float* workspace, int M, int H, float eps, void* stream);
+/* y[r] = x[r] + table[r % P]: the resampler's position-embedding adds (resampler.py:158-161), table shared by the
+ * batch. */
+int rlaifv_add_rows_bcast(const void* x, const void* table, void* y, long long M, int P, int H, void* stream);
 
 /* ---- RoPE on the fused qkv buffer (HF:llama/modeling_llama.py:124-168; positions 0..T-1 because
  * position_ids are not forwarded, llava_llama.py:94). cos/sin: bf16 [T][head_dim]. In place. */

@@ -47,9 +47,12 @@ template <int D, bool CAUSAL>
 __global__ void __launch_bounds__(160, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ out, long long ld_out,
-                     float* __restrict__ lse_out, int S, int n_heads, int kv_group, float scale) {
+                     float* __restrict__ lse_out, int Sq, int Skv, int n_heads, int kv_group, int q_shared,
+                     float scale) {
   // kv_group = query heads per key/value head (1 = MHA; 4 = Mistral-7B's 32/8 GQA,
   // omnilmm/model/omnilmm.py -> HF MistralForCausalLM): K/V tiles come from head / kv_group.
+  // Sq != Skv / q_shared: cross-attention of the perceiver resampler (omnilmm/model/resampler.py:149-168):
+  // 64 learned queries, identical for every image (q_shared: Q is read from sequence 0), over Skv vision tokens.
   using Cfg = AttFwdCfg<D>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -64,12 +67,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_q_tiles = (S + ATT_BQ - 1) / ATT_BQ;
+  const int num_q_tiles = (Sq + ATT_BQ - 1) / ATT_BQ;
   const int q_tile = num_q_tiles - 1 - blockIdx.x;  // heavy (late) tiles first
   const int head = blockIdx.y, seq = blockIdx.z;
+  const int q_seq = q_shared ? 0 : seq;
   const int kv_head = head / kv_group;
   const int q0 = q_tile * ATT_BQ;
-  const int n_kv = CAUSAL ? (q_tile + 1) : (S + ATT_BKV - 1) / ATT_BKV;
+  const int n_kv = CAUSAL ? (q_tile + 1) : (Skv + ATT_BKV - 1) / ATT_BKV;
 
   if (warp == 4) {
     if (lane == 0) {
@@ -126,7 +130,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       mbar_arrive_expect_tx(q_full, Cfg::Q_BYTES);
 #pragma unroll
       for (int a = 0; a < D / 64; ++a)
-        tma_load_3d(smem + Cfg::OFF_Q + a * (ATT_BQ * 128), &tmQ, q_full, head * D + a * 64, q0, seq);
+        tma_load_3d(smem + Cfg::OFF_Q + a * (ATT_BQ * 128), &tmQ, q_full, head * D + a * 64, q0, q_seq);
       load_kv(0);
       if (n_kv > 1) load_kv(1);
       mbar_wait(q_full, 0);
@@ -165,7 +169,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       const int kv0 = j * ATT_BKV;
-      const bool need_mask = (kv0 + ATT_BKV > S) || (CAUSAL && j == q_tile);
+      const bool need_mask = (kv0 + ATT_BKV > Skv) || (CAUSAL && j == q_tile);
       // single pass over S: the whole 128-column row is pulled into registers with two async
       // TMEM loads (one wait), then max / exp2 / pack run from registers.
       uint32_t v[128];
@@ -176,7 +180,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
         for (int i = 0; i < 128; ++i) {
           const int kv = kv0 + i;
-          if ((kv >= S) || (CAUSAL && kv > q_idx)) v[i] = 0xff800000u;   // -inf
+          if ((kv >= Skv) || (CAUSAL && kv > q_idx)) v[i] = 0xff800000u;   // -inf
         }
       }
       float mx = -INFINITY;
@@ -232,8 +236,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     mbar_wait(o_done, (n_kv - 1) & 1);
     tc_fence_after();
     const float inv = 1.f / l;
-    const bool row_ok = q_idx < S;
-    bf16* o_row = out + ((long long)seq * S + q_idx) * ld_out + head * D;
+    const bool row_ok = q_idx < Sq;
+    bf16* o_row = out + ((long long)seq * Sq + q_idx) * ld_out + head * D;
 #pragma unroll 1
     for (int ch = 0; ch < D / 32; ++ch) {
       uint32_t v[32];
@@ -252,7 +256,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
     }
     if (row_ok && lse_out)
-      lse_out[((long long)seq * n_heads + head) * S + q_idx] = (m_used + log2f(l)) * LN2;
+      lse_out[((long long)seq * n_heads + head) * Sq + q_idx] = (m_used + log2f(l)) * LN2;
   }
   tc_fence_before();
   __syncthreads();
@@ -263,7 +267,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 }
 
 // ================================================================================================
-// backward (causal, D = 128)
+// backward (D = 128; causal self-attention, or non-causal cross-attention with Sq != Skv)
 // ================================================================================================
 // delta[seq][head][q] = sum_d dO * O   (fp32)
 __global__ void attention_delta_kernel(const bf16* __restrict__ o, long long ld_o,
@@ -314,8 +318,11 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                      const float* __restrict__ lse, const float* __restrict__ delta,
                      float* __restrict__ dq_f32, bf16* __restrict__ dk, bf16* __restrict__ dv,
-                     long long ld_dkv, int S, int n_heads, int kv_group, float scale) {
+                     long long ld_dkv, int Sq, int Skv, int n_heads, int kv_group, int causal, int q_shared,
+                     float scale) {
   // grid.y = key/value heads; the CTA loops over the kv_group query heads that share its K/V tile.
+  // q_shared: Q (and the dQ accumulator) belong to sequence 0 for every image — the fp32 red.add then also
+  // sums dQ over the batch, which is the gradient of the resampler's shared learned queries.
   using Cfg = AttBwdCfg;
   constexpr int D = Cfg::D;
   extern __shared__ uint8_t smem_raw[];
@@ -333,12 +340,14 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   float* s_delta = reinterpret_cast<float*>(smem + Cfg::OFF_DELTA);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = (S + 127) / 128;
+  const int num_q_tiles = (Sq + 127) / 128;
   const int kv_tile = blockIdx.x;
   const int kv_head = blockIdx.y, seq = blockIdx.z;
+  const int q_seq = q_shared ? 0 : seq;
   const int kv0 = kv_tile * 128;
-  const int n_qt = num_tiles - kv_tile;     // q tiles kv_tile .. num_tiles-1 (per query head)
-  const int n_q = n_qt * kv_group;          // iterations: (query head of the group) x (q tile)
+  const int q_first = causal ? kv_tile : 0;  // causal: q tiles kv_tile .. last (per query head); else all
+  const int n_qt = num_q_tiles - q_first;
+  const int n_q = n_qt * kv_group;           // iterations: (query head of the group) x (q tile)
 
   if (warp == 4) {
     if (lane == 0) {
@@ -376,11 +385,11 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tma_load_3d(smem + Cfg::OFF_V + a * 16384, &tmV, kv_full, kv_head * D + a * 64, kv0, seq);
       }
       auto load_q = [&](int it) {
-        const int q0 = (kv_tile + it % n_qt) * 128;
+        const int q0 = (q_first + it % n_qt) * 128;
         const int head = kv_head * kv_group + it / n_qt;
         mbar_arrive_expect_tx(q_full, 2 * Cfg::TILE_BYTES);
         for (int a = 0; a < 2; ++a) {
-          tma_load_3d(smem + Cfg::OFF_Q + a * 16384, &tmQ, q_full, head * D + a * 64, q0, seq);
+          tma_load_3d(smem + Cfg::OFF_Q + a * 16384, &tmQ, q_full, head * D + a * 64, q0, q_seq);
           tma_load_3d(smem + Cfg::OFF_DO + a * 16384, &tmDO, q_full, head * D + a * 64, q0, seq);
         }
       };
@@ -435,7 +444,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
     const float c = scale * LOG2E;
     for (int it = 0; it < n_q; ++it) {
-      const int q_tile = kv_tile + it % n_qt;
+      const int q_tile = q_first + it % n_qt;
       const int head = kv_head * kv_group + it / n_qt;
       const int q0 = q_tile * 128;
       // stage LSE / delta of this q tile (previous readers finished before last pt_full arrive;
@@ -443,14 +452,14 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       asm volatile("bar.sync 1, 128;");
       {
         const int q = q0 + r;
-        const long long base = ((long long)seq * n_heads + head) * S;
-        s_lse[r] = q < S ? lse[base + q] * LOG2E : INFINITY;   // exp2(x - inf) = 0 for padded q
-        s_delta[r] = q < S ? delta[base + q] : 0.f;
+        const long long base = ((long long)seq * n_heads + head) * Sq;
+        s_lse[r] = q < Sq ? lse[base + q] * LOG2E : INFINITY;   // exp2(x - inf) = 0 for padded q
+        s_delta[r] = q < Sq ? delta[base + q] : 0.f;
       }
       asm volatile("bar.sync 1, 128;");
       mbar_wait(st_full, it & 1);
       tc_fence_after();
-      const bool diag = (q_tile == kv_tile);
+      const bool diag = causal && (q_tile == kv_tile);
       uint8_t* pt_row = smem + Cfg::OFF_PT + r * 128;
       uint8_t* dst_row = smem + Cfg::OFF_DST + r * 128;
 #pragma unroll 1
@@ -467,7 +476,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int qi = hf * 64 + g * 8 + i;
-            const bool masked = (kv_idx >= S) || (diag && kv_idx > q0 + qi);
+            const bool masked = (kv_idx >= Skv) || (diag && kv_idx > q0 + qi);
             const float pv = masked ? 0.f : fast_exp2(__uint_as_float(sv[g * 8 + i]) * c - s_lse[qi]);
             p[i] = pv;
             ds[i] = pv * (__uint_as_float(dpv[g * 8 + i]) - s_delta[qi]) * scale;
@@ -490,13 +499,13 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       tc_fence_after();
       {
         const int q = q0 + r;
-        float* dq_row = dq_f32 + ((long long)seq * S + q) * ((long long)n_heads * D) + head * D;
+        float* dq_row = dq_f32 + ((long long)q_seq * Sq + q) * ((long long)n_heads * D) + head * D;
 #pragma unroll 1
         for (int ch = 0; ch < 4; ++ch) {
           uint32_t v[32];
           tmem_ld_32x32b_x32(tmem_DQ + lane_off + ch * 32, v);
           tmem_wait_ld();
-          if (q < S) {
+          if (q < Sq) {
             // 128-bit vector reductions: 4x fewer L2 atomic operations than scalar red.add
 #pragma unroll
             for (int i = 0; i < 32; i += 4)
@@ -514,9 +523,9 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     // acc_done for the last iteration was already waited above
     tc_fence_after();
     {
-      const bool row_ok = kv_idx < S;  // loads stay warp-convergent; only the stores are predicated
-      bf16* dv_row = dv + ((long long)seq * S + kv_idx) * ld_dkv + kv_head * D;
-      bf16* dk_row = dk + ((long long)seq * S + kv_idx) * ld_dkv + kv_head * D;
+      const bool row_ok = kv_idx < Skv;  // loads stay warp-convergent; only the stores are predicated
+      bf16* dv_row = dv + ((long long)seq * Skv + kv_idx) * ld_dkv + kv_head * D;
+      bf16* dk_row = dk + ((long long)seq * Skv + kv_idx) * ld_dkv + kv_head * D;
 #pragma unroll 1
       for (int ch = 0; ch < 4; ++ch) {
         uint32_t a[32], b[32];
@@ -559,8 +568,8 @@ static int make_qkv_tmap(CUtensorMap* tm, const void* ptr, long long ld, int nse
 
 template <int D, bool CAUSAL>
 static int launch_att_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, bf16* out,
-                          long long ld_out, float* lse, int nseq, int S, int n_heads, int kv_group, float scale,
-                          cudaStream_t st) {
+                          long long ld_out, float* lse, int nseq, int Sq, int Skv, int n_heads, int kv_group,
+                          int q_shared, float scale, cudaStream_t st) {
   using Cfg = AttFwdCfg<D>;
   auto kern = attention_fwd_kernel<D, CAUSAL>;
   static bool configured = false;
@@ -568,8 +577,8 @@ static int launch_att_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CU
     B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
     configured = true;
   }
-  dim3 grid((S + ATT_BQ - 1) / ATT_BQ, n_heads, nseq);
-  kern<<<grid, 160, Cfg::SMEM_BYTES, st>>>(tq, tk, tv, out, ld_out, lse, S, n_heads, kv_group, scale);
+  dim3 grid((Sq + ATT_BQ - 1) / ATT_BQ, n_heads, nseq);
+  kern<<<grid, 160, Cfg::SMEM_BYTES, st>>>(tq, tk, tv, out, ld_out, lse, Sq, Skv, n_heads, kv_group, q_shared, scale);
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -578,74 +587,89 @@ static int launch_att_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CU
 
 using namespace b200;
 
-static int attention_fwd_impl(const void* q, const void* k, const void* v, long long ld_qkv, void* out,
-                              long long ld_out, float* lse, int nseq, int S, int n_heads, int n_kv_heads,
-                              int head_dim, int causal, float scale, void* stream) {
+static int attention_fwd_impl(const void* q, long long ld_q, const void* k, const void* v, long long ld_kv, void* out,
+                              long long ld_out, float* lse, int nseq, int Sq, int Skv, int n_heads, int n_kv_heads,
+                              int head_dim, int causal, int q_shared, float scale, void* stream) {
   B200_REQUIRE(head_dim == 128 || head_dim == 64, "attention_fwd: head_dim %d not in {64,128}", head_dim);
-  B200_REQUIRE(ld_qkv % 8 == 0 && ld_out % 8 == 0, "attention_fwd: ld must be a multiple of 8");
+  B200_REQUIRE(ld_q % 8 == 0 && ld_kv % 8 == 0 && ld_out % 8 == 0, "attention_fwd: ld must be a multiple of 8");
   B200_REQUIRE(n_kv_heads > 0 && n_heads % n_kv_heads == 0, "attention_fwd: n_heads %d not a multiple of n_kv_heads %d",
                n_heads, n_kv_heads);
+  B200_REQUIRE(!causal || Sq == Skv, "attention_fwd: causal needs Sq == Skv (%d vs %d)", Sq, Skv);
+  B200_REQUIRE(nseq > 0 && Sq > 0 && Skv > 0, "attention_fwd: empty problem");
   CUtensorMap tq, tk, tv;
   int rc;
-  if ((rc = make_qkv_tmap(&tq, q, ld_qkv, nseq, S, n_heads * head_dim))) return rc;
-  if ((rc = make_qkv_tmap(&tk, k, ld_qkv, nseq, S, n_kv_heads * head_dim))) return rc;
-  if ((rc = make_qkv_tmap(&tv, v, ld_qkv, nseq, S, n_kv_heads * head_dim))) return rc;
+  if ((rc = make_qkv_tmap(&tq, q, ld_q, q_shared ? 1 : nseq, Sq, n_heads * head_dim))) return rc;
+  if ((rc = make_qkv_tmap(&tk, k, ld_kv, nseq, Skv, n_kv_heads * head_dim))) return rc;
+  if ((rc = make_qkv_tmap(&tv, v, ld_kv, nseq, Skv, n_kv_heads * head_dim))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int g = n_heads / n_kv_heads;
+  bf16* o = (bf16*)out;
   if (head_dim == 128) {
-    return causal ? launch_att_fwd<128, true>(tq, tk, tv, (bf16*)out, ld_out, lse, nseq, S, n_heads, g, scale, st)
-                  : launch_att_fwd<128, false>(tq, tk, tv, (bf16*)out, ld_out, lse, nseq, S, n_heads, g, scale, st);
+    return causal ? launch_att_fwd<128, true>(tq, tk, tv, o, ld_out, lse, nseq, Sq, Skv, n_heads, g, q_shared, scale, st)
+                  : launch_att_fwd<128, false>(tq, tk, tv, o, ld_out, lse, nseq, Sq, Skv, n_heads, g, q_shared, scale, st);
   }
-  return causal ? launch_att_fwd<64, true>(tq, tk, tv, (bf16*)out, ld_out, lse, nseq, S, n_heads, g, scale, st)
-                : launch_att_fwd<64, false>(tq, tk, tv, (bf16*)out, ld_out, lse, nseq, S, n_heads, g, scale, st);
+  return causal ? launch_att_fwd<64, true>(tq, tk, tv, o, ld_out, lse, nseq, Sq, Skv, n_heads, g, q_shared, scale, st)
+                : launch_att_fwd<64, false>(tq, tk, tv, o, ld_out, lse, nseq, Sq, Skv, n_heads, g, q_shared, scale, st);
 }
 
 extern "C" int rlaifv_attention_fwd(const void* q, const void* k, const void* v, long long ld_qkv, void* out,
                                     long long ld_out, float* lse, int nseq, int S, int n_heads, int head_dim,
                                     int causal, float scale, void* stream) {
-  return attention_fwd_impl(q, k, v, ld_qkv, out, ld_out, lse, nseq, S, n_heads, n_heads, head_dim, causal, scale,
-                            stream);
+  return attention_fwd_impl(q, ld_qkv, k, v, ld_qkv, out, ld_out, lse, nseq, S, S, n_heads, n_heads, head_dim, causal, 0,
+                            scale, stream);
 }
 // grouped-query attention: k/v hold n_kv_heads heads, query head h reads kv head h / (n_heads / n_kv_heads)
 extern "C" int rlaifv_attention_fwd_gqa(const void* q, const void* k, const void* v, long long ld_qkv, void* out,
                                         long long ld_out, float* lse, int nseq, int S, int n_heads, int n_kv_heads,
                                         int head_dim, int causal, float scale, void* stream) {
-  return attention_fwd_impl(q, k, v, ld_qkv, out, ld_out, lse, nseq, S, n_heads, n_kv_heads, head_dim, causal, scale,
-                            stream);
+  return attention_fwd_impl(q, ld_qkv, k, v, ld_qkv, out, ld_out, lse, nseq, S, S, n_heads, n_kv_heads, head_dim,
+                            causal, 0, scale, stream);
+}
+// Cross-attention (non-causal): q [(q_shared ? 1 : nseq) * Sq rows][ld_q], k/v [nseq * Skv rows][ld_kv], out
+// [nseq * Sq rows][ld_out], lse fp32 [nseq][n_heads][Sq]. Replaces nn.MultiheadAttention's core inside
+// Resampler.forward (omnilmm/model/resampler.py:158-163): q_shared = the learned queries are batch-independent.
+extern "C" int rlaifv_cross_attention_fwd(const void* q, long long ld_q, const void* k, const void* v, long long ld_kv,
+                                          void* out, long long ld_out, float* lse, int nseq, int Sq, int Skv,
+                                          int n_heads, int head_dim, int q_shared, float scale, void* stream) {
+  return attention_fwd_impl(q, ld_q, k, v, ld_kv, out, ld_out, lse, nseq, Sq, Skv, n_heads, n_heads, head_dim, 0,
+                            q_shared, scale, stream);
 }
 
-static int attention_bwd_impl(const void* q, const void* k, const void* v, long long ld_qkv, const void* out,
-                              long long ld_out, const void* d_out, long long ld_dout, const float* lse, float* dq_f32,
-                              void* dk, void* dv, long long ld_dkv, float* delta_ws, int nseq, int S, int n_heads,
-                              int n_kv_heads, int head_dim, float scale, void* stream) {
+static int attention_bwd_impl(const void* q, long long ld_q, const void* k, const void* v, long long ld_kv,
+                              const void* out, long long ld_out, const void* d_out, long long ld_dout, const float* lse,
+                              float* dq_f32, void* dk, void* dv, long long ld_dkv, float* delta_ws, int nseq, int Sq,
+                              int Skv, int n_heads, int n_kv_heads, int head_dim, int causal, int q_shared, float scale,
+                              void* stream) {
   B200_REQUIRE(head_dim == 128, "attention_bwd: head_dim must be 128 (got %d)", head_dim);
   B200_REQUIRE(n_kv_heads > 0 && n_heads % n_kv_heads == 0, "attention_bwd: bad head counts %d / %d", n_heads,
                n_kv_heads);
+  B200_REQUIRE(!causal || Sq == Skv, "attention_bwd: causal needs Sq == Skv (%d vs %d)", Sq, Skv);
+  B200_REQUIRE(nseq > 0 && Sq > 0 && Skv > 0, "attention_bwd: empty problem");
   cudaStream_t st = (cudaStream_t)stream;
   {
-    const long long total = (long long)nseq * S * n_heads;
+    const long long total = (long long)nseq * Sq * n_heads;
     long long blocks = (total + 7) / 8;
     if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
     attention_delta_kernel<<<(int)blocks, 256, 0, st>>>((const bf16*)out, ld_out, (const bf16*)d_out, ld_dout,
-                                                        delta_ws, nseq, S, n_heads, head_dim);
+                                                        delta_ws, nseq, Sq, n_heads, head_dim);
     B200_CHECK_CUDA(cudaGetLastError());
   }
   CUtensorMap tq, tk, tv, tdo;
   int rc;
-  if ((rc = make_qkv_tmap(&tq, q, ld_qkv, nseq, S, n_heads * head_dim))) return rc;
-  if ((rc = make_qkv_tmap(&tk, k, ld_qkv, nseq, S, n_kv_heads * head_dim))) return rc;
-  if ((rc = make_qkv_tmap(&tv, v, ld_qkv, nseq, S, n_kv_heads * head_dim))) return rc;
-  if ((rc = make_qkv_tmap(&tdo, d_out, ld_dout, nseq, S, n_heads * head_dim))) return rc;
+  if ((rc = make_qkv_tmap(&tq, q, ld_q, q_shared ? 1 : nseq, Sq, n_heads * head_dim))) return rc;
+  if ((rc = make_qkv_tmap(&tk, k, ld_kv, nseq, Skv, n_kv_heads * head_dim))) return rc;
+  if ((rc = make_qkv_tmap(&tv, v, ld_kv, nseq, Skv, n_kv_heads * head_dim))) return rc;
+  if ((rc = make_qkv_tmap(&tdo, d_out, ld_dout, nseq, Sq, n_heads * head_dim))) return rc;
   static bool configured = false;
   if (!configured) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)AttBwdCfg::SMEM_BYTES));
     configured = true;
   }
-  dim3 grid((S + 127) / 128, n_kv_heads, nseq);
+  dim3 grid((Skv + 127) / 128, n_kv_heads, nseq);
   attention_bwd_kernel<<<grid, 160, AttBwdCfg::SMEM_BYTES, st>>>(tq, tk, tv, tdo, lse, delta_ws, dq_f32, (bf16*)dk,
-                                                                 (bf16*)dv, ld_dkv, S, n_heads, n_heads / n_kv_heads,
-                                                                 scale);
+                                                                 (bf16*)dv, ld_dkv, Sq, Skv, n_heads,
+                                                                 n_heads / n_kv_heads, causal, q_shared, scale);
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -656,8 +680,8 @@ extern "C" int rlaifv_attention_bwd(const void* q, const void* k, const void* v,
                                     const float* lse, float* dq_f32, void* dk, void* dv, long long ld_dkv,
                                     float* delta_ws, int nseq, int S, int n_heads, int head_dim, float scale,
                                     void* stream) {
-  return attention_bwd_impl(q, k, v, ld_qkv, out, ld_out, d_out, ld_dout, lse, dq_f32, dk, dv, ld_dkv, delta_ws, nseq,
-                            S, n_heads, n_heads, head_dim, scale, stream);
+  return attention_bwd_impl(q, ld_qkv, k, v, ld_qkv, out, ld_out, d_out, ld_dout, lse, dq_f32, dk, dv, ld_dkv, delta_ws,
+                            nseq, S, S, n_heads, n_heads, head_dim, 1, 0, scale, stream);
 }
 // GQA: dk/dv hold n_kv_heads heads (sum over the query heads of each group is formed in TMEM).
 extern "C" int rlaifv_attention_bwd_gqa(const void* q, const void* k, const void* v, long long ld_qkv,
@@ -665,6 +689,17 @@ extern "C" int rlaifv_attention_bwd_gqa(const void* q, const void* k, const void
                                         const float* lse, float* dq_f32, void* dk, void* dv, long long ld_dkv,
                                         float* delta_ws, int nseq, int S, int n_heads, int n_kv_heads, int head_dim,
                                         float scale, void* stream) {
-  return attention_bwd_impl(q, k, v, ld_qkv, out, ld_out, d_out, ld_dout, lse, dq_f32, dk, dv, ld_dkv, delta_ws, nseq,
-                            S, n_heads, n_kv_heads, head_dim, scale, stream);
+  return attention_bwd_impl(q, ld_qkv, k, v, ld_qkv, out, ld_out, d_out, ld_dout, lse, dq_f32, dk, dv, ld_dkv, delta_ws,
+                            nseq, S, S, n_heads, n_kv_heads, head_dim, 1, 0, scale, stream);
+}
+// Cross-attention backward (non-causal, head_dim 128). dq_f32 fp32 [(q_shared ? 1 : nseq) * Sq][n_heads*128],
+// zeroed by the caller (with q_shared it receives the sum over the batch); dk/dv bf16 [nseq * Skv rows][ld_dkv];
+// delta_ws fp32 [nseq * n_heads * Sq].
+extern "C" int rlaifv_cross_attention_bwd(const void* q, long long ld_q, const void* k, const void* v, long long ld_kv,
+                                          const void* out, long long ld_out, const void* d_out, long long ld_dout,
+                                          const float* lse, float* dq_f32, void* dk, void* dv, long long ld_dkv,
+                                          float* delta_ws, int nseq, int Sq, int Skv, int n_heads, int head_dim,
+                                          int q_shared, float scale, void* stream) {
+  return attention_bwd_impl(q, ld_q, k, v, ld_kv, out, ld_out, d_out, ld_dout, lse, dq_f32, dk, dv, ld_dkv, delta_ws,
+                            nseq, Sq, Skv, n_heads, n_heads, head_dim, 0, q_shared, scale, stream);
 }

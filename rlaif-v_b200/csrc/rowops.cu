@@ -232,6 +232,99 @@ layernorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
   }
 }
 
+// LayerNorm backward (trainable LayerNorms of the perceiver resampler, omnilmm/model/resampler.py:137-141).
+// Statistics are recomputed from x (fp32). xhat = (x-mean)*rstd, g = w*dy:
+//   dx = rstd * (g - mean(g) - xhat * mean(g*xhat));  dw[h] += sum_rows dy*xhat;  db[h] += sum_rows dy
+// dw / db are accumulated per CTA in registers and written to partial[2][grid][H] (fp32).
+__global__ void __launch_bounds__(NORM_THREADS)
+layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ w,
+                     bf16* __restrict__ dx, float* __restrict__ dw_partial, float* __restrict__ db_partial,
+                     int M, int H, float eps) {
+  const int nch = H >> 3;
+  float dwacc[NORM_MAXCH][8], dbacc[NORM_MAXCH][8];
+#pragma unroll
+  for (int i = 0; i < NORM_MAXCH; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { dwacc[i][j] = 0.f; dbacc[i][j] = 0.f; }
+  for (long long row = blockIdx.x; row < M; row += gridDim.x) {
+    const bf16* xr = x + row * H;
+    const bf16* dyr = dy + row * H;
+    float xv[NORM_MAXCH][8], g[NORM_MAXCH][8];
+    float s = 0.f, ss = 0.f;
+#pragma unroll
+    for (int ci = 0; ci < NORM_MAXCH; ++ci) {
+      const int c = threadIdx.x + ci * NORM_THREADS;
+      if (c >= nch) continue;
+      load8(xr + c * 8, xv[ci]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s += xv[ci][j]; ss += xv[ci][j] * xv[ci][j]; }
+    }
+    const float2 tot = block_sum2(s, ss);
+    const float mean = tot.x / (float)H;
+    const float var = fmaxf(tot.y / (float)H - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int ci = 0; ci < NORM_MAXCH; ++ci) {
+      const int c = threadIdx.x + ci * NORM_THREADS;
+      if (c >= nch) continue;
+      float dv[8], wv[8];
+      load8(dyr + c * 8, dv);
+      load8(w + c * 8, wv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        xv[ci][j] = (xv[ci][j] - mean) * rstd;     // xhat
+        g[ci][j] = wv[j] * dv[j];
+        sg += g[ci][j];
+        sgx += g[ci][j] * xv[ci][j];
+        dwacc[ci][j] += dv[j] * xv[ci][j];
+        dbacc[ci][j] += dv[j];
+      }
+    }
+    const float2 t2 = block_sum2(sg, sgx);
+    const float mg = t2.x / (float)H, mgx = t2.y / (float)H;
+#pragma unroll
+    for (int ci = 0; ci < NORM_MAXCH; ++ci) {
+      const int c = threadIdx.x + ci * NORM_THREADS;
+      if (c >= nch) continue;
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = rstd * (g[ci][j] - mg - xv[ci][j] * mgx);
+      store8(dx + row * H + c * 8, o);
+    }
+  }
+#pragma unroll
+  for (int ci = 0; ci < NORM_MAXCH; ++ci) {
+    const int c = threadIdx.x + ci * NORM_THREADS;
+    if (c >= nch) continue;
+    float* dst = dw_partial + (long long)blockIdx.x * H + c * 8;
+    *reinterpret_cast<float4*>(dst) = make_float4(dwacc[ci][0], dwacc[ci][1], dwacc[ci][2], dwacc[ci][3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(dwacc[ci][4], dwacc[ci][5], dwacc[ci][6], dwacc[ci][7]);
+    dst = db_partial + (long long)blockIdx.x * H + c * 8;
+    *reinterpret_cast<float4*>(dst) = make_float4(dbacc[ci][0], dbacc[ci][1], dbacc[ci][2], dbacc[ci][3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(dbacc[ci][4], dbacc[ci][5], dbacc[ci][6], dbacc[ci][7]);
+  }
+}
+
+// y[r] = bf16(x[r] + t[r % P])  — the resampler's position-embedding adds (resampler.py:158-161): the table t
+// ([P][H], frozen sin-cos embedding) is shared by every image of the batch.
+__global__ void add_rows_bcast_kernel(const bf16* __restrict__ x, const bf16* __restrict__ t, bf16* __restrict__ y,
+                                      long long M, int P, int H) {
+  const int nch = H >> 3;
+  const long long total = M * nch;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / nch;
+    const int c = (int)(idx % nch);
+    float a[8], b[8];
+    load8(x + row * H + c * 8, a);
+    load8(t + (row % P) * (long long)H + c * 8, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += b[j];
+    store8(y + row * H + c * 8, a);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // RoPE (HF llama/modeling_llama.py:124-168): cos/sin tables are bf16 [T][D];
 // out = bf16(bf16(x*cos) + bf16(rotate_half(x)*sin)), applied in place to the q and k column blocks
@@ -893,6 +986,34 @@ extern "C" int rlaifv_layernorm_fwd(const void* x, const void* w, const void* b,
   const int grid = M < num_sms() * 8 ? M : num_sms() * 8;
   layernorm_fwd_kernel<<<grid, NORM_THREADS, 0, ST>>>((const bf16*)x, (const bf16*)w, (const bf16*)b,
                                                      (bf16*)y, M, H, eps);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// workspace: fp32 [2 * rlaifv_rmsnorm_bwd_partials() * H]; dw / db bf16 [H] (overwritten or accumulated)
+extern "C" int rlaifv_layernorm_bwd(const void* dy, const void* x, const void* w, void* dx, void* dw, void* db,
+                                    int accumulate, float* workspace, int M, int H, float eps, void* stream) {
+  B200_REQUIRE(H % 8 == 0 && H <= NORM_THREADS * 8 * NORM_MAXCH && M > 0, "layernorm_bwd: shape [%d,%d] unsupported", M,
+               H);
+  int grid = num_sms() * 2;
+  if (grid > M) grid = M;
+  float* dbp = workspace + (long long)num_sms() * 2 * H;
+  layernorm_bwd_kernel<<<grid, NORM_THREADS, 0, ST>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, (bf16*)dx,
+                                                     workspace, dbp, M, H, eps);
+  B200_CHECK_CUDA(cudaGetLastError());
+  reduce_partials_kernel<<<(H + 31) / 32, 256, 0, ST>>>(workspace, grid, H, (bf16*)dw, accumulate);
+  reduce_partials_kernel<<<(H + 31) / 32, 256, 0, ST>>>(dbp, grid, H, (bf16*)db, accumulate);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int rlaifv_add_rows_bcast(const void* x, const void* table, void* y, long long M, int P, int H,
+                                     void* stream) {
+  B200_REQUIRE(H % 8 == 0 && M > 0 && P > 0, "add_rows_bcast: bad shape");
+  const long long total = M * (H / 8);
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
+  add_rows_bcast_kernel<<<(int)blocks, 256, 0, ST>>>((const bf16*)x, (const bf16*)table, (bf16*)y, M, P, H);
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -97,6 +97,36 @@ def attention_bwd(q, k, v, out, d_out, lse, nseq, S, n_heads, head_dim, scale, d
     return dq_f32, dk, dv
 
 
+def cross_attention_fwd(q, k, v, nseq, Sq, Skv, n_heads, head_dim, scale, q_shared=True, out=None, lse=None):
+    """Non-causal cross-attention: q [(1 if q_shared else nseq)*Sq, ld_q], k/v [nseq*Skv, ld_kv] (column blocks of
+    one buffer allowed) -> out [nseq*Sq, n_heads*head_dim], lse [nseq, n_heads, Sq]."""
+    _chk(q), _chk(k), _chk(v)
+    assert k.stride(0) == v.stride(0) and q.stride(1) == 1
+    if out is None:
+        out = torch.empty((nseq * Sq, n_heads * head_dim), dtype=torch.bfloat16, device=q.device)
+    if lse is None:
+        lse = torch.empty((nseq, n_heads, Sq), dtype=torch.float32, device=q.device)
+    _l.call("rlaifv_cross_attention_fwd", _l.ptr(q), q.stride(0), _l.ptr(k), _l.ptr(v), k.stride(0), _l.ptr(out),
+            out.stride(0), _l.ptr(lse), nseq, Sq, Skv, n_heads, head_dim, int(q_shared), float(scale), _l.stream_ptr())
+    return out, lse
+
+
+def cross_attention_bwd(q, k, v, out, d_out, lse, nseq, Sq, Skv, n_heads, head_dim, scale, dq_f32, dk, dv,
+                        q_shared=True, delta_ws=None):
+    """dq_f32 fp32 [(1 if q_shared else nseq)*Sq, n_heads*head_dim] must be zeroed (q_shared: receives the batch sum);
+    dk/dv bf16 [nseq*Skv, ...] views with a shared row stride."""
+    _chk(q), _chk(k), _chk(v), _chk(out), _chk(d_out), _chk(dk), _chk(dv)
+    _chk(dq_f32, torch.float32), _chk(lse, torch.float32)
+    assert dk.stride(0) == dv.stride(0) and k.stride(0) == v.stride(0)
+    if delta_ws is None:
+        delta_ws = torch.empty((nseq, n_heads, Sq), dtype=torch.float32, device=q.device)
+    _l.call("rlaifv_cross_attention_bwd", _l.ptr(q), q.stride(0), _l.ptr(k), _l.ptr(v), k.stride(0), _l.ptr(out),
+            out.stride(0), _l.ptr(d_out), d_out.stride(0), _l.ptr(lse), _l.ptr(dq_f32), _l.ptr(dk), _l.ptr(dv),
+            dk.stride(0), _l.ptr(delta_ws), nseq, Sq, Skv, n_heads, head_dim, int(q_shared), float(scale),
+            _l.stream_ptr())
+    return dq_f32, dk, dv
+
+
 # --------------------------------------------------------------------------------------------
 # row kernels
 # --------------------------------------------------------------------------------------------
@@ -141,6 +171,27 @@ def layernorm_fwd(x, w, b, eps, out=None):
     if out is None:
         out = torch.empty_like(x)
     _l.call("rlaifv_layernorm_fwd", _l.ptr(x), _l.ptr(w), _l.ptr(b), _l.ptr(out), M, H, float(eps),
+            _l.stream_ptr())
+    return out
+
+
+def layernorm_bwd(dy, x, w, eps, dx, dw, db, accumulate=True):
+    """dx = layernorm'(dy) (statistics recomputed from x); dw (+)= sum_rows dy*xhat; db (+)= sum_rows dy."""
+    _chk(dy), _chk(x), _chk(w), _chk(dx), _chk(dw), _chk(db)
+    M, H = x.shape
+    ws = _norm_workspace(2 * H, x.device)
+    _l.call("rlaifv_layernorm_bwd", _l.ptr(dy), _l.ptr(x), _l.ptr(w), _l.ptr(dx), _l.ptr(dw), _l.ptr(db),
+            int(accumulate), _l.ptr(ws), M, H, float(eps), _l.stream_ptr())
+    return dx
+
+
+def add_rows_bcast(x, table, out=None):
+    """out[r] = x[r] + table[r % P] (position-embedding add shared by every image of the batch)."""
+    _chk(x), _chk(table)
+    assert x.shape[1] == table.shape[1] and x.is_contiguous() and table.is_contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    _l.call("rlaifv_add_rows_bcast", _l.ptr(x), _l.ptr(table), _l.ptr(out), x.shape[0], table.shape[0], x.shape[1],
             _l.stream_ptr())
     return out
 

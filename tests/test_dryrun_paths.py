@@ -60,3 +60,33 @@ def test_launch_sequence_dry_run(monkeypatch, use_lora, cfg_name):
     assert calls.count("rlaifv_attention_bwd_gqa" if gqa else "rlaifv_attention_bwd") == dims.num_layers
     names = {b.name for b in pol.trainable_buckets()}
     assert ("projector" in names) and (("lora0" in names) == use_lora) and (("embed" in names) != use_lora)
+
+
+def test_resampler_launch_sequence_dry_run(monkeypatch):
+    """Perceiver resampler (config d piece): forward + backward orchestration against the recording C ABI."""
+    from rlaifv_b200 import lib, ops
+    from rlaifv_b200.resampler import Resampler
+    from oracle import resampler_oracle as R
+    calls = []
+
+    def fake_call(name, *args):
+        assert len(args) == len(lib._SIGNATURES[name]), name
+        calls.append(name)
+
+    monkeypatch.setattr(lib, "call", fake_call)
+    monkeypatch.setattr(lib, "stream_ptr", lambda: ctypes.c_void_p(0))
+    monkeypatch.setattr(lib, "load", lambda: type("L", (), {"rlaifv_rmsnorm_bwd_partials": staticmethod(lambda: 4)})())
+    monkeypatch.setattr(ops, "_chk", lambda t, dtype=None: t)
+    c = R.TINY_R
+    m = Resampler(c.grid_size, c.embed_dim, c.num_heads, c.kv_dim, device="cpu", state=R.make_resampler_params(c, 1))
+    assert set(m.state_dict()) == set(R.PARAM_SHAPES(c)) | {"pos_embed"}
+    x = torch.zeros(3, c.kv_tokens, c.kv_dim, dtype=torch.bfloat16)
+    y = m(x)
+    assert y.shape == (3, c.num_queries, c.embed_dim)
+    assert calls.count("rlaifv_cross_attention_fwd") == 1 and calls.count("rlaifv_layernorm_fwd") == 3
+    dx = m.backward(torch.zeros_like(y))
+    assert dx.shape == x.shape
+    assert calls.count("rlaifv_cross_attention_bwd") == 1 and calls.count("rlaifv_layernorm_bwd") == 3
+    # bicubic position table for the 12x12 vision grid was prepared from the 4x4 query grid
+    assert m._pos_for(144).shape == (144, c.embed_dim)
+    assert torch.allclose(m.pos_embed_f32, R.sincos_2d(c.embed_dim, c.grid_size), atol=1e-6)
