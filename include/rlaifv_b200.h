@@ -160,6 +160,13 @@ int rlaifv_splice_count(const long long* ids, int nseq, int L, int P, int max_le
 int rlaifv_splice_map(const long long* ids, const long long* labels, const int* n_img, const int* img_index,
                       int nseq, int L, int P, int T, int max_len, int* src, long long* new_labels,
                       void* stream);
+/* OmniLMM in-place splice map (omnilmm/model/omnilmm.py:219-258): src[b][t] = t for text rows, -1-(block*num_query+j)
+ * for the j-th row after an <im_start>; blocks consumed in batch order through img_index; length unchanged.
+ * status (int32[1], zeroed by the caller): bit0 = unequal <im_start>/<im_end> counts, bit1 = <im_end> not at
+ * start+num_query+1 — the two ValueErrors of omnilmm.py:234-247. */
+int rlaifv_splice_map_inplace(const long long* ids, const int* img_index, int nseq, int L, int num_query,
+                              long long im_patch, long long im_start, long long im_end, int* src, int* status,
+                              void* stream);
 int rlaifv_splice_gather(const int* src, const long long* ids, const void* embed, const void* feat, void* out,
                          int nseq, int L, int T, int H, void* stream);
 int rlaifv_splice_scatter(const int* src, const long long* ids, const void* dx, float* d_embed, float* d_feat,

@@ -633,6 +633,54 @@ __global__ void splice_map_kernel(const long long* __restrict__ ids,
     nl[t] = IGNORE_INDEX;
   }
 }
+// In-place splice map of OmniLMM (omnilmm/model/omnilmm.py:219-258): the sequence already holds
+// <im_start> <im_patch>*Q <im_end>; the Q rows after each <im_start> take the image's resampled features, every
+// other row keeps its token embedding (src[b][t] = t), the length does not change. Feature blocks are consumed in
+// batch order (cur_image_idx); a sequence without <im_patch> consumes none. status bit0: #<im_start> != #<im_end>,
+// bit1: <im_end> not at start+Q+1 (the reference raises ValueError for both). One warp walks the whole batch.
+__global__ void splice_map_inplace_kernel(const long long* __restrict__ ids, const int* __restrict__ img_index,
+                                          int nseq, int L, int Q, long long im_patch, long long im_start,
+                                          long long im_end, int* __restrict__ src, int* __restrict__ status) {
+  const int lane = threadIdx.x;
+  int slot = 0;
+  for (int b = 0; b < nseq; ++b) {
+    const long long* row = ids + (long long)b * L;
+    int* sr = src + (long long)b * L;
+    int np = 0, ns = 0, ne = 0;
+    for (int j = lane; j < L; j += 32) {
+      const long long t = row[j];
+      np += (t == im_patch);
+      ns += (t == im_start);
+      ne += (t == im_end);
+      sr[j] = j;
+    }
+    np = __reduce_add_sync(0xffffffffu, np);
+    ns = __reduce_add_sync(0xffffffffu, ns);
+    ne = __reduce_add_sync(0xffffffffu, ne);
+    __syncwarp();
+    if (np == 0) continue;
+    if (ns != ne) {
+      if (lane == 0) atomicOr(status, 1);
+      continue;
+    }
+    for (int base = 0; base < L; base += 32) {
+      const int j = base + lane;
+      const bool is_start = j < L && row[j] == im_start;
+      const unsigned mask = __ballot_sync(0xffffffffu, is_start);
+      if (is_start) {
+        const int k = __popc(mask & ((1u << lane) - 1));
+        if (j + Q + 1 >= L || row[j + Q + 1] != im_end) {
+          atomicOr(status, 2);
+        } else {
+          const int blk = img_index[slot + k];
+          for (int q = 0; q < Q; ++q) sr[j + 1 + q] = -1 - (blk * Q + q);
+        }
+      }
+      slot += __popc(mask);
+      __syncwarp();
+    }
+  }
+}
 // row gather: out[b][t][:] = embed[ids[b][src]] | feat[-1-src] | 0     (bit-exact copies)
 __global__ void splice_gather_kernel(const int* __restrict__ src, const long long* __restrict__ ids,
                                      const bf16* __restrict__ embed, const bf16* __restrict__ feat,
@@ -1129,6 +1177,15 @@ extern "C" int rlaifv_splice_map(const long long* ids, const long long* labels, 
                                  const int* img_index, int nseq, int L, int P, int T, int max_len, int* src,
                                  long long* new_labels, void* stream) {
   splice_map_kernel<<<nseq, 32, 0, ST>>>(ids, labels, n_img, img_index, nseq, L, P, T, max_len, src, new_labels);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int rlaifv_splice_map_inplace(const long long* ids, const int* img_index, int nseq, int L, int num_query,
+                                         long long im_patch, long long im_start, long long im_end, int* src,
+                                         int* status, void* stream) {
+  B200_REQUIRE(nseq > 0 && L > 0 && num_query > 0, "splice_map_inplace: bad shape");
+  splice_map_inplace_kernel<<<1, 32, 0, ST>>>(ids, img_index, nseq, L, num_query, im_patch, im_start, im_end, src,
+                                              status);
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -118,8 +118,8 @@ class DPOStepEngine:
                                accumulate=mi > 0)
         pol.finalize_embed_grad()
         if self.world > 1:
-            self.opt.reduce_bucket("embed")
-            self.opt.reduce_bucket("projector")
+            for name in pol.tail_bucket_names():
+                self.opt.reduce_bucket(name)
         if optimizer_step:
             self.opt.finish_step()
             self.global_step += 1

@@ -46,6 +46,15 @@ class LlavaDims:
     patch_size: int = 14
     clip_eps: float = 1e-5
     select_layer: int = -2
+    # vision front-end: "clip_mlp" = frozen CLIP tower + trainable mlp2x_gelu projector (LLaVA-1.5);
+    # "resampler" = OmniLMM-12B: external vision-tower tokens -> trainable perceiver resampler -> in-place
+    # <im_patch> splice (omnilmm_model.OmniLMMDPOPolicy; omnilmm/model/omnilmm.py:107-120, 183-265)
+    frontend: str = "clip_mlp"
+    num_query: int = 64            # resampler queries = <im_patch> tokens per image (omnilmm.py:46-51)
+    vision_width: int = 1792       # EVA-02-E token width
+    im_patch_token: int = -1
+    im_start_token: int = -1
+    im_end_token: int = -1
 
     @property
     def head_dim(self):
@@ -136,7 +145,8 @@ class ParamStore:
                         (f"l{i}.down", (H, F))],
                        [(f"l{i}.ln1", (H,)), (f"l{i}.ln2", (H,))])
         add_bucket("head", [("lm_head", (V, H))], [("norm", (H,))])
-        add_bucket("projector", [("proj.w0", (H, C)), ("proj.w2", (H, H))], [("proj.b0", (H,)), ("proj.b2", (H,))])
+        if d.frontend == "clip_mlp":
+            add_bucket("projector", [("proj.w0", (H, C)), ("proj.w2", (H, H))], [("proj.b0", (H,)), ("proj.b2", (H,))])
         self.numel = off
         self.flat = torch.zeros(off, dtype=_BF, device=device)
         self.grad = torch.zeros(off, dtype=_BF, device=device)
@@ -153,9 +163,10 @@ class ParamStore:
         d = self.dims
         H, F, KV = d.hidden_size, d.intermediate_size, d.kv_size
         out = {"model.embed_tokens.weight": self.p["embed"], "model.norm.weight": self.p["norm"],
-               "lm_head.weight": self.p["lm_head"],
-               "model.mm_projector.0.weight": self.p["proj.w0"], "model.mm_projector.0.bias": self.p["proj.b0"],
-               "model.mm_projector.2.weight": self.p["proj.w2"], "model.mm_projector.2.bias": self.p["proj.b2"]}
+               "lm_head.weight": self.p["lm_head"]}
+        if d.frontend == "clip_mlp":
+            out.update({"model.mm_projector.0.weight": self.p["proj.w0"], "model.mm_projector.0.bias": self.p["proj.b0"],
+                        "model.mm_projector.2.weight": self.p["proj.w2"], "model.mm_projector.2.bias": self.p["proj.b2"]})
         for i in range(d.num_layers):
             pre = f"model.layers.{i}."
             qkv, gu = self.p[f"l{i}.qkv"], self.p[f"l{i}.gu"]
@@ -334,12 +345,13 @@ class LlavaDPOPolicy:
         self.dims = dims
         self.device = torch.device(device)
         self.store = ParamStore(dims, self.device)
+        has_clip = dims.frontend == "clip_mlp"
         if hf_state is not None:
             self.store.load_hf(hf_state)
-            self.clip = ClipWeights(dims, self.device, hf_state)
+            self.clip = ClipWeights(dims, self.device, hf_state) if has_clip else None
         else:
             self._random_init(seed, init_std)
-            self.clip = ClipWeights(dims, self.device, None, seed + 1)
+            self.clip = ClipWeights(dims, self.device, None, seed + 1) if has_clip else None
         self._rope = {}
         self._bufs = {}
         # True: also stash the normalised inputs and the SwiGLU product (22 KB/token/layer more memory,
@@ -381,6 +393,10 @@ class LlavaDPOPolicy:
 
     def layer_bucket_name(self, i):
         return f"layer{i}" if self.lora is None else f"lora{i}"
+
+    def tail_bucket_names(self):
+        """Buckets whose gradients are final only after the whole backward (reduced at the end of the step)."""
+        return ["embed", "projector"]
 
     # ---- one linear group = base GEMM (+ LoRA adapters sharing the input) ----
     _GROUPS = {"qkv": ("A_qkv", ("B_q", "B_k", "B_v"), "B_qkv"), "o": ("A_o", ("B_o",), "B_o_cat"),
@@ -604,11 +620,7 @@ class LlavaDPOPolicy:
         st = {"layers": []} if keep_stash else None
         self._fwd_count += 1
 
-        feats = self.encode_images(images)                                   # [b*Pn, C]
-        self._need("projector")
-        pre = ops.gemm(feats, P["proj.w0"], self.buf("proj_pre", (feats.shape[0], H)), bias=P["proj.b0"])
-        post = ops.gelu_fwd(pre, self.buf("proj_post", pre.shape))
-        proj = ops.gemm(post, P["proj.w2"], self.buf("proj_out", pre.shape), bias=P["proj.b2"])
+        proj = self._frontend_fwd(images, st)                                # [b*Pn, H] image rows
         # images are shared by the win and rej copy of a pair (trainers.py:190 cat([images, images]))
         n_slots = nseq
         img_index = (torch.arange(n_slots, dtype=torch.int32, device=dev) % b).contiguous() if nseq == 2 * b \
@@ -618,8 +630,8 @@ class LlavaDPOPolicy:
                                             T_hint=(T_hint, n_slots) if T_hint is not None else None)
         M = nseq * T
         if keep_stash:
-            st.update(feats=feats, proj_pre=pre, proj_post=post, src=src, input_ids=input_ids, labels=new_labels,
-                      T=T, nseq=nseq, b=b)
+            st.update(src=src, input_ids=input_ids, labels=new_labels, T=T, nseq=nseq, b=b,
+                      n_feat_rows=proj.shape[0])
         x = self._run_layers(x, nseq, T, st)
         self._need("head")
         rstd_f = torch.empty(M, dtype=_F32, device=dev) if keep_stash else None
@@ -694,19 +706,37 @@ class LlavaDPOPolicy:
             self.embed_grad_f32 = torch.zeros((V, H), dtype=_F32, device=dev)
         elif not acc:
             self.embed_grad_f32.zero_()
-        n_feat_rows = st["proj_pre"].shape[0]
+        n_feat_rows = st["n_feat_rows"]
         dfeat32 = self.buf("dfeat32", (n_feat_rows, H), _F32)
         dfeat32.zero_()
         ops.splice_scatter(st["src"], st["input_ids"], dx, None if frozen else self.embed_grad_f32, dfeat32)
         dproj = ops.f32_to_bf16(dfeat32, self.buf("dproj", (n_feat_rows, H)))
-        # ---- projector ----
+        self._frontend_bwd(dproj, st, acc)
+        self._stash = None
+
+    # ------------------------------------------------------------------ vision front-end (LLaVA-1.5: CLIP + projector)
+    def _frontend_fwd(self, images, st):
+        """images [b,3,S,S] -> projected image rows [b*P, H]; st (dict or None) receives what the backward needs."""
+        P, H = self.store.p, self.dims.hidden_size
+        feats = self.encode_images(images)                                   # [b*Pn, C]
+        self._need("projector")
+        pre = ops.gemm(feats, P["proj.w0"], self.buf("proj_pre", (feats.shape[0], H)), bias=P["proj.b0"])
+        post = ops.gelu_fwd(pre, self.buf("proj_post", pre.shape))
+        proj = ops.gemm(post, P["proj.w2"], self.buf("proj_out", pre.shape), bias=P["proj.b2"])
+        if st is not None:
+            st.update(feats=feats, proj_pre=pre, proj_post=post)
+        return proj
+
+    def _frontend_bwd(self, dproj, st, acc):
+        """dproj [b*P, H] bf16 = gradient of the image rows -> mm_projector gradients (the CLIP tower is frozen)."""
+        P, G, H = self.store.p, self.store.g, self.dims.hidden_size
+        n_feat_rows = dproj.shape[0]
         ops.gemm(dproj, st["proj_post"], G["proj.w2"], a_mn=True, b_mn=True, accumulate=acc)
         ops.colsum(dproj, G["proj.b2"], accumulate=acc)
         dpost = ops.gemm(dproj, P["proj.w2"], self.buf("dpost", (n_feat_rows, H)), b_mn=True)
         dpre = ops.gelu_bwd(st["proj_pre"], dpost, self.buf("dpre", (n_feat_rows, H)))
         ops.gemm(dpre, st["feats"], G["proj.w0"], a_mn=True, b_mn=True, accumulate=acc)
         ops.colsum(dpre, G["proj.b0"], accumulate=acc)
-        self._stash = None
 
     on_layer_grads_ready = None
     on_head_grads_ready = None

@@ -298,6 +298,17 @@ def splice_map(ids, labels, n_img, img_index, n_feat_tokens, T, max_len):
     return src, new_labels
 
 
+def splice_map_inplace(input_ids, img_index, num_query, im_patch, im_start, im_end):
+    """OmniLMM in-place splice: -> (src [nseq, L] int32, status int32[1])."""
+    assert input_ids.dtype == torch.int64 and input_ids.is_contiguous() and img_index.dtype == torch.int32
+    nseq, L = input_ids.shape
+    src = torch.empty((nseq, L), dtype=torch.int32, device=input_ids.device)
+    status = torch.zeros(1, dtype=torch.int32, device=input_ids.device)
+    _l.call("rlaifv_splice_map_inplace", _l.ptr(input_ids), _l.ptr(img_index), nseq, L, int(num_query), int(im_patch),
+            int(im_start), int(im_end), _l.ptr(src), _l.ptr(status), _l.stream_ptr())
+    return src, status
+
+
 def splice_gather(src, ids, embed, feat, out=None):
     _chk(embed), _chk(feat)
     nseq, T = src.shape

@@ -27,9 +27,13 @@ from . import ops
 _BF = torch.bfloat16
 _F32 = torch.float32
 
-PARAM_ORDER = ("query", "proj", "kv_proj.weight", "attn.in_proj_weight", "attn.in_proj_bias", "attn.out_proj.weight",
-               "attn.out_proj.bias", "ln_q.weight", "ln_q.bias", "ln_kv.weight", "ln_kv.bias", "ln_post.weight",
-               "ln_post.bias")
+# storage order = weight-decay group first (matrices and the learned queries), then what HF's Trainer exempts
+# (biases and LayerNorm parameters), so the flat buffer is one optimizer bucket with a `decay_size` prefix
+DECAY_PARAMS = ("query", "proj", "kv_proj.weight", "attn.in_proj_weight", "attn.out_proj.weight")
+NO_DECAY_PARAMS = ("attn.in_proj_bias", "attn.out_proj.bias", "ln_q.weight", "ln_q.bias", "ln_kv.weight", "ln_kv.bias",
+                   "ln_post.weight", "ln_post.bias")
+PARAM_ORDER = DECAY_PARAMS + NO_DECAY_PARAMS
+BUCKET_PAD = 1024
 
 
 def _sincos_1d(dim, pos):
@@ -70,6 +74,8 @@ class Resampler:
                   "ln_q.weight": (E,), "ln_q.bias": (E,), "ln_kv.weight": (E,), "ln_kv.bias": (E,),
                   "ln_post.weight": (E,), "ln_post.bias": (E,)}
         total = sum(int(np.prod(s)) for s in shapes.values())
+        self.decay_size = sum(int(np.prod(shapes[n])) for n in DECAY_PARAMS)
+        total = (total + BUCKET_PAD - 1) // BUCKET_PAD * BUCKET_PAD         # divisible by 8 * world for ZeRO-2 slices
         self.flat = torch.zeros(total, dtype=_BF, device=self.device)      # one flat bucket (ZeRO-2 ready)
         self.grad = torch.zeros(total, dtype=_BF, device=self.device)
         self.p, self.g, off = {}, {}, 0
@@ -111,6 +117,11 @@ class Resampler:
 
     def zero_grad(self):
         self.grad.zero_()
+
+    def opt_bucket(self, name="resampler"):
+        """The whole module as one ZeRO-2 / AdamW bucket (zero2.OptBucket)."""
+        from .zero2 import OptBucket
+        return OptBucket(name, self.flat, self.grad, self.decay_size)
 
     def _pos_for(self, n_tokens):
         if n_tokens not in self._pos_kv:

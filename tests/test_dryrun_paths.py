@@ -90,3 +90,50 @@ def test_resampler_launch_sequence_dry_run(monkeypatch):
     # bicubic position table for the 12x12 vision grid was prepared from the 4x4 query grid
     assert m._pos_for(144).shape == (144, c.embed_dim)
     assert torch.allclose(m.pos_embed_f32, R.sincos_2d(c.embed_dim, c.grid_size), atol=1e-6)
+
+
+def test_omnilmm_policy_launch_sequence_dry_run(monkeypatch):
+    """OmniLMM policy (resampler front-end + in-place splice + GQA decoder) against the recording C ABI; also runs the
+    bf16 oracle path once so the GPU parity test's CPU half is known to work."""
+    from rlaifv_b200 import lib, ops
+    from rlaifv_b200.model import LlavaDims
+    from rlaifv_b200.omnilmm_model import OmniLMMDPOPolicy, omnilmm_dims
+    from oracle import omnilmm_oracle as OM
+    calls = []
+
+    def fake_call(name, *args):
+        assert len(args) == len(lib._SIGNATURES[name]), name
+        calls.append(name)
+
+    monkeypatch.setattr(lib, "call", fake_call)
+    monkeypatch.setattr(lib, "stream_ptr", lambda: ctypes.c_void_p(0))
+    monkeypatch.setattr(lib, "load", lambda: type("L", (), {"rlaifv_rmsnorm_bwd_partials": staticmethod(lambda: 4)})())
+    monkeypatch.setattr(ops, "_chk", lambda t, dtype=None: t)
+    d, r, t = OM.TINY_OMNI_DEC, OM.TINY_OMNI_RES, OM.TINY_OMNI_TOK
+    dims = LlavaDims(frontend="resampler", vocab_size=d.vocab_size, hidden_size=d.hidden_size,
+                     intermediate_size=d.intermediate_size, num_layers=d.num_layers, num_heads=d.num_heads,
+                     num_kv_heads=d.num_kv_heads, num_query=r.num_queries, vision_width=r.kv_dim,
+                     im_patch_token=t.im_patch, im_start_token=t.im_start, im_end_token=t.im_end)
+    params = OM.make_omnilmm_params(d, r, 1)
+    pol = OmniLMMDPOPolicy(dims, "cpu", hf_state=params)
+    assert "projector" not in {b.name for b in pol.store.buckets} and pol.clip is None
+    names = [b.name for b in pol.trainable_buckets()]
+    assert names[-1] == "resampler" and "embed" in names and pol.tail_bucket_names() == ["embed", "resampler"]
+    assert all(b.size % 64 == 0 for b in pol.trainable_buckets())
+    assert set(pol.hf_views()) == set(params)
+    batch = OM.synthetic_omni_batch(d, r, t, 2, 28, 20, seed=2)
+    out = pol.forward_logps(batch["concatenated_input_ids"], batch["concatenated_labels"], batch["vision_tokens"])
+    L = batch["concatenated_input_ids"].shape[1]
+    assert out["T"] == L and out["per_token_logps"].shape == (4, L - 1)
+    pol.backward_logps(torch.zeros(4))
+    pol.finalize_embed_grad()
+    assert calls.count("rlaifv_splice_map_inplace") == 1 and calls.count("rlaifv_cross_attention_bwd") == 1
+    assert calls.count("rlaifv_attention_fwd_gqa") == d.num_layers and "rlaifv_clip_im2col" not in calls
+    assert pol.vision_token_grad.shape == batch["vision_tokens"].shape
+    full = omnilmm_dims()
+    assert full.kv_size == 1024 and full.intermediate_size == 14336 and full.vocab_size % 8 == 0
+    # bf16 evaluation order of the oracle (used as the second comparison point on the GPU)
+    pb = {k: v.to(torch.bfloat16) for k, v in params.items()}
+    ob = OM.omnilmm_policy_logps(pb, d, r, t, batch["concatenated_input_ids"], batch["concatenated_labels"],
+                                 batch["vision_tokens"].to(torch.bfloat16))
+    assert ob["logp"].shape == (4,) and bool(torch.isfinite(ob["logp"].float()).all())

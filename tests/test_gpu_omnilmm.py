@@ -1,0 +1,126 @@
+"""-m gpu: OmniLMM-12B DPO policy downstream of the vision tower (BASELINE config d) through the
+C ABI — resampler, in-place <im_patch> splice (index map bit-exact), Mistral GQA decoder, log-prob gather, DPO loss,
+full backward — against the oracle and the fixtures of the unmodified reference OmniLMMForCausalLM."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import omnilmm_oracle as OM
+
+pytestmark = pytest.mark.gpu
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "omnilmm", "*.npz")))
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+def tiny_dims():
+    from rlaifv_b200.model import LlavaDims
+    d, r, t = OM.TINY_OMNI_DEC, OM.TINY_OMNI_RES, OM.TINY_OMNI_TOK
+    return LlavaDims(frontend="resampler", vocab_size=d.vocab_size, hidden_size=d.hidden_size,
+                     intermediate_size=d.intermediate_size, num_layers=d.num_layers, num_heads=d.num_heads,
+                     num_kv_heads=d.num_kv_heads, rms_eps=d.rms_eps, num_query=r.num_queries, vision_width=r.kv_dim,
+                     im_patch_token=t.im_patch, im_start_token=t.im_start, im_end_token=t.im_end)
+
+
+def test_inplace_splice_map_bit_exact_and_errors():
+    from rlaifv_b200 import ops
+    tok, Q = OM.TINY_OMNI_TOK, 16
+    b = OM.synthetic_omni_batch(OM.TINY_OMNI_DEC, OM.TINY_OMNI_RES, tok, 3, 30, 12, seed=5)
+    ids = b["concatenated_input_ids"].clone()
+    ids[1, :] = torch.randint(3, 400, (ids.shape[1],))                          # a text-only row consumes no image
+    slots = torch.tensor([2, 0, 1, 2, 0], dtype=torch.int32)                     # arbitrary image-of-slot table
+    want = OM.inplace_splice_map(ids, tok, Q, image_of_slot=slots)
+    src, status = ops.splice_map_inplace(ids.cuda(), slots.cuda(), Q, tok.im_patch, tok.im_start, tok.im_end)
+    assert int(status.item()) == 0 and torch.equal(src.cpu().long(), want)
+    bad = ids.clone()
+    bad[0, 4 + Q + 1] = 7                                                        # <im_end> missing -> count mismatch
+    _, status = ops.splice_map_inplace(bad.cuda(), slots.cuda(), Q, tok.im_patch, tok.im_start, tok.im_end)
+    assert int(status.item()) & 1
+    bad = ids.clone()
+    bad[0, 4 + Q + 1], bad[0, 4 + Q + 3] = 7, tok.im_end                        # <im_end> displaced
+    _, status = ops.splice_map_inplace(bad.cuda(), slots.cuda(), Q, tok.im_patch, tok.im_start, tok.im_end)
+    assert int(status.item()) & 2
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_omnilmm_policy_matches_oracle_and_reference_fixture(path):
+    from rlaifv_b200 import ops
+    from rlaifv_b200.omnilmm_model import OmniLMMDPOPolicy
+    fx = np.load(path)
+    dec, res, tok = OM.TINY_OMNI_DEC, OM.TINY_OMNI_RES, OM.TINY_OMNI_TOK
+    B, seed = int(fx["B"]), int(fx["seed"])
+    params = OM.make_omnilmm_params(dec, res, seed)
+    pol = OmniLMMDPOPolicy(tiny_dims(), "cuda", hf_state=params)
+    batch = OM.synthetic_omni_batch(dec, res, tok, B, 28, 20, seed=seed + 7, ragged=bool(fx["ragged"]))
+    ids, labels, vt = batch["concatenated_input_ids"], batch["concatenated_labels"], batch["vision_tokens"]
+    out = pol.forward_logps(ids, labels, vt, keep_stash=True)
+    # integer work: bit exact
+    slots = torch.arange(2 * B) % B
+    assert torch.equal(pol._stash["src"].cpu().long(), OM.inplace_splice_map(ids, tok, res.num_queries, slots))
+    assert torch.equal(out["labels"].cpu(), labels) and out["T"] == ids.shape[1]
+    # bf16-op-order oracle on the same bf16-rounded parameters / inputs, and the fp32 reference fixture
+    pb = {k: v.to(torch.bfloat16) for k, v in params.items()}
+    ob = OM.omnilmm_policy_logps(pb, dec, res, tok, ids, labels, vt.to(torch.bfloat16))
+    logp = out["logp"].cpu()
+    ref_fp32 = torch.from_numpy(fx["logp"])
+    inherent = rel(ob["logp"], ref_fp32)
+    e_ref, e_orc = rel(logp, ref_fp32), rel(logp, ob["logp"])
+    print(f"summed logp rel err: cuda-vs-fp32ref {e_ref:.2e}, cuda-vs-bf16oracle {e_orc:.2e}, inherent {inherent:.2e}")
+    assert e_orc <= 1e-3 and e_ref <= 1e-3
+    mask = labels[:, 1:] != -100
+    pt, ref_pt = out["per_token_logps"].cpu(), torch.from_numpy(fx["per_token_logps"])
+    inh_pt = rel(ob["per_token_logps"].float()[mask], ref_pt[mask])
+    e_pt = rel(pt[mask], ref_pt[mask])
+    print(f"per-token rel err: cuda-vs-fp32ref {e_pt:.2e}, inherent {inh_pt:.2e}")
+    assert e_pt <= max(1e-3, 2.5 * inh_pt) and e_pt <= 1e-2
+    # DPO loss + backward
+    rw, rr = torch.from_numpy(fx["ref_win_logp"]).cuda(), torch.from_numpy(fx["ref_rej_logp"]).cuda()
+    losses, cr, rj, dpw, dpr, out9 = ops.dpo_loss(out["logp"][:B].contiguous(), out["logp"][B:].contiguous(), rw, rr, 0.1)
+    pol.backward_logps(torch.cat([dpw, dpr]).contiguous())
+    pol.finalize_embed_grad()
+    torch.cuda.synchronize()
+    assert rel(losses, fx["losses"]) <= 2e-2 and rel(out9[0], fx["loss"]) <= 2e-2
+    grads = dict(pol.store.hf_grad_views())
+    grads.update({"model.resampler." + k: v for k, v in pol.resampler.g.items()})
+    for key in fx.files:
+        if not key.startswith("gradnorm:"):
+            continue
+        name = key.split(":", 1)[1]
+        g = grads[name].float().flatten().cpu()
+        ref = torch.from_numpy(fx["gradsample:" + name])
+        got = g[torch.linspace(0, g.numel() - 1, min(64, g.numel())).long()]
+        gn, nrm = float(fx[key]), float(g.double().norm())
+        err, scale = float((got - ref).abs().max()), float(ref.abs().max()) + 1e-12
+        print(f"{name}: sample max err {err:.3e} (ref max {scale:.3e}); norm {nrm:.4e} vs ref {gn:.4e}")
+        assert abs(nrm - gn) <= 3e-2 * gn, name
+        assert err <= 6e-2 * scale, name
+    dv = pol.vision_token_grad.float()
+    assert abs(float(dv.norm()) - float(fx["dvision_norm"])) <= 3e-2 * float(fx["dvision_norm"])
+
+
+def test_omnilmm_engine_step_trains_decoder_and_resampler():
+    from rlaifv_b200.engine import DPOStepEngine
+    from rlaifv_b200.omnilmm_model import OmniLMMDPOPolicy
+    dec, res, tok = OM.TINY_OMNI_DEC, OM.TINY_OMNI_RES, OM.TINY_OMNI_TOK
+    pol = OmniLMMDPOPolicy(tiny_dims(), "cuda", hf_state=OM.make_omnilmm_params(dec, res, 3))
+    eng = DPOStepEngine(pol, lr=1e-3, total_steps=10, constant_lr=True, micro_pairs=1)
+    assert [b.name for b in eng.opt.buckets][-1] == "resampler"
+    batch = OM.synthetic_omni_batch(dec, res, tok, 2, 28, 20, seed=9)
+    ref = pol.forward_logps(batch["concatenated_input_ids"], batch["concatenated_labels"], batch["vision_tokens"],
+                            keep_stash=False)["logp"].float().cpu()
+    batch.update(images=batch["vision_tokens"], ref_win_logp=ref[:2], ref_rej_logp=ref[2:], beta=0.1)
+    w0, r0 = pol.store.flat.clone(), pol.resampler.flat.clone()
+    m = eng.train_step(batch)
+    torch.cuda.synchronize()
+    loss1 = float(m[0])                                     # (the engine reuses its metrics tensor)
+    assert abs(loss1 - 0.6931472) < 1e-4                    # policy == reference -> loss ln 2
+    assert not torch.equal(pol.store.flat, w0) and not torch.equal(pol.resampler.flat, r0)
+    m2 = eng.train_step(batch)
+    torch.cuda.synchronize()
+    assert float(m2[0]) < loss1                             # one AdamW step on the same batch lowers the loss
