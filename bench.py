@@ -122,12 +122,74 @@ def synthetic_batch(rank, step, B):
             "images": images.pin_memory(), "beta": 0.1}
 
 
+def synthetic_omni_batch(rank, step, B, dims, n_vision_tokens=1024):
+    """Config (d) shape downstream of the vision tower: the same 48-token prompt / 512-token responses, the image slot
+    expanded in place to <im_start> <im_patch>*64 <im_end> (omnilmm token layout), and the tower's output tokens
+    [B, 1024, 1792] (448 px / 14) as `images`."""
+    g = torch.Generator().manual_seed(1234 + 1000 * rank + step)
+    Q = dims.num_query
+    P = PROMPT_LEN - 1 + Q + 2
+    L = P + RESP_LEN
+    ids = torch.empty((2 * B, L), dtype=torch.int64)
+    labels = torch.full((2 * B, L), -100, dtype=torch.int64)
+    for i in range(B):
+        text = torch.randint(3, 32000, (PROMPT_LEN,), generator=g)
+        text[0] = 1
+        slot = torch.cat([torch.tensor([dims.im_start_token]), torch.full((Q,), dims.im_patch_token),
+                          torch.tensor([dims.im_end_token])])
+        prompt = torch.cat([text[:IMAGE_POS], slot, text[IMAGE_POS + 1:]])
+        for row in (i, B + i):
+            resp = torch.randint(3, 32000, (RESP_LEN,), generator=g)
+            resp[-1] = 2
+            ids[row] = torch.cat([prompt, resp])
+            labels[row, P:] = resp
+    tokens = torch.randn(B, n_vision_tokens, dims.vision_width, generator=g).to(torch.bfloat16)
+    return {"concatenated_input_ids": ids.pin_memory(), "concatenated_labels": labels.pin_memory(),
+            "images": tokens.pin_memory(), "beta": 0.1}
+
+
+def omni_flops_per_pair(d, T, n_vision_tokens=1024):
+    """Algorithmic FLOPs of one pair downstream of the tower: 3 x (2 sequences through the GQA decoder + head) +
+    3 x resampler (one image per pair)."""
+    H, F, KV, V = d.hidden_size, d.intermediate_size, d.kv_size, d.vocab_size
+    n_dec = d.num_layers * (2 * H * H + 2 * H * KV + 3 * H * F)
+    f_seq = 2 * (n_dec + H * V) * T + d.num_layers * 4 * T * T * H * 0.5
+    N, Q = n_vision_tokens, d.num_query
+    f_res = 2 * N * d.vision_width * H + 2 * 2 * N * H * H + 2 * Q * H * H + 4 * Q * N * H + 2 * 2 * Q * H * H
+    return 3 * 2 * f_seq + 3 * f_res
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU arm: oracle port of the reference path on the host cores, bounded sample
 # ------------------------------------------------------------------------------------------------
+CHECKER_PARAM_SCALE = 0.3   # std multiplier of oracle.make_params for the full-width checker model: random matrices at
+                            # the stock scale give per-token log-probs of -15 and attention scores of std ~10 at
+                            # h=4096 — an ill-conditioned network on which two valid evaluation orders (fp32 vs the
+                            # reference's own bf16 op order) already differ by 1e-2 in summed log-prob; at 0.3 the
+                            # logits look like a real checkpoint's (mean per-token logp -10.9 ~ ln 32000) and the two
+                            # orders agree to 5e-5 (tools/cpu_fullwidth_inherent.py)
+
+
+def full_width_case(num_layers, dtype=torch.float32):
+    """The oracle-side model / batch of the cpu_baseline leg: full width, config (a) shape (1 pair, R=64, T=687)."""
+    from oracle import llava_dpo_oracle as O
+    cfg = O.OracleConfig(num_layers=num_layers)
+    p = O.make_params(cfg, seed=0, dtype=dtype, scale=CHECKER_PARAM_SCALE)
+    for k in p:
+        if k.startswith(O.TRAINABLE_PREFIXES):
+            p[k].requires_grad_(True)
+    batch = O.synthetic_pair_batch(cfg, 1, 48, 64, seed=1234, image_pos=35)
+    batch["images"] = batch["images"].to(dtype)
+    batch["ref_win_logp"] = torch.tensor([-700.0])
+    batch["ref_rej_logp"] = torch.tensor([-690.5])
+    return cfg, p, batch
+
+
 def gpu_full_width_parity(p, cfg, batch, out):
     """Checker leg: the CUDA path on the SAME full-width 1-layer model / batch the oracle port just ran
-    (h=4096, ffn=11008, vocab=32000, CLIP-L 23 layers; config (a) shape) — log-probs, loss and gradients."""
+    (h=4096, ffn=11008, vocab=32000, CLIP-L 23 layers; config (a) shape) — log-probs, loss and gradients; plus the
+    oracle in the reference's bf16 op order as the yardstick of what bf16 storage costs by itself."""
+    from oracle import llava_dpo_oracle as O
     from rlaifv_b200 import ops
     from rlaifv_b200.model import LlavaDims, LlavaDPOPolicy
     pol = LlavaDPOPolicy(LlavaDims(num_layers=cfg.num_layers), "cuda", hf_state={k: v.detach() for k, v in p.items()})
@@ -140,10 +202,16 @@ def gpu_full_width_parity(p, cfg, batch, out):
     pol.backward_logps(torch.cat([dpw, dpr]).contiguous())
     pol.finalize_embed_grad()
     torch.cuda.synchronize()
+    with torch.no_grad():
+        pb = {k: v.detach().to(torch.bfloat16) for k, v in p.items()}
+        ob = O.policy_logps(pb, cfg, batch["concatenated_input_ids"], batch["concatenated_labels"],
+                            batch["images"].to(torch.bfloat16))
     ref_lp = out["logp"].detach().double()
     mask = (out["labels"][:, 1:] != -100)
     pt_ref = out["per_token_logps"].detach().double()[mask]
     pt_gpu = o["per_token_logps"].double().cpu()[mask]
+    pt_bf = ob["per_token_logps"].double()[mask]
+    relmax = lambda a, b: float(((a - b).abs() / b.abs()).max())
     grads = pol.store.hf_grad_views()
     gerr = {}
     for name in ("model.mm_projector.0.weight", "model.mm_projector.2.weight", "model.layers.0.self_attn.q_proj.weight",
@@ -153,15 +221,56 @@ def gpu_full_width_parity(p, cfg, batch, out):
         ref = p[name].grad.detach().double()
         got = grads[name].double().cpu().view_as(ref)
         gerr[name] = float((got - ref).norm() / (ref.norm() + 1e-300))
-    res = {"shape": "1 decoder layer at full width, 1 pair, R=64 (T=687)",
-           "logp_oracle": ref_lp.tolist(), "logp_gpu": lp.double().cpu().tolist(),
-           "logp_rel_err": float(((lp.double().cpu() - ref_lp).abs() / ref_lp.abs()).max()),
-           "per_token_logp_max_rel_err": float(((pt_gpu - pt_ref).abs() / pt_ref.abs().clamp_min(1e-6)).max()),
-           "loss_oracle": float(out["loss"]), "loss_gpu": float(out9[0]),
+    res = {"shape": "1 decoder layer at full width, 1 pair, R=64 (T=687); oracle.make_params scale %g" % CHECKER_PARAM_SCALE,
+           "logp_oracle_fp32": ref_lp.tolist(), "logp_gpu": lp.double().cpu().tolist(),
+           "logp_oracle_bf16_order": ob["logp"].double().tolist(),
+           "logp_rel_err": relmax(lp.double().cpu(), ref_lp),
+           "logp_rel_err_inherent_bf16_order": relmax(ob["logp"].double(), ref_lp),
+           "per_token_logp_max_abs_err": float((pt_gpu - pt_ref).abs().max()),
+           "per_token_logp_max_abs_err_inherent_bf16_order": float((pt_bf - pt_ref).abs().max()),
+           "loss_oracle": float(out["loss"].detach()), "loss_gpu": float(out9[0]),
            "grad_rel_l2_err": gerr}
     del pol
     torch.cuda.empty_cache()
     return res
+
+
+def usable_cores():
+    """Host cores this process may really use: min(cpu_count, scheduler affinity, cgroup cpu quota)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        pass
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()
+        if quota != "max":
+            n = min(n, max(1, int(math.ceil(int(quota) / int(period)))))
+    except (OSError, ValueError):
+        pass
+    return max(1, n)
+
+
+def pick_cpu_threads():
+    """Thread count that gives the reference's CPU path its best throughput on this box: a 2048^3 fp32 matmul is
+    timed at a few candidate counts (a container can report 128 CPUs and still be scheduled on far fewer, where 128
+    threads thrash)."""
+    n = usable_cores()
+    cands = sorted({c for c in (n, n // 2, 64, 32, 16, 8, 4) if 1 <= c <= n}, reverse=True)
+    a = torch.randn(2048, 2048)
+    best, best_t = cands[0], float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        a @ a
+        t0 = time.perf_counter()
+        for _ in range(3):
+            a @ a
+        t = time.perf_counter() - t0
+        if t < best_t * 0.95:           # prefer more threads unless fewer are clearly faster
+            best, best_t = c, t
+    torch.set_num_threads(best)
+    return best
 
 
 def cpu_reference_pairs_per_sec(dtype_name="float32", check=None):
@@ -169,19 +278,11 @@ def cpu_reference_pairs_per_sec(dtype_name="float32", check=None):
     CLIP-L 23 layers, 336 px) on config (a) shape (1 pair, 64-token responses, T=687) with 1 and 2
     decoder layers, and extrapolates linearly to 32 layers."""
     from oracle import llava_dpo_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
+    threads = pick_cpu_threads()
     dt = getattr(torch, dtype_name)
     times = {}
     for nl in (1, 2):
-        cfg = O.OracleConfig(num_layers=nl)
-        p = O.make_params(cfg, seed=0, dtype=dt)
-        for k in p:
-            if k.startswith(O.TRAINABLE_PREFIXES):
-                p[k].requires_grad_(True)
-        batch = O.synthetic_pair_batch(cfg, 1, 48, 64, seed=1234, image_pos=35)
-        batch["images"] = batch["images"].to(dt)
-        batch["ref_win_logp"] = torch.tensor([-660.0])
-        batch["ref_rej_logp"] = torch.tensor([-661.0])
+        cfg, p, batch = full_width_case(nl, dt)
         names = O.trainable_names(p)
         state = {k: (torch.zeros_like(p[k], dtype=torch.float32), torch.zeros_like(p[k], dtype=torch.float32))
                  for k in names}
@@ -202,7 +303,8 @@ def cpu_reference_pairs_per_sec(dtype_name="float32", check=None):
     t_full = times[1] + 31 * t_layer
     sample = ("oracle port, torch-CPU %s, full width, 1 pair, R=64 (T=687): fwd+bwd+AdamW timed with 1 and 2 "
               "decoder layers (%.1fs, %.1fs) and extrapolated linearly to 32 layers" % (dtype_name, times[1], times[2]))
-    return 1.0 / t_full, os.cpu_count() or 1, sample
+    sample += "; %d torch threads (best of a matmul calibration; os.cpu_count()=%s)" % (threads, os.cpu_count())
+    return 1.0 / t_full, threads, sample
 
 
 def run_reference_arm(args, rank):
@@ -236,6 +338,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stash-extra", action="store_true")
     ap.add_argument("--lora", action="store_true", help="BASELINE config (e): LoRA-DPO r=64 (not the headline line)")
+    ap.add_argument("--omnilmm", action="store_true",
+                    help="BASELINE config (d) downstream of the vision tower: resampler + Mistral-7B GQA decoder "
+                         "(not the headline line; the EVA-02 tower is not built)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -254,10 +359,15 @@ def main():
     from rlaifv_b200.engine import DPOStepEngine
     from rlaifv_b200.model import LlavaDims, LlavaDPOPolicy
 
-    dims = LlavaDims(num_layers=args.layers)
     B = PAIRS_PER_GPU
     micro = args.micro_pairs or B
-    policy = LlavaDPOPolicy(dims, torch.device("cuda", local_rank), seed=0)
+    if args.omnilmm:
+        from rlaifv_b200.omnilmm_model import OmniLMMDPOPolicy, omnilmm_dims
+        dims = omnilmm_dims(num_layers=args.layers)
+        policy = OmniLMMDPOPolicy(dims, torch.device("cuda", local_rank), seed=0)
+    else:
+        dims = LlavaDims(num_layers=args.layers)
+        policy = LlavaDPOPolicy(dims, torch.device("cuda", local_rank), seed=0)
     if args.lora:
         policy.enable_lora(r=64, alpha=16)
     engine = DPOStepEngine(policy, lr=1e-5 if args.lora else 5e-7, weight_decay=0.01, total_steps=2672, micro_pairs=micro,
@@ -265,10 +375,11 @@ def main():
     # HBM plan: with the optimizer state sharded over >= 2 GPUs there is room to stash the normalised inputs
     # and the SwiGLU product (no recompute in the backward); one GPU holds the unsharded 81 GB state.
     policy.stash_extra = world > 1 and not args.no_stash_extra
-    T = PROMPT_LEN + RESP_LEN - 1 + dims.num_patches
+    T = PROMPT_LEN + RESP_LEN - 1 + (dims.num_query + 2 if args.omnilmm else dims.num_patches)
 
     # frozen-reference log-probs = initial policy log-probs (step-0 loss = ln 2 known answer)
-    host_batches = [synthetic_batch(rank, s, B) for s in range(2)]
+    host_batches = [synthetic_omni_batch(rank, s, B, dims) if args.omnilmm else synthetic_batch(rank, s, B)
+                    for s in range(2)]
     for hb in host_batches:
         rw, rr = [], []
         for lo in range(0, B, micro):
@@ -412,7 +523,7 @@ def main():
     e2e_value = total_pairs / (ms_e2e * 1e-3)
     hb = host_batches[0]
     h2d = sum(v.numel() * v.element_size() for v in hb.values() if torch.is_tensor(v))
-    f_pair = flops_per_pair(T)
+    f_pair = omni_flops_per_pair(dims, T) if args.omnilmm else flops_per_pair(T)
     if args.lora:   # base wgrad skipped, adapters (159 907 840 params) added
         n_dec = 32 * (4 * 4096 ** 2 + 3 * 4096 * 11008)
         n_head = 4096 * 32000
@@ -421,11 +532,15 @@ def main():
         f_proj = 2 * (1024 * 4096 + 4096 ** 2) * 576
         f_pair = 2 * T * (4 * (n_dec + n_head) + 6 * 159907840) + 3 * 2 * attn_seq + f_clip + 3 * f_proj
     line = {
-        "metric": "preference-pairs/sec LLaVA-1.5-7B DPO step", "value": value, "unit": "pairs/s",
+        "metric": ("preference-pairs/sec OmniLMM-12B DPO step (downstream of the vision tower)" if args.omnilmm
+                   else "preference-pairs/sec LLaVA-1.5-7B DPO step"), "value": value, "unit": "pairs/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": ("LLaVA-1.5-7B %sDPO bf16, %d pairs/GPU, 336px, 512-tok responses (T=%d), ZeRO-2 AdamW"
-                                % ("LoRA(r=64)-" if args.lora else "", B, T)),
+        "config": {"workload": (("OmniLMM-12B DPO DOWNSTREAM OF THE VISION TOWER (resampler + Mistral-7B GQA decoder; "
+                                 "EVA-02 tower not built) bf16, %d pairs/GPU, 1024 vision tokens, 512-tok responses "
+                                 "(T=%d), ZeRO-2 AdamW" % (B, T)) if args.omnilmm else
+                                ("LLaVA-1.5-7B %sDPO bf16, %d pairs/GPU, 336px, 512-tok responses (T=%d), ZeRO-2 AdamW"
+                                 % ("LoRA(r=64)-" if args.lora else "", B, T))),
                    "layers": args.layers, "pairs_per_gpu": B, "micro_pairs": micro, "parallelism": "dp%d" % world,
                    "l2": "per-step working set (>100 GB of weights/activations) is far larger than the 126 MB L2",
                    "step0_loss": loss0, "step0_loss_expected": math.log(2.0)},
@@ -452,7 +567,7 @@ def main():
                                  "backward's GEMMs run concurrently"},
     }
     if rank == 0:
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and not args.omnilmm:
             policy._stash = None
             policy._bufs.clear()
             torch.cuda.empty_cache()
