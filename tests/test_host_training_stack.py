@@ -14,9 +14,10 @@ import torch
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def script_flags():
-    txt = open(os.path.join(REPO, "script", "train", "llava15_train.sh")).read()
-    txt = txt[txt.index("rlaifv_b200.train_llava15"):]
+def script_flags(name="llava15_train.sh", module="rlaifv_b200.train_llava15"):
+    txt = open(os.path.join(REPO, "script", "train", name)).read()
+    txt = txt[txt.index(module):]
+    txt = txt.split("\n\n")[0]                       # the launch command only (the LoRA script post-processes after it)
     toks = re.findall(r"(--[a-z_0-9]+)\s+([^\\\n]+?)\s*(?:\\|$)", txt, flags=re.M)
     argv = []
     for k, v in toks:
@@ -33,6 +34,20 @@ def test_every_reference_flag_parses():
     assert m.mm_vision_select_layer == -2 and m.mm_projector_type == "mlp2x_gelu" and t.model_max_length == 2048
     assert zero_stage(os.path.join(REPO, "script", "zero2.json")) == 2
     assert len(argv) // 2 >= 40
+
+
+def test_every_reference_lora_flag_parses():
+    """script/train/llava15_train_lora.sh (reference: same file name, :6-49) through the LoRA entry's argv path."""
+    from rlaifv_b200.train_llava15 import parse_args_into_dataclasses
+    argv = [a.replace("$task_name-$exp_name", "x").replace("$exp_name", "x")
+            for a in script_flags("llava15_train_lora.sh", "rlaifv_b200.train_llava15_lora")]
+    assert "--lora_enable" in argv
+    m, d, t = parse_args_into_dataclasses(argv)
+    assert t.lora_enable is True and t.lora_r == 64 and t.lora_alpha == 16 and t.lora_dropout == 0.05
+    assert t.learning_rate == 1e-5 and t.fully_tune is False and t.task == "DPO" and t.lora_bias == "none"
+    # the module the script launches exists and forces --lora_enable when the flag is absent
+    import rlaifv_b200.train_llava15_lora as L
+    assert callable(L.train)
 
 
 def test_llava_v1_encoding_matches_reference_fixture():
@@ -115,8 +130,16 @@ GLOO_WORKER = textwrap.dedent('''
     torch.manual_seed(100 + rank)
     st.grad.copy_((torch.randn(st.numel) * 0.5).bfloat16())        # rank-local grads (already 1/world scaled)
     gsum = st.grad.float().clone(); dist.all_reduce(gsum)
-    opt = zero2.Zero2AdamW(st, lr=0.1, weight_decay=0.0, rank=rank, world=world)
-    assert opt.owned * world == st.numel
+    # an extra trainable bucket outside the ParamStore (LoRA adapters / the OmniLMM resampler are passed like this)
+    torch.manual_seed(7)
+    xflat = torch.randn(2048).bfloat16(); xgrad = torch.zeros(2048, dtype=torch.bfloat16)
+    x0 = xflat.clone().float()
+    torch.manual_seed(200 + rank); xgrad.copy_((torch.randn(2048) * 0.5).bfloat16())
+    xsum = xgrad.float().clone(); dist.all_reduce(xsum)
+    buckets = zero2.store_buckets(st) + [zero2.OptBucket("resampler", xflat, xgrad, 1024)]
+    opt = zero2.Zero2AdamW(buckets, lr=0.1, weight_decay=0.0, rank=rank, world=world,
+                           gather_order=["resampler", "embed", "layer0", "layer1", "head", "projector"])
+    assert opt.owned * world == st.numel + 2048 and opt.index["resampler"] == len(buckets) - 1
     opt.reduce_all()
     opt.step(0.1)
     expect = (p0 - 0.1 * gsum.bfloat16().float()).bfloat16().float()
@@ -124,8 +147,9 @@ GLOO_WORKER = textwrap.dedent('''
     # every rank holds the full updated parameters after the all-gather
     chk = st.flat.float().clone(); dist.all_reduce(chk)
     same = (chk / world - st.flat.float()).abs().max().item()
-    print("RESULT", rank, err, same)
-    assert err <= 4e-2 and same == 0.0
+    xerr = (xflat.float() - (x0 - 0.1 * xsum.bfloat16().float()).bfloat16().float()).abs().max().item()
+    print("RESULT", rank, err, same, xerr)
+    assert err <= 4e-2 and same == 0.0 and xerr <= 4e-2
     dist.destroy_process_group()
 ''')
 
