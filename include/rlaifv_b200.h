@@ -183,6 +183,16 @@ int rlaifv_logp_fwd(const void* logits, long long ld, const long long* labels, i
 int rlaifv_logp_bwd(void* logits, long long ld, const long long* labels, const float* lse, const float* d_logp,
                     const float* count_or_null, int nseq, int T, int V, void* stream);
 
+/* Token-weighted log-prob reduction and its backward: compute_weighted_logp (muffin/train/trainers.py:128-137), used by
+ * the `dpo_token_weighted` branch of get_beta_and_logps (:246-261; the reference raises NotImplementedError for
+ * LLaVA-1.5 there, so this serves the OmniLMM path). token_weight fp32 [nseq][T-1]; weighted_mask = weight * (label !=
+ * -100); logp_w = sum per_tok * weighted_mask, avg_w = logp_w / sum weighted_mask (wsum). Backward in place on the logits
+ * like rlaifv_logp_bwd, each row scaled by its token weight (and 1/wsum in average mode). */
+int rlaifv_logp_weighted_reduce(const float* per_tok, const long long* labels, const float* token_weight, int nseq,
+                                int T, float* logp_w, float* avg_w, float* wsum_or_null, void* stream);
+int rlaifv_logp_bwd_weighted(void* logits, long long ld, const long long* labels, const float* lse, const float* d_logp,
+                             const float* token_weight, const float* wsum_or_null, int nseq, int T, int V, void* stream);
+
 /* ---- DPO loss + gradient (muffin/train/trainers.py:91-126, :279-311) ---------------------------
  * out9: [0] loss = DPO_w*mean(losses) - SFT_w*mean(pw); [1..8] local means of chosen_reward,
  * rejected_reward, accuracy, margin, logp_rejected, logp_chosen, ref_rejected, ref_chosen. */

@@ -66,9 +66,9 @@ def import_reference(kv_dim):
     sys.modules.update(mods)
     sys.path.insert(0, REF)
     from omnilmm.model.omnilmm import OmniLMMForCausalLM, OmniLMMConfig
-    from muffin.train.trainers import forward_DPO, dpo_loss
+    from muffin.train.trainers import forward_DPO, dpo_loss, compute_weighted_logp
     from muffin.eval.muffin_inference_logp import get_batch_logps
-    return OmniLMMForCausalLM, OmniLMMConfig, forward_DPO, dpo_loss, get_batch_logps
+    return OmniLMMForCausalLM, OmniLMMConfig, forward_DPO, dpo_loss, get_batch_logps, compute_weighted_logp
 
 
 def sample(t, n=64):
@@ -78,7 +78,7 @@ def sample(t, n=64):
 
 def main():
     dec, res, tok = OM.TINY_OMNI_DEC, OM.TINY_OMNI_RES, OM.TINY_OMNI_TOK
-    Model, Config, forward_DPO, dpo_loss, get_batch_logps = import_reference(res.kv_dim)
+    Model, Config, forward_DPO, dpo_loss, get_batch_logps, compute_weighted_logp = import_reference(res.kv_dim)
     cfg = Config(vocab_size=dec.vocab_size, hidden_size=dec.hidden_size, intermediate_size=dec.intermediate_size,
                  num_hidden_layers=dec.num_layers, num_attention_heads=dec.num_heads,
                  num_key_value_heads=dec.kv_heads, rms_norm_eps=dec.rms_eps, max_position_embeddings=4096,
@@ -91,7 +91,8 @@ def main():
     vc = model.model.vision_config
     vc.im_patch_token, vc.im_start_token, vc.im_end_token, vc.use_im_start_end = tok.im_patch, tok.im_start, tok.im_end, True
     out_dir = os.path.join(REPO, "tests", "golden", "omnilmm")
-    for name, B, seed, ragged in (("omni_ragged_b2", 2, 41, True), ("omni_equal_b1", 1, 42, False)):
+    for name, B, seed, ragged, weighted in (("omni_ragged_b2", 2, 41, True, False), ("omni_equal_b1", 1, 42, False, False),
+                                            ("omni_weighted_b2", 2, 43, True, True)):
         p = OM.make_omnilmm_params(dec, res, seed=seed)
         missing, unexpected = model.load_state_dict({k: v.clone() for k, v in p.items()}, strict=False)
         missing = [m for m in missing if "vision_tower" not in m and "rotary" not in m]
@@ -103,9 +104,18 @@ def main():
         model.train()
         model.zero_grad()
         images = torch.cat([vt, vt], dim=0)                                   # trainers.py:190
-        logp = forward_DPO(model, ids, labels.clone(), None, images)          # attention_mask=None (trainers.py:199)
-        logits = model(input_ids=ids, images=images, attention_mask=None).logits
-        per_tok = get_batch_logps(logits, labels.clone(), return_per_token_logp=True)
+        tw = None
+        if weighted:
+            # --dpo_token_weighted (trainers.py:246-261): per-token log-probs out of forward_DPO, re-weighted by the
+            # collator's token weights (1 / mod_token_weight=3 pattern) through the reference's compute_weighted_logp
+            g = torch.Generator().manual_seed(seed + 11)
+            tw = torch.where(torch.rand(ids.shape[0], ids.shape[1] - 1, generator=g) < 0.3, 3.0, 1.0)
+            per_tok = forward_DPO(model, ids, labels.clone(), None, images, token_weighted=True)
+            logp = compute_weighted_logp(per_tok, labels, tw, False)
+        else:
+            logp = forward_DPO(model, ids, labels.clone(), None, images)      # attention_mask=None (trainers.py:199)
+            logits = model(input_ids=ids, images=images, attention_mask=None).logits
+            per_tok = get_batch_logps(logits, labels.clone(), return_per_token_logp=True)
         ref_w = logp[:B].detach() + 0.3
         ref_r = logp[B:].detach() - 0.2
         losses, cr, rr = dpo_loss(logp[:B], logp[B:], ref_w, ref_r, beta=0.1)
@@ -113,12 +123,16 @@ def main():
         # ---- restatement on the same inputs ----
         po = {k: v.clone().requires_grad_("pos_embed" not in k) for k, v in p.items()}
         vo = batch["vision_tokens"].clone().requires_grad_(True)
-        o = OM.omnilmm_dpo_step(po, dec, res, tok, dict(batch, vision_tokens=vo, ref_win_logp=ref_w, ref_rej_logp=ref_r))
+        ob = dict(batch, vision_tokens=vo, ref_win_logp=ref_w, ref_rej_logp=ref_r)
+        if weighted:
+            ob["token_weight"] = tw
+        o = OM.omnilmm_dpo_step(po, dec, res, tok, ob)
         o["loss"].backward()
         rel = lambda a, b: float((a.detach() - b.detach()).abs().max() / (b.detach().abs().max() + 1e-30))
         worst = max(rel(o["logp"], logp), rel(o["per_token_logps"], per_tok), rel(o["losses"], losses),
                     rel(vo.grad, vt.grad))
         fx = {"case": name, "B": B, "seed": seed, "ragged": ragged, "logp": logp.detach().numpy(),
+              **({"token_weight": tw.numpy()} if weighted else {}),
               "per_token_logps": per_tok.detach().numpy(), "losses": losses.detach().numpy(),
               "chosen_rewards": cr.numpy(), "rejected_rewards": rr.numpy(), "ref_win_logp": ref_w.numpy(),
               "ref_rej_logp": ref_r.numpy(), "loss": float(losses.mean()),

@@ -99,9 +99,23 @@ def omnilmm_policy_logps(p, dec_cfg, res_cfg, tok, input_ids, labels, vision_tok
     return dict(src=src, per_token_logps=per_tok, logp=logp, avg_logp=avg, logits=logits, image_features=feats)
 
 
-def omnilmm_dpo_step(p, dec_cfg, res_cfg, tok, batch, beta=0.1):
+def compute_weighted_logp(per_token_logp, labels, token_weight, use_average=False):
+    """muffin/train/trainers.py:128-137 (the dpo_token_weighted branch of get_beta_and_logps, :246-261)."""
+    weighted_mask = token_weight * (labels[:, 1:] != O.IGNORE_INDEX)
+    logp = (per_token_logp * weighted_mask).sum(-1)
+    return logp / weighted_mask.sum(-1) if use_average else logp
+
+
+def omnilmm_dpo_step(p, dec_cfg, res_cfg, tok, batch, beta=0.1, use_average=False):
+    """batch["token_weight"] [2B, L-1] present => the token-weighted loss (policy log-probs re-weighted per token;
+    the reference log-probs in the batch are expected to be weighted the same way by the caller)."""
     out = omnilmm_policy_logps(p, dec_cfg, res_cfg, tok, batch["concatenated_input_ids"],
                                batch["concatenated_labels"], batch["vision_tokens"])
+    if "token_weight" in batch:
+        out["logp"] = compute_weighted_logp(out["per_token_logps"], batch["concatenated_labels"], batch["token_weight"],
+                                            use_average)
+    elif use_average:
+        out["logp"] = out["avg_logp"]
     B = out["logp"].shape[0] // 2
     pw, pr = out["logp"][:B], out["logp"][B:]
     losses, cr, rr = O.dpo_loss(pw, pr, batch["ref_win_logp"], batch["ref_rej_logp"], beta)

@@ -858,6 +858,65 @@ logp_bwd_kernel(bf16* __restrict__ logits, long long ld, const long long* __rest
   }
 }
 
+// Token-weighted variant (compute_weighted_logp, muffin/train/trainers.py:128-137 — the `dpo_token_weighted` branch of
+// get_beta_and_logps, :246-261, available to the non-LLaVA models): weighted_mask = token_weight * (label != -100);
+// logp_w[b] = sum_t per_tok * weighted_mask; avg_w = logp_w / sum_t weighted_mask. token_weight is [nseq][T-1].
+__global__ void logp_weighted_reduce_kernel(const float* __restrict__ per_tok, const long long* __restrict__ labels,
+                                            const float* __restrict__ token_weight, int nseq, int T,
+                                            float* __restrict__ logp_w, float* __restrict__ avg_w,
+                                            float* __restrict__ wsum_out) {
+  const int b = blockIdx.x;
+  float s = 0.f, c = 0.f;
+  for (int t = threadIdx.x; t < T - 1; t += blockDim.x) {
+    const bool mk = labels[(long long)b * T + t + 1] != IGNORE_INDEX;
+    if (mk) {
+      const float w = token_weight[(long long)b * (T - 1) + t];
+      s += per_tok[(long long)b * (T - 1) + t] * w;
+      c += w;
+    }
+  }
+  const float2 tot = block_sum2(s, c);
+  if (threadIdx.x == 0) {
+    logp_w[b] = tot.x;
+    avg_w[b] = tot.x / tot.y;
+    if (wsum_out) wsum_out[b] = tot.y;
+  }
+}
+// backward of the weighted sum, in place: logits[b][t][v] <- g_b * w[b][t] * mask * (onehot - softmax), row T-1 <- 0;
+// g_b = d_logp[b] (sum mode) or d_logp[b] / wsum[b] (average mode, wsum passed non-null).
+__global__ void __launch_bounds__(LOGP_THREADS)
+logp_bwd_weighted_kernel(bf16* __restrict__ logits, long long ld, const long long* __restrict__ labels,
+                         const float* __restrict__ lse, const float* __restrict__ d_logp,
+                         const float* __restrict__ token_weight, const float* __restrict__ wsum, int nseq, int T,
+                         int V) {
+  const long long rows = (long long)nseq * T;
+  const int nch = V >> 3;
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+    const int b = (int)(r / T);
+    const int t = (int)(r % T);
+    bf16* lr = logits + r * ld;
+    long long lab = (t < T - 1) ? labels[(long long)b * T + t + 1] : IGNORE_INDEX;
+    if (lab == IGNORE_INDEX) {
+      for (int c = threadIdx.x; c < nch; c += LOGP_THREADS)
+        *reinterpret_cast<uint4*>(lr + c * 8) = make_uint4(0, 0, 0, 0);
+      continue;
+    }
+    float g = d_logp[b] * token_weight[(long long)b * (T - 1) + t];
+    if (wsum) g /= wsum[b];
+    const float l = lse[r];
+    for (int c = threadIdx.x; c < nch; c += LOGP_THREADS) {
+      float v[8];
+      load8(lr + c * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float p = __expf(v[j] - l);
+        v[j] = g * (((long long)(c * 8 + j) == lab ? 1.f : 0.f) - p);
+      }
+      store8(lr + c * 8, v);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // DPO loss + gradient (muffin/train/trainers.py:91-126, 279-311). One warp.
 //   z = beta*((pw-pr)-(rw-rr)); losses = -logsigmoid(z); loss = DPO_w*mean(losses) - SFT_w*mean(pw)
@@ -1233,6 +1292,26 @@ extern "C" int rlaifv_logp_bwd(void* logits, long long ld, const long long* labe
   const long long rows = (long long)nseq * T;
   const int grid = (int)(rows < (long long)num_sms() * 8 ? rows : (long long)num_sms() * 8);
   logp_bwd_kernel<<<grid, LOGP_THREADS, 0, ST>>>((bf16*)logits, ld, labels, lse, d_logp, count_or_null, nseq, T, V);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int rlaifv_logp_weighted_reduce(const float* per_tok, const long long* labels, const float* token_weight,
+                                           int nseq, int T, float* logp_w, float* avg_w, float* wsum_or_null,
+                                           void* stream) {
+  B200_REQUIRE(nseq > 0 && T >= 2, "logp_weighted_reduce: bad shape");
+  logp_weighted_reduce_kernel<<<nseq, 256, 0, ST>>>(per_tok, labels, token_weight, nseq, T, logp_w, avg_w, wsum_or_null);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int rlaifv_logp_bwd_weighted(void* logits, long long ld, const long long* labels, const float* lse,
+                                        const float* d_logp, const float* token_weight, const float* wsum_or_null,
+                                        int nseq, int T, int V, void* stream) {
+  B200_REQUIRE(V % 8 == 0 && token_weight != nullptr, "logp_bwd_weighted: V %% 8 != 0 or no weights");
+  const long long rows = (long long)nseq * T;
+  const int grid = (int)(rows < (long long)num_sms() * 8 ? rows : (long long)num_sms() * 8);
+  logp_bwd_weighted_kernel<<<grid, LOGP_THREADS, 0, ST>>>((bf16*)logits, ld, labels, lse, d_logp, token_weight,
+                                                          wsum_or_null, nseq, T, V);
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

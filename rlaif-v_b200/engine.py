@@ -26,7 +26,8 @@ METRIC_NAMES = ("loss", "rewards_train/chosen", "rewards_train/rejected", "rewar
 class DPOStepEngine:
     def __init__(self, policy: LlavaDPOPolicy, lr=5e-7, weight_decay=0.01, betas=(0.9, 0.999), eps=1e-8,
                  total_steps=2672, warmup_ratio=0.05, dpo_use_average=False, micro_pairs=None,
-                 rank=0, world=1, group=None, constant_lr=False, hf_deepspeed_input_cast=False):
+                 rank=0, world=1, group=None, constant_lr=False, hf_deepspeed_input_cast=False,
+                 dpo_token_weighted=False):
         self.policy = policy
         self.rank, self.world, self.group = rank, world, group
         self.opt = Zero2AdamW(policy.trainable_buckets(), lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
@@ -34,6 +35,11 @@ class DPOStepEngine:
         self.base_lr, self.total_steps, self.warmup_ratio = lr, total_steps, warmup_ratio
         self.constant_lr = constant_lr
         self.dpo_use_average = dpo_use_average
+        # --dpo_token_weighted (muffin/train/trainers.py:246-261): log-probs become token-weighted sums; the reference
+        # refuses it for LLaVA-1.5 (:246-248), so it is only accepted for the OmniLMM policy
+        self.dpo_token_weighted = dpo_token_weighted
+        if dpo_token_weighted and policy.dims.frontend == "clip_mlp":
+            raise NotImplementedError("dpo_token_weighted with LLaVA-1.5 (the reference raises too, trainers.py:246-248)")
         self.micro_pairs = micro_pairs
         # HF Trainer._prepare_inputs casts every floating input to bf16 under DeepSpeed-bf16, which
         # rounds the reference log-probs (|logp| ~ 5e3 -> granularity 32) before dpo_loss. The drop-in
@@ -84,9 +90,18 @@ class DPOStepEngine:
         ids = self._h2d(batch["concatenated_input_ids"])
         labels = self._h2d(batch["concatenated_labels"])
         images = self._h2d(batch["images"])
-        key = "avg_logp" if self.dpo_use_average else "logp"
-        rw = self._h2d(batch["ref_win_" + key]).to(_F32)
-        rr = self._h2d(batch["ref_rej_" + key]).to(_F32)
+        tw = None
+        if self.dpo_token_weighted:
+            from .trainers import compute_weighted_logp     # host tensors from the collator, [B, L-1] each
+            rw = self._h2d(compute_weighted_logp(batch["ref_win_per_token_logp"], batch["win_labels"],
+                                                 batch["win_token_weight"], self.dpo_use_average)).to(_F32)
+            rr = self._h2d(compute_weighted_logp(batch["ref_rej_per_token_logp"], batch["rej_labels"],
+                                                 batch["rej_token_weight"], self.dpo_use_average)).to(_F32)
+            tw = self._h2d(batch["concatenated_token_weight"]).to(_F32).contiguous()       # [2B, L-1]
+        else:
+            key = "avg_logp" if self.dpo_use_average else "logp"
+            rw = self._h2d(batch["ref_win_" + key]).to(_F32)
+            rr = self._h2d(batch["ref_rej_" + key]).to(_F32)
         if self.hf_deepspeed_input_cast:
             rw = rw.to(torch.bfloat16).to(_F32)
             rr = rr.to(torch.bfloat16).to(_F32)
@@ -110,12 +125,17 @@ class DPOStepEngine:
             mlab = torch.cat([labels[lo:hi], labels[B + lo:B + hi]], 0)
             out = pol.forward_logps(mids, mlab, images[lo:hi], keep_stash=True)
             lp = out["avg_logp"] if self.dpo_use_average else out["logp"]
+            mtw = wsum = None
+            if tw is not None:
+                mtw = torch.cat([tw[lo:hi], tw[B + lo:B + hi]], 0).contiguous()
+                lw, aw, wsum = ops.logp_weighted_reduce(out["per_token_logps"], out["labels"], mtw)
+                lp = aw if self.dpo_use_average else lw
             _, _, _, dpw, dpr, out9 = ops.dpo_loss(lp[:b].contiguous(), lp[b:].contiguous(), rw[lo:hi].contiguous(),
                                                    rr[lo:hi].contiguous(), beta, dpo_w, sft_w,
                                                    grad_scale=(b / B) / self.world)
             self._metrics.add_(out9, alpha=b / B)
             pol.backward_logps(torch.cat([dpw, dpr]).contiguous(), use_average=self.dpo_use_average,
-                               accumulate=mi > 0)
+                               accumulate=mi > 0, token_weight=mtw, weight_sum=wsum)
         pol.finalize_embed_grad()
         if self.world > 1:
             for name in pol.tail_bucket_names():

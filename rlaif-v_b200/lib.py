@@ -80,6 +80,9 @@ _SIGNATURES = {
     "rlaifv_layernorm_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int,
                              c_int, c_float, c_void_p],
     "rlaifv_add_rows_bcast": [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p],
+    "rlaifv_logp_weighted_reduce": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    "rlaifv_logp_bwd_weighted": [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                 c_void_p],
     "rlaifv_splice_map_inplace": [c_void_p, c_void_p, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_void_p, c_void_p,
                                   c_void_p],
 }

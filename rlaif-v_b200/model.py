@@ -644,9 +644,10 @@ class LlavaDPOPolicy:
         return dict(per_token_logps=per_tok, logp=logp, avg_logp=avg, labels=new_labels, T=T)
 
     # ------------------------------------------------------------------ backward
-    def backward_logps(self, d_logp, use_average=False, accumulate=False):
+    def backward_logps(self, d_logp, use_average=False, accumulate=False, token_weight=None, weight_sum=None):
         """Gradients of sum_b d_logp[b] * logp[b] into store.grad (bf16; `accumulate` adds to what is
-        there — used for the 2nd.. micro-batch of a step)."""
+        there — used for the 2nd.. micro-batch of a step). token_weight [nseq, T-1] fp32: logp is the token-weighted
+        sum of compute_weighted_logp (muffin/train/trainers.py:128-137); with use_average also pass weight_sum."""
         st = self._stash
         assert st is not None, "forward_logps(keep_stash=True) must precede backward_logps"
         d, P, G = self.dims, self.store.p, self.store.g
@@ -659,8 +660,13 @@ class LlavaDPOPolicy:
         cos, sin = self.rope_tables(T)
         acc = bool(accumulate)
 
-        dlogits = ops.logp_bwd(st["logits"], st["labels"], st["lse_v"], d_logp, nseq, T,
-                               count=st["count"] if use_average else None)
+        if token_weight is not None:
+            assert not use_average or weight_sum is not None
+            dlogits = ops.logp_bwd_weighted(st["logits"], st["labels"], st["lse_v"], d_logp, token_weight, nseq, T,
+                                            wsum=weight_sum if use_average else None)
+        else:
+            dlogits = ops.logp_bwd(st["logits"], st["labels"], st["lse_v"], d_logp, nseq, T,
+                                   count=st["count"] if use_average else None)
         frozen = self.lora is not None            # LoRA: lm_head / norms / embeddings / base matrices are frozen
         scratch_h = self.buf("frozen_dw", (H,)) if frozen else None
         if not frozen:

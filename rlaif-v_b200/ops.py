@@ -360,6 +360,30 @@ def logp_bwd(logits, labels, lse, d_logp, nseq, T, count=None):
     return logits
 
 
+def logp_weighted_reduce(per_tok, labels, token_weight):
+    """compute_weighted_logp: per_tok / token_weight fp32 [nseq, T-1], labels int64 [nseq, T] ->
+    (logp_w [nseq], avg_w [nseq], wsum [nseq])."""
+    _chk(per_tok, _f32), _chk(token_weight, _f32)
+    assert labels.dtype == torch.int64 and labels.is_contiguous() and per_tok.is_contiguous()
+    nseq, T = labels.shape
+    assert tuple(per_tok.shape) == (nseq, T - 1) and tuple(token_weight.shape) == (nseq, T - 1) \
+        and token_weight.is_contiguous()
+    lw = torch.empty(nseq, dtype=_f32, device=per_tok.device)
+    aw, ws = torch.empty_like(lw), torch.empty_like(lw)
+    _l.call("rlaifv_logp_weighted_reduce", _l.ptr(per_tok), _l.ptr(labels), _l.ptr(token_weight), nseq, T, _l.ptr(lw),
+            _l.ptr(aw), _l.ptr(ws), _l.stream_ptr())
+    return lw, aw, ws
+
+
+def logp_bwd_weighted(logits, labels, lse, d_logp, token_weight, nseq, T, wsum=None):
+    """In place: logits <- d loss / d logits for the token-weighted log-prob (wsum given = average mode)."""
+    _chk(logits), _chk(lse, _f32), _chk(d_logp, _f32), _chk(token_weight, _f32)
+    assert tuple(token_weight.shape) == (nseq, T - 1) and token_weight.is_contiguous()
+    _l.call("rlaifv_logp_bwd_weighted", _l.ptr(logits), logits.stride(0), _l.ptr(labels), _l.ptr(lse), _l.ptr(d_logp),
+            _l.ptr(token_weight), _l.ptr(wsum), nseq, T, logits.shape[1], _l.stream_ptr())
+    return logits
+
+
 def dpo_loss(policy_win, policy_rej, ref_win, ref_rej, beta, dpo_weight=1.0, sft_weight=0.0, grad_scale=1.0,
              want_grad=True):
     for t in (policy_win, policy_rej, ref_win, ref_rej):

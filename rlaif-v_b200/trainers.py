@@ -78,8 +78,16 @@ def dpo_loss(policy_chosen_logps, policy_rejected_logps, reference_chosen_logps,
 
 
 def compute_weighted_logp(per_token_logp, labels, token_weight, use_average):
-    raise NotImplementedError("dpo_token_weighted is not implemented for LLaVA-1.5 in the reference either "
-                              "(muffin/train/trainers.py:246-248 raises)")
+    """muffin/train/trainers.py:128-137, for host-side tensors (the frozen-reference per-token log-probs the collator
+    delivers). The policy side of the token-weighted loss runs in the CUDA library (ops.logp_weighted_reduce /
+    ops.logp_bwd_weighted through DPOStepEngine(dpo_token_weighted=True)); the reference — and this drop-in — raise
+    NotImplementedError for LLaVA-1.5 (:246-248), the branch exists for the OmniLMM / MiniCPM-style models."""
+    loss_mask = labels[:, 1:] != -100
+    weighted_mask = token_weight * loss_mask
+    logp = (per_token_logp * weighted_mask).sum(-1)
+    if use_average:
+        return logp / weighted_mask.sum(-1)
+    return logp
 
 
 def get_beta_and_logps(data_dict, model, args, is_minicpm=False, is_llava15=False):
@@ -88,7 +96,7 @@ def get_beta_and_logps(data_dict, model, args, is_minicpm=False, is_llava15=Fals
     if not is_llava15 or is_minicpm:
         raise NotImplementedError("only the is_llava15=True branch is on the B200 hot path")
     if getattr(args, "dpo_token_weighted", False):
-        raise NotImplementedError
+        raise NotImplementedError          # muffin/train/trainers.py:246-248 (is_llava15)
     if getattr(args, "task", "DPO") != "DPO":
         raise NotImplementedError("KTO task")
     win_input_ids = data_dict.pop("win_input_ids")

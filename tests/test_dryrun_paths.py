@@ -130,6 +130,13 @@ def test_omnilmm_policy_launch_sequence_dry_run(monkeypatch):
     assert calls.count("rlaifv_splice_map_inplace") == 1 and calls.count("rlaifv_cross_attention_bwd") == 1
     assert calls.count("rlaifv_attention_fwd_gqa") == d.num_layers and "rlaifv_clip_im2col" not in calls
     assert pol.vision_token_grad.shape == batch["vision_tokens"].shape
+    # token-weighted variant (--dpo_token_weighted): weighted reduce + weighted backward entry points
+    out = pol.forward_logps(batch["concatenated_input_ids"], batch["concatenated_labels"], batch["vision_tokens"])
+    tw = torch.ones(4, L - 1)
+    lw, aw, ws = ops.logp_weighted_reduce(out["per_token_logps"], out["labels"], tw)
+    n_plain = calls.count("rlaifv_logp_bwd")
+    pol.backward_logps(torch.zeros(4), use_average=True, token_weight=tw, weight_sum=ws)
+    assert calls.count("rlaifv_logp_bwd_weighted") == 1 and calls.count("rlaifv_logp_bwd") == n_plain
     full = omnilmm_dims()
     assert full.kv_size == 1024 and full.intermediate_size == 14336 and full.vocab_size % 8 == 0
     # bf16 evaluation order of the oracle (used as the second comparison point on the GPU)

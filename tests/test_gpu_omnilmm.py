@@ -67,7 +67,18 @@ def test_omnilmm_policy_matches_oracle_and_reference_fixture(path):
     # bf16-op-order oracle on the same bf16-rounded parameters / inputs, and the fp32 reference fixture
     pb = {k: v.to(torch.bfloat16) for k, v in params.items()}
     ob = OM.omnilmm_policy_logps(pb, dec, res, tok, ids, labels, vt.to(torch.bfloat16))
-    logp = out["logp"].cpu()
+    weighted = "token_weight" in fx.files                  # --dpo_token_weighted fixture (trainers.py:246-261)
+    tw = wsum = None
+    if weighted:
+        tw = torch.from_numpy(fx["token_weight"]).cuda()
+        lw, aw, wsum = ops.logp_weighted_reduce(out["per_token_logps"], out["labels"], tw)
+        ob["logp"] = OM.compute_weighted_logp(ob["per_token_logps"].float(), labels, tw.cpu())
+        logp_dev = lw
+        wm = tw.cpu() * (labels[:, 1:] != -100)
+        assert torch.allclose(wsum.cpu(), wm.sum(-1)) and torch.allclose(aw.cpu(), lw.cpu() / wm.sum(-1), rtol=1e-6)
+    else:
+        logp_dev = out["logp"]
+    logp = logp_dev.cpu()
     ref_fp32 = torch.from_numpy(fx["logp"])
     inherent = rel(ob["logp"], ref_fp32)
     e_ref, e_orc = rel(logp, ref_fp32), rel(logp, ob["logp"])
@@ -81,8 +92,8 @@ def test_omnilmm_policy_matches_oracle_and_reference_fixture(path):
     assert e_pt <= max(1e-3, 2.5 * inh_pt) and e_pt <= 1e-2
     # DPO loss + backward
     rw, rr = torch.from_numpy(fx["ref_win_logp"]).cuda(), torch.from_numpy(fx["ref_rej_logp"]).cuda()
-    losses, cr, rj, dpw, dpr, out9 = ops.dpo_loss(out["logp"][:B].contiguous(), out["logp"][B:].contiguous(), rw, rr, 0.1)
-    pol.backward_logps(torch.cat([dpw, dpr]).contiguous())
+    losses, cr, rj, dpw, dpr, out9 = ops.dpo_loss(logp_dev[:B].contiguous(), logp_dev[B:].contiguous(), rw, rr, 0.1)
+    pol.backward_logps(torch.cat([dpw, dpr]).contiguous(), token_weight=tw, weight_sum=wsum)
     pol.finalize_embed_grad()
     torch.cuda.synchronize()
     assert rel(losses, fx["losses"]) <= 2e-2 and rel(out9[0], fx["loss"]) <= 2e-2
@@ -124,3 +135,64 @@ def test_omnilmm_engine_step_trains_decoder_and_resampler():
     m2 = eng.train_step(batch)
     torch.cuda.synchronize()
     assert float(m2[0]) < loss1                             # one AdamW step on the same batch lowers the loss
+
+
+def test_weighted_logp_kernels_match_torch():
+    """rlaifv_logp_weighted_reduce / rlaifv_logp_bwd_weighted vs fp32 torch (sum and average mode)."""
+    from rlaifv_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    nseq, T, V = 3, 37, 320
+    logits = (torch.randn(nseq * T, V, generator=g) * 2).to(torch.bfloat16).cuda()
+    labels = torch.randint(0, V, (nseq, T), generator=g)
+    labels[:, :9] = -100
+    labels[1, 30:] = -100
+    tw = torch.where(torch.rand(nseq, T - 1, generator=g) < 0.4, 3.0, 1.0)
+    d = torch.tensor([0.7, -1.3, 0.2])
+    for use_avg in (False, True):
+        lf = logits.float().cpu().view(nseq, T, V).clone().requires_grad_(True)
+        pt = torch.gather(torch.log_softmax(lf[:, :-1], -1), 2, labels[:, 1:].clamp_min(0).unsqueeze(-1)).squeeze(-1)
+        wm = tw * (labels[:, 1:] != -100)
+        ref = (pt * wm).sum(-1) / (wm.sum(-1) if use_avg else 1.0)
+        (ref * d).sum().backward()
+        lg = logits.clone()
+        per_tok, lse, _, _, _ = ops.logp_fwd(lg, labels.cuda(), nseq, T)
+        lw, aw, ws = ops.logp_weighted_reduce(per_tok, labels.cuda(), tw.cuda())
+        got = (aw if use_avg else lw).cpu()
+        assert rel(got, ref.detach()) < 2e-3
+        ops.logp_bwd_weighted(lg, labels.cuda(), lse, d.cuda(), tw.cuda(), nseq, T, wsum=ws if use_avg else None)
+        torch.cuda.synchronize()
+        want = lf.grad.view(nseq * T, V)
+        assert float((lg.float().cpu() - want).norm() / want.norm()) < 8e-3
+        assert float(lg.float().cpu().view(nseq, T, V)[:, -1].abs().max()) == 0.0      # last position: no target
+
+
+def test_engine_token_weighted_step_and_llava_refusal():
+    from rlaifv_b200.engine import DPOStepEngine
+    from rlaifv_b200.model import LlavaDims, LlavaDPOPolicy
+    from rlaifv_b200.omnilmm_model import OmniLMMDPOPolicy
+    dec, res, tok = OM.TINY_OMNI_DEC, OM.TINY_OMNI_RES, OM.TINY_OMNI_TOK
+    pol = OmniLMMDPOPolicy(tiny_dims(), "cuda", hf_state=OM.make_omnilmm_params(dec, res, 3))
+    eng = DPOStepEngine(pol, lr=1e-3, total_steps=10, constant_lr=True, dpo_token_weighted=True)
+    batch = OM.synthetic_omni_batch(dec, res, tok, 2, 28, 20, seed=9)
+    ids, labels = batch["concatenated_input_ids"], batch["concatenated_labels"]
+    g = torch.Generator().manual_seed(1)
+    tw = torch.where(torch.rand(4, ids.shape[1] - 1, generator=g) < 0.3, 3.0, 1.0)
+    ref_pt = pol.forward_logps(ids, labels, batch["vision_tokens"], keep_stash=False)["per_token_logps"].float().cpu()
+    batch.update(images=batch["vision_tokens"], beta=0.1, concatenated_token_weight=tw, win_token_weight=tw[:2],
+                 rej_token_weight=tw[2:], win_labels=labels[:2], rej_labels=labels[2:],
+                 ref_win_per_token_logp=ref_pt[:2], ref_rej_per_token_logp=ref_pt[2:])
+    m = eng.train_step(batch)
+    torch.cuda.synchronize()
+    loss1 = float(m[0])
+    assert abs(loss1 - 0.6931472) < 1e-4                    # weighted policy == weighted reference -> ln 2
+    want_chosen = OM.compute_weighted_logp(ref_pt[:2], labels[:2], tw[:2]).mean()
+    assert abs(float(m[6]) - float(want_chosen)) < 1e-2 * abs(float(want_chosen))     # logps_train/chosen is weighted
+    assert float(eng.train_step(batch)[0]) < loss1
+    c = __import__("oracle.llava_dpo_oracle", fromlist=["TINY"]).TINY
+    llava = LlavaDPOPolicy(LlavaDims(vocab_size=c.vocab_size, hidden_size=c.hidden_size,
+                                     intermediate_size=c.intermediate_size, num_layers=c.num_layers,
+                                     num_heads=c.num_heads, clip_hidden=c.clip_hidden,
+                                     clip_intermediate=c.clip_intermediate, clip_layers=c.clip_layers,
+                                     clip_heads=c.clip_heads, image_size=c.image_size, patch_size=c.patch_size), "cuda")
+    with pytest.raises(NotImplementedError):                # the reference refuses it for LLaVA-1.5 too
+        DPOStepEngine(llava, dpo_token_weighted=True)

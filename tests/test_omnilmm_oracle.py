@@ -18,7 +18,7 @@ def sample(t, n=64):
 
 
 def test_fixtures_present():
-    assert len(GOLDEN) == 2
+    assert len(GOLDEN) == 3 and any("weighted" in p for p in GOLDEN)
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
@@ -31,6 +31,8 @@ def test_oracle_matches_reference_omnilmm_fixture(path):
     batch["vision_tokens"].requires_grad_(True)
     batch["ref_win_logp"] = torch.from_numpy(fx["ref_win_logp"])
     batch["ref_rej_logp"] = torch.from_numpy(fx["ref_rej_logp"])
+    if "token_weight" in fx.files:                       # --dpo_token_weighted case (trainers.py:246-261)
+        batch["token_weight"] = torch.from_numpy(fx["token_weight"])
     o = OM.omnilmm_dpo_step(p, dec, res, tok, batch)
     o["loss"].backward()
     close = lambda a, b, tol: np.abs(np.asarray(a) - np.asarray(b)).max() <= tol * (np.abs(np.asarray(b)).max() + 1e-30)
@@ -58,3 +60,18 @@ def test_inplace_splice_map_semantics():
     bad[0, 7] = 9                                                              # <im_end> missing
     with pytest.raises(ValueError):
         OM.inplace_splice_map(bad, tok, Q)
+
+
+def test_host_compute_weighted_logp_matches_reference_output():
+    """rlaifv_b200.trainers.compute_weighted_logp (host side of --dpo_token_weighted) on the reference's own per-token
+    log-probs reproduces the reference's compute_weighted_logp output stored in the fixture."""
+    from rlaifv_b200.trainers import compute_weighted_logp
+    fx = np.load([p for p in GOLDEN if "weighted" in p][0])
+    dec, res, tok = OM.TINY_OMNI_DEC, OM.TINY_OMNI_RES, OM.TINY_OMNI_TOK
+    batch = OM.synthetic_omni_batch(dec, res, tok, int(fx["B"]), 28, 20, seed=int(fx["seed"]) + 7, ragged=True)
+    pt, tw = torch.from_numpy(fx["per_token_logps"]), torch.from_numpy(fx["token_weight"])
+    got = compute_weighted_logp(pt, batch["concatenated_labels"], tw, False)
+    assert torch.allclose(got, torch.from_numpy(fx["logp"]), rtol=1e-6, atol=1e-4)
+    avg = compute_weighted_logp(pt, batch["concatenated_labels"], tw, True)
+    wm = tw * (batch["concatenated_labels"][:, 1:] != -100)
+    assert torch.allclose(avg, got / wm.sum(-1), rtol=1e-6)
