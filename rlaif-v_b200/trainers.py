@@ -2,6 +2,8 @@
 
   dpo_loss(...)                      muffin/train/trainers.py:91-126   -> CUDA dpo_loss kernel
   get_beta_and_logps(...)            muffin/train/trainers.py:161-275  -> fused policy forward (the seam)
+  forward_DPO(...)                   muffin/train/trainers.py:66-88    -> generic branch (OmniLMM policy)
+  compute_weighted_logp(...)         muffin/train/trainers.py:128-137  (--dpo_token_weighted)
   collect_preference_metrics(...)    muffin/train/trainers.py:140-158
   LLaVA15DPOTrainer.compute_loss     muffin/train/trainers.py:279-311  (textually the same flow)
 
@@ -90,20 +92,61 @@ def compute_weighted_logp(per_token_logp, labels, token_weight, use_average):
     return logp
 
 
+class _PolicyPerTokenLogps(torch.autograd.Function):
+    """forward: per-token log-probs [2B, T-1] (forward_DPO(token_weighted=True)); backward: an arbitrary per-token
+    gradient is exactly the token-weighted backward with d_logp = 1 and token_weight = d_per_token."""
+
+    @staticmethod
+    def forward(ctx, anchor, policy, input_ids, labels, images):
+        out = policy.forward_logps(input_ids, labels, images, keep_stash=anchor.requires_grad)
+        ctx.policy = policy
+        return out["per_token_logps"].clone()
+
+    @staticmethod
+    def backward(ctx, d_pt):
+        pol = ctx.policy
+        ones = torch.ones(d_pt.shape[0], dtype=_F32, device=d_pt.device)
+        pol.backward_logps(ones, token_weight=d_pt.to(_F32).contiguous(),
+                           accumulate=getattr(pol, "_grad_accumulate", False))
+        pol.finalize_embed_grad()
+        return None, None, None, None, None
+
+
+def forward_DPO(model, input_ids, labels, attention_mask, images, **kwargs):
+    """muffin/train/trainers.py:66-88 for a policy of this package (OmniLMMDPOPolicy: `images` = the vision tower's
+    output tokens, B or — as the reference passes them, :190 — 2B of them): summed / averaged log-probs [2B], or the
+    per-token log-probs [2B, L-1] with token_weighted=True; autograd-connected to the hand-written backward."""
+    token_weighted = kwargs.pop("token_weighted", False)
+    dpo_use_average = kwargs.pop("dpo_use_average", False)
+    if kwargs.pop("is_minicpm", False):
+        raise NotImplementedError("MiniCPM-V branch")
+    if attention_mask is not None:
+        raise NotImplementedError("attention_mask=None path only (muffin/train/trainers.py:199 sets it to None)")
+    policy = model.policy if hasattr(model, "policy") else model
+    anchor = torch.zeros((), device=policy.device, requires_grad=torch.is_grad_enabled())
+    if token_weighted:
+        return _PolicyPerTokenLogps.apply(anchor, policy, input_ids, labels, images)
+    return _PolicyLogps.apply(anchor, policy, input_ids, labels, images, bool(dpo_use_average))
+
+
 def get_beta_and_logps(data_dict, model, args, is_minicpm=False, is_llava15=False):
-    """Same contract as the reference: pops the collator keys, returns
-    (policy_win_logp, policy_rej_logp, ref_win_logp, ref_rej_logp, beta)."""
-    if not is_llava15 or is_minicpm:
-        raise NotImplementedError("only the is_llava15=True branch is on the B200 hot path")
-    if getattr(args, "dpo_token_weighted", False):
+    """Same contract as the reference (muffin/train/trainers.py:161-275): pops the collator keys, returns
+    (policy_win_logp, policy_rej_logp, ref_win_logp, ref_rej_logp, beta). is_llava15=True: LLaVA-1.5 policy;
+    otherwise the generic `forward_DPO` branch (:233-261) on an OmniLMM policy, including --dpo_token_weighted."""
+    if is_minicpm:
+        raise NotImplementedError("MiniCPM-V branch")
+    token_weighted = bool(getattr(args, "dpo_token_weighted", False))
+    if token_weighted and is_llava15:
         raise NotImplementedError          # muffin/train/trainers.py:246-248 (is_llava15)
     if getattr(args, "task", "DPO") != "DPO":
         raise NotImplementedError("KTO task")
     win_input_ids = data_dict.pop("win_input_ids")
     rej_input_ids = data_dict.pop("rej_input_ids")
-    for k in ("win_labels", "rej_labels", "win_attention_mask", "rej_attention_mask", "ref_win_per_token_logp",
-              "ref_rej_per_token_logp", "concatenated_attention_mask", "win_token_weight", "rej_token_weight",
-              "concatenated_token_weight"):
+    win_labels, rej_labels = data_dict.pop("win_labels", None), data_dict.pop("rej_labels", None)
+    ref_win_pt, ref_rej_pt = data_dict.pop("ref_win_per_token_logp", None), data_dict.pop("ref_rej_per_token_logp", None)
+    win_tw, rej_tw = data_dict.pop("win_token_weight", None), data_dict.pop("rej_token_weight", None)
+    cat_tw = data_dict.pop("concatenated_token_weight", None)
+    for k in ("win_attention_mask", "rej_attention_mask", "concatenated_attention_mask"):
         data_dict.pop(k, None)
     ref_win_avg_logp = data_dict.pop("ref_win_avg_logp")
     ref_rej_avg_logp = data_dict.pop("ref_rej_avg_logp")
@@ -117,8 +160,20 @@ def get_beta_and_logps(data_dict, model, args, is_minicpm=False, is_llava15=Fals
     labels = data_dict.pop("concatenated_labels")
     policy = model.policy if hasattr(model, "policy") else model
     dev = policy.device
-    anchor = torch.zeros((), device=dev, requires_grad=torch.is_grad_enabled())
-    logp = _PolicyLogps.apply(anchor, policy, ids, labels, images, bool(args.dpo_use_average))
+    if is_llava15 != (policy.dims.frontend == "clip_mlp"):
+        raise ValueError("is_llava15=%s does not match the policy's vision front-end %r" % (is_llava15,
+                                                                                             policy.dims.frontend))
+    if is_llava15:
+        anchor = torch.zeros((), device=dev, requires_grad=torch.is_grad_enabled())
+        logp = _PolicyLogps.apply(anchor, policy, ids, labels, images, bool(args.dpo_use_average))
+    else:
+        logp = forward_DPO(model, ids, labels, None, images, token_weighted=token_weighted,
+                           dpo_use_average=args.dpo_use_average)
+        if token_weighted:                                  # trainers.py:246-261
+            ua = bool(args.dpo_use_average)
+            ref_win_logp = compute_weighted_logp(ref_win_pt, win_labels, win_tw, ua)
+            ref_rej_logp = compute_weighted_logp(ref_rej_pt, rej_labels, rej_tw, ua)
+            logp = compute_weighted_logp(logp, labels.to(dev), cat_tw.to(dev), ua)
     win_size, rej_size = win_input_ids.shape[0], rej_input_ids.shape[0]
     assert win_size == rej_size
     policy_win_logp, policy_rej_logp = logp.split([win_size, rej_size])

@@ -137,6 +137,30 @@ def test_omnilmm_policy_launch_sequence_dry_run(monkeypatch):
     n_plain = calls.count("rlaifv_logp_bwd")
     pol.backward_logps(torch.zeros(4), use_average=True, token_weight=tw, weight_sum=ws)
     assert calls.count("rlaifv_logp_bwd_weighted") == 1 and calls.count("rlaifv_logp_bwd") == n_plain
+    # generic get_beta_and_logps branch (forward_DPO) incl. --dpo_token_weighted, autograd bridge end to end
+    from types import SimpleNamespace
+    from rlaifv_b200 import trainers
+    ids, labels = batch["concatenated_input_ids"], batch["concatenated_labels"]
+    for weighted in (False, True):
+        dd = {"win_input_ids": ids[:2], "rej_input_ids": ids[2:], "win_labels": labels[:2], "rej_labels": labels[2:],
+              "ref_win_per_token_logp": torch.zeros(2, L - 1), "ref_rej_per_token_logp": torch.zeros(2, L - 1),
+              "win_token_weight": tw[:2], "rej_token_weight": tw[2:], "concatenated_token_weight": tw,
+              "ref_win_avg_logp": torch.zeros(2), "ref_rej_avg_logp": torch.zeros(2), "ref_win_logp": torch.zeros(2),
+              "ref_rej_logp": torch.zeros(2), "beta": 0.1, "images": batch["vision_tokens"],
+              "concatenated_input_ids": ids, "concatenated_labels": labels, "concatenated_attention_mask": None}
+        args = SimpleNamespace(dpo_use_average=False, dpo_token_weighted=weighted, task="DPO")
+        n_w = calls.count("rlaifv_logp_bwd_weighted")
+        pw, pr, rw, rr, beta = trainers.get_beta_and_logps(dd, pol, args, is_llava15=False)
+        assert pw.shape == (2,) and pr.shape == (2,) and pw.requires_grad and not dd
+        losses, cr, rj = trainers.dpo_loss(pw, pr, rw, rr, beta)
+        losses.mean().backward()
+        assert calls.count("rlaifv_logp_bwd_weighted") == n_w + (1 if weighted else 0)
+    with pytest.raises(ValueError):
+        trainers.get_beta_and_logps({**{k: None for k in ("win_input_ids", "rej_input_ids", "ref_win_avg_logp",
+                                                          "ref_rej_avg_logp", "ref_win_logp", "ref_rej_logp", "beta",
+                                                          "images", "concatenated_input_ids", "concatenated_labels")}},
+                                    pol, SimpleNamespace(dpo_use_average=False, dpo_token_weighted=False, task="DPO"),
+                                    is_llava15=True)
     full = omnilmm_dims()
     assert full.kv_size == 1024 and full.intermediate_size == 14336 and full.vocab_size % 8 == 0
     # bf16 evaluation order of the oracle (used as the second comparison point on the GPU)

@@ -196,3 +196,49 @@ def test_engine_token_weighted_step_and_llava_refusal():
                                      clip_heads=c.clip_heads, image_size=c.image_size, patch_size=c.patch_size), "cuda")
     with pytest.raises(NotImplementedError):                # the reference refuses it for LLaVA-1.5 too
         DPOStepEngine(llava, dpo_token_weighted=True)
+
+
+@pytest.mark.parametrize("case", ["omni_ragged_b2", "omni_weighted_b2"])
+def test_generic_get_beta_and_logps_branch_matches_reference_fixture(case):
+    """trainers.get_beta_and_logps(is_llava15=False) -> forward_DPO (-> compute_weighted_logp) -> dpo_loss -> autograd
+    backward through the hand-written kernels, against the reference fixture (muffin/train/trainers.py:233-275)."""
+    from types import SimpleNamespace
+    from rlaifv_b200 import trainers
+    from rlaifv_b200.omnilmm_model import OmniLMMDPOPolicy
+    fx = np.load([p for p in GOLDEN if case in p][0])
+    dec, res, tok = OM.TINY_OMNI_DEC, OM.TINY_OMNI_RES, OM.TINY_OMNI_TOK
+    B, seed = int(fx["B"]), int(fx["seed"])
+    pol = OmniLMMDPOPolicy(tiny_dims(), "cuda", hf_state=OM.make_omnilmm_params(dec, res, seed))
+    batch = OM.synthetic_omni_batch(dec, res, tok, B, 28, 20, seed=seed + 7, ragged=True)
+    ids, labels = batch["concatenated_input_ids"], batch["concatenated_labels"]
+    L = ids.shape[1]
+    weighted = "token_weight" in fx.files
+    tw = torch.from_numpy(fx["token_weight"]) if weighted else torch.ones(2 * B, L - 1)
+    rw, rr = torch.from_numpy(fx["ref_win_logp"]), torch.from_numpy(fx["ref_rej_logp"])
+    # per-token reference log-probs whose weighted sums are the fixture's reference log-probs
+    ref_pt = torch.zeros(2 * B, L - 1)
+    first = (labels[:, 1:] != -100).float().argmax(-1)
+    for b in range(2 * B):
+        ref_pt[b, first[b]] = (rw[b] if b < B else rr[b - B]) / tw[b, first[b]]
+    dd = {"win_input_ids": ids[:B], "rej_input_ids": ids[B:], "win_labels": labels[:B], "rej_labels": labels[B:],
+          "ref_win_per_token_logp": ref_pt[:B], "ref_rej_per_token_logp": ref_pt[B:], "win_token_weight": tw[:B],
+          "rej_token_weight": tw[B:], "concatenated_token_weight": tw, "ref_win_avg_logp": rw / 10,
+          "ref_rej_avg_logp": rr / 10, "ref_win_logp": rw, "ref_rej_logp": rr, "beta": 0.1,
+          "images": batch["vision_tokens"], "concatenated_input_ids": ids, "concatenated_labels": labels,
+          "concatenated_attention_mask": torch.ones_like(ids), "win_attention_mask": None, "rej_attention_mask": None}
+    args = SimpleNamespace(dpo_use_average=False, dpo_token_weighted=weighted, task="DPO")
+    pol.resampler.zero_grad()
+    pw, pr, rw_d, rr_d, beta = trainers.get_beta_and_logps(dd, pol, args, is_llava15=False)
+    assert not dd and beta == 0.1
+    assert rel(torch.cat([pw, pr]).detach(), fx["logp"]) <= 1e-3
+    assert torch.allclose(rw_d.cpu(), rw, rtol=1e-5) and torch.allclose(rr_d.cpu(), rr, rtol=1e-5)
+    losses, cr, rj = trainers.dpo_loss(pw, pr, rw_d, rr_d, beta)
+    assert rel(losses.detach(), fx["losses"]) <= 2e-2
+    losses.mean().backward()
+    torch.cuda.synchronize()
+    grads = dict(pol.store.hf_grad_views())
+    grads.update({"model.resampler." + k: v for k, v in pol.resampler.g.items()})
+    for name in ("lm_head.weight", "model.layers.0.self_attn.q_proj.weight", "model.layers.1.mlp.down_proj.weight",
+                 "model.resampler.proj", "model.resampler.attn.in_proj_weight", "model.embed_tokens.weight"):
+        gn = float(fx["gradnorm:" + name])
+        assert abs(float(grads[name].float().norm()) - gn) <= 3e-2 * gn, name
