@@ -14,20 +14,29 @@ import torch
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def script_flags(name="llava15_train.sh", module="rlaifv_b200.train_llava15"):
+def script_flags(name="llava15_train.sh"):
+    """--flag value pairs of the bash arrays in the launch script."""
     txt = open(os.path.join(REPO, "script", "train", name)).read()
-    txt = txt[txt.index(module):]
-    txt = txt.split("\n\n")[0]                       # the launch command only (the LoRA script post-processes after it)
-    toks = re.findall(r"(--[a-z_0-9]+)\s+([^\\\n]+?)\s*(?:\\|$)", txt, flags=re.M)
+    body = "\n".join(re.findall(r"^[A-Z]+=\((.*?)\)$", txt, flags=re.M | re.S))
+    toks = re.findall(r"(--[a-z_0-9]+)\s+('[^']*'|\"[^\"]*\"|[^\s]+)", body)
     argv = []
     for k, v in toks:
-        argv += [k, v.strip().strip("'\"")]
+        argv += [k, v.strip("'\"")]
     return argv
+
+
+def reference_script_flags(name):
+    """Flag names of the reference's own launch scripts (fixture: every `--flag` token of
+    /root/reference/script/train/<name>, extracted with re.findall(r"(--[a-z_0-9]+)") in the build container)."""
+    with open(os.path.join(REPO, "tests", "golden_host", "reference_script_flags.json")) as f:
+        return set(json.load(f)[name])
 
 
 def test_every_reference_flag_parses():
     from rlaifv_b200.train_llava15 import parse_args_into_dataclasses, zero_stage
-    argv = [a.replace("$task_name-$exp_name", "x").replace("$exp_name", "x") for a in script_flags()]
+    argv = [a.replace("$CKPT", "x").replace("$exp_name", "x") for a in script_flags()]
+    ref = reference_script_flags("llava15_train.sh")
+    assert ref <= set(argv[0::2]), ref - set(argv[0::2])      # every flag of the reference recipe is present
     m, d, t = parse_args_into_dataclasses(argv)
     assert t.task == "DPO" and d.dpo_beta == 0.1 and t.dpo_use_average is False and t.max_steps == 2672
     assert t.learning_rate == 5e-7 and t.weight_decay == 0.01 and t.warmup_ratio == 0.05 and t.bf16 is True
@@ -39,9 +48,11 @@ def test_every_reference_flag_parses():
 def test_every_reference_lora_flag_parses():
     """script/train/llava15_train_lora.sh (reference: same file name, :6-49) through the LoRA entry's argv path."""
     from rlaifv_b200.train_llava15 import parse_args_into_dataclasses
-    argv = [a.replace("$task_name-$exp_name", "x").replace("$exp_name", "x")
-            for a in script_flags("llava15_train_lora.sh", "rlaifv_b200.train_llava15_lora")]
-    assert "--lora_enable" in argv
+    argv = [a.replace("$CKPT", "x").replace("$exp_name", "x") for a in script_flags("llava15_train_lora.sh")]
+    ref = reference_script_flags("llava15_train_lora.sh")
+    assert ref <= set(argv[0::2]), ref - set(argv[0::2])
+    assert "--lora_enable" in argv and "rlaifv_b200.train_llava15_lora" in open(
+        os.path.join(REPO, "script", "train", "llava15_train_lora.sh")).read()
     m, d, t = parse_args_into_dataclasses(argv)
     assert t.lora_enable is True and t.lora_r == 64 and t.lora_alpha == 16 and t.lora_dropout == 0.05
     assert t.learning_rate == 1e-5 and t.fully_tune is False and t.task == "DPO" and t.lora_bias == "none"
