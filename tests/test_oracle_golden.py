@@ -133,3 +133,24 @@ def test_adamw_matches_torch():
         opt.step()
         p, m, v = O.adamw_update(p, g * step, m, v, step, 1e-3)
         assert torch.allclose(p, ref_p.detach(), atol=1e-6)
+
+
+def test_splice_edge_cases_match_reference_fixture():
+    """Oracle splice on edge inputs (truncation, image-less sequence, image first/last, two images, very ragged) ==
+    the unmodified reference's prepare_inputs_labels_for_multimodal (oracle/gen_golden_splice_edges.py)."""
+    fx = np.load(os.path.join(os.path.dirname(__file__), "golden_host", "splice_edge_cases.npz"))
+    cfg = O.TINY
+    params = O.make_params(cfg, seed=0)
+    assert len(fx["names"]) == 6
+    for name in [str(n) for n in fx["names"]]:
+        ids, labels = torch.from_numpy(fx[name + ":ids"]), torch.from_numpy(fx[name + ":labels"])
+        max_len, n_images = int(fx[name + ":max_len"]), int(fx[name + ":n_images"])
+        g = torch.Generator().manual_seed(int(fx[name + ":image_seed"]))
+        images = torch.randn(n_images, 3, cfg.image_size, cfg.image_size, generator=g)
+        with torch.no_grad():
+            feats = O.mm_projector(params, O.clip_features(params, images, cfg))
+            src, new_labels, T = O.splice_index_map(ids, labels, cfg.num_patches, max_len)
+            emb = O.splice_embeds(params, ids, src, feats)
+        assert np.array_equal(new_labels.numpy(), fx[name + ":ref_labels"]), name            # bit-exact
+        assert T <= max_len
+        assert np.allclose(emb.double().sum(-1).numpy(), fx[name + ":ref_embeds_rowsum"], rtol=1e-6, atol=1e-6), name
