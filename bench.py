@@ -15,7 +15,12 @@ fused fp32 AdamW, on BASELINE.json configs[1]: 8 synthetic pairs per GPU, 336x33
 `roofline`: dominant kernel = the tcgen05 GEMM; achieved = sum(2MNK) / sum(CUDA-event durations) of
            every GEMM launch of one instrumented step, against MEASURED_PEAKS.json.
 `cpu_baseline` / `--impl reference`: the oracle port of the reference path (oracle/llava_dpo_oracle.py)
-           on the host cores, on a bounded sample (see cpu_reference_pairs_per_sec).
+           on the host cores, on a bounded sample (see cpu_reference_pairs_per_sec); thread count calibrated
+           against the container's real CPU quota.
+`parity_full_width`: checker leg — the CUDA path vs the oracle on the same full-width 1-layer model (log-probs,
+           loss, gradients), with the reference's own bf16-vs-fp32 gap beside it.
+Side workloads (not the headline line): `--lora` (BASELINE config e), `--omnilmm` (config d downstream of the
+vision tower).
 """
 import argparse
 import json
