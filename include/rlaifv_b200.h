@@ -58,6 +58,9 @@ int rlaifv_gemm_set_2cta(int enable);
 /* raster group size (row-blocks per group, default 16) and profiling switches (debug: bit0 skip stores,
  * bit1 skip TMEM loads too — results are then garbage; for roofline experiments only). */
 int rlaifv_gemm_set_tuning(int group_m, int debug);
+/* EXPERIMENTAL (default off): run GEMMs with K >= min_k and no bias / activation / residual as n K-slice passes
+ * (passes 2.. with C +=) so each pass's operand slabs fit the L2. n <= 1 switches it off. */
+int rlaifv_gemm_set_split_k(int n, int min_k);
 
 /* ---- attention (tcgen05, S/O accumulators in TMEM) ---------------------------------------------
  * q/k/v/out: [nseq*S][ld] bf16, head h at columns [h*head_dim, (h+1)*head_dim); lse fp32

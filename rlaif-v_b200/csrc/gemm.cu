@@ -650,12 +650,38 @@ extern "C" int rlaifv_gemm_set_2cta(int enable) {
 }
 
 // C ABI — see include/rlaifv_b200.h for the contract.
+// EXPERIMENTAL, off by default (rlaifv_gemm_set_split_k): long-K launches without bias / activation / residual
+// (dgrad, wgrad) run as `n` passes over K slices, passes 2.. with C += — each pass's operand slabs then fit the L2
+// (tools/l2_raster_model.py: dgrad 2.4 -> ~0.9 GB DRAM reads at n = 2). One extra bf16 rounding per pass boundary.
+static int g_split_k = 0;
+static int g_split_k_min_k = 8192;
+extern "C" int rlaifv_gemm_set_split_k(int n, int min_k) {
+  g_split_k = n > 1 ? n : 0;
+  if (min_k > 0) g_split_k_min_k = min_k;
+  return 0;
+}
+
 static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major,
                      void* C, long long ldc, int M, int N, int K, const void* bias, const void* residual,
                      long long ldr, int act, int accumulate, int tile_n, float alpha, void* stream,
                      const void* A2 = nullptr, long long lda2 = 0, const void* B2 = nullptr, long long ldb2 = 0,
                      int K2 = 0, int r2 = 0, int n_sub = 0) {
   B200_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  if (g_split_k > 1 && K2 == 0 && !bias && !residual && act == 0 && K >= g_split_k_min_k) {
+    const int n = g_split_k;
+    const int ks = ((K + n - 1) / n + GEMM_BK - 1) / GEMM_BK * GEMM_BK;   // slice = whole 64-wide k blocks
+    g_split_k = 0;                                   // the passes themselves are ordinary launches
+    int rc = 0;
+    for (int s = 0; s * ks < K && rc == 0; ++s) {
+      const int klen = K - s * ks < ks ? K - s * ks : ks;                 // the last slice takes the ragged tail
+      const bf16* As = (const bf16*)A + (a_mn_major ? (long long)s * ks * lda : (long long)s * ks);
+      const bf16* Bs = (const bf16*)B + (b_mn_major ? (long long)s * ks * ldb : (long long)s * ks);
+      rc = gemm_impl(As, lda, a_mn_major, Bs, ldb, b_mn_major, C, ldc, M, N, klen, nullptr, nullptr, 0, 0,
+                     s == 0 ? accumulate : 1, tile_n, alpha, stream);
+    }
+    g_split_k = n;
+    return rc;
+  }
   B200_REQUIRE(N % 8 == 0 && ldc % 8 == 0, "gemm: N (%d) and ldc (%lld) must be multiples of 8", N,
                ldc);
   B200_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8");
