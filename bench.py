@@ -14,9 +14,10 @@ fused fp32 AdamW, on BASELINE.json configs[1]: 8 synthetic pairs per GPU, 336x33
            H2D of ids/labels/images/ref-logps and a D2H read of the loss inside the timed region.
 `roofline`: dominant kernel = the tcgen05 GEMM; achieved = sum(2MNK) / sum(CUDA-event durations) of
            every GEMM launch of one instrumented step, against MEASURED_PEAKS.json.
-`cpu_baseline` / `--impl reference`: the oracle port of the reference path (oracle/llava_dpo_oracle.py)
-           on the host cores, on a bounded sample (see cpu_reference_pairs_per_sec); thread count calibrated
-           against the container's real CPU quota.
+`cpu_baseline` / `--impl reference`: the UNMODIFIED reference staged under oracle/_ref (oracle/stage_ref.py; the
+           oracle port only if that staging is absent) on the host cores, on a bounded sample: full-width config-(a)
+           steps at 2 and 4 decoder layers after a warm-up, min of 3, extrapolated to 32 layers, raw timings in the
+           line (see cpu_reference_pairs_per_sec); thread count calibrated against the container's real CPU quota.
 `parity_full_width`: checker leg — the CUDA path vs the oracle on the same full-width 1-layer model (log-probs,
            loss, gradients), with the reference's own bf16-vs-fp32 gap beside it.
 Side workloads (not the headline line): `--lora` (BASELINE config e), `--omnilmm` (config d downstream of the
@@ -278,57 +279,150 @@ def pick_cpu_threads():
     return best
 
 
-def cpu_reference_pairs_per_sec(dtype_name="float32", check=None):
-    """Times oracle.dpo_step fwd + bwd + AdamW at FULL WIDTH (h=4096, ffn=11008, vocab=32000,
-    CLIP-L 23 layers, 336 px) on config (a) shape (1 pair, 64-token responses, T=687) with 1 and 2
-    decoder layers, and extrapolates linearly to 32 layers."""
-    from oracle import llava_dpo_oracle as O
-    threads = pick_cpu_threads()
-    dt = getattr(torch, dtype_name)
-    times = {}
-    for nl in (1, 2):
-        cfg, p, batch = full_width_case(nl, dt)
-        names = O.trainable_names(p)
-        state = {k: (torch.zeros_like(p[k], dtype=torch.float32), torch.zeros_like(p[k], dtype=torch.float32))
-                 for k in names}
+REF_ARM_LAYERS = (2, 4)     # full-width decoder depths that are timed; the 32-layer step is extrapolated linearly
+
+
+def _time_cpu_steps(step_fn, warmup, reps):
+    """`warmup` untimed passes (first-touch page faults of parameters / gradients / AdamW state / activations, oneDNN
+    primitive creation), then `reps` timed ones; returns the list of wall-clock seconds."""
+    for _ in range(warmup):
+        step_fn()
+    out = []
+    for _ in range(reps):
         t0 = time.perf_counter()
+        step_fn()
+        out.append(time.perf_counter() - t0)
+    return out
+
+
+def _reference_step_fn(nl, cfg=None):
+    """One DPO optimisation step of the UNMODIFIED reference (staged under oracle/_ref by oracle/stage_ref.py) on
+    torch-CPU fp32 at full width with `nl` decoder layers, config (a) shape: the reference's collator ->
+    get_beta_and_logps(is_llava15=True) [prepare_inputs_labels_for_multimodal -> LlavaLlamaForCausalLM.forward ->
+    get_batch_logps] -> dpo_loss -> backward -> torch.optim.AdamW.step."""
+    from oracle import llava_dpo_oracle as O       # input synthesis only (SURVEY §8d canonical inputs)
+    from oracle import stage_ref
+    import dataclasses
+    R = stage_ref.import_reference()
+    cfg = O.OracleConfig(num_layers=nl) if cfg is None else dataclasses.replace(cfg, num_layers=nl)
+    model = stage_ref.build_reference_model(R, cfg, None)      # HF random init at true dimensions
+    model.train()
+    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=5e-7, weight_decay=0.01)
+    batch = O.synthetic_pair_batch(cfg, 1, PROMPT_LEN, 64, seed=1234, image_pos=IMAGE_POS)
+
+    class Tok:
+        pad_token_id = 0
+
+    class Args:
+        dpo_use_average = False
+        dpo_token_weighted = False
+        task = "DPO"
+
+    ids, labs = batch["concatenated_input_ids"], batch["concatenated_labels"]
+    inst = []
+    for kind, row in (("rej", 1), ("win", 0)):
+        inst.append({"input_ids": ids[row].clone(), "labels": labs[row].clone(), "image": batch["images"][0],
+                     f"ref_{kind}_logp": -700.0 if kind == "win" else -690.5, f"ref_{kind}_avg_logp": -10.9,
+                     f"ref_{kind}_per_token_logp": [0.0] * (ids.shape[1] + 600)})
+    data = R["DataCollatorForDPODataset"](tokenizer=Tok(), beta=0.1, mod_token_weight=1.0)([tuple(inst)])
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        pw, pr, rw, rr, beta = R["get_beta_and_logps"](dict(data), model, Args(), is_llava15=True)
+        losses, _, _ = R["dpo_loss"](pw, pr, rw, rr, beta=beta)
+        loss = losses.mean()
+        loss.backward()
+        opt.step()
+        return float(loss)
+    return step
+
+
+def _port_step_fn(nl):
+    """Fallback when oracle/_ref is not staged: the oracle port of the same path (kind "port")."""
+    from oracle import llava_dpo_oracle as O
+    cfg, p, batch = full_width_case(nl, torch.float32)
+    names = O.trainable_names(p)
+    state = {k: [torch.zeros_like(p[k]), torch.zeros_like(p[k])] for k in names}
+
+    def step():
+        for k in names:
+            p[k].grad = None
         out = O.dpo_step(p, cfg, batch, beta=0.1)
         out["loss"].backward()
-        if check is not None and nl == 1:
-            t_pause = time.perf_counter()
-            check(p, cfg, batch, out)
-            t0 += time.perf_counter() - t_pause
         with torch.no_grad():
             for k in names:
-                new_p, m, v = O.adamw_update(p[k].float(), p[k].grad.float(), state[k][0], state[k][1], 1, 5e-7)
-                p[k].copy_(new_p.to(dt))
-        times[nl] = time.perf_counter() - t0
-        del p, state, out
-    t_layer = max(times[2] - times[1], 1e-9)
-    t_full = times[1] + 31 * t_layer
-    sample = ("oracle port, torch-CPU %s, full width, 1 pair, R=64 (T=687): fwd+bwd+AdamW timed with 1 and 2 "
-              "decoder layers (%.1fs, %.1fs) and extrapolated linearly to 32 layers" % (dtype_name, times[1], times[2]))
-    sample += "; %d torch threads (best of a matmul calibration; os.cpu_count()=%s)" % (threads, os.cpu_count())
-    return 1.0 / t_full, threads, sample
+                new_p, m, v = O.adamw_update(p[k], p[k].grad, state[k][0], state[k][1], 1, 5e-7)
+                p[k].copy_(new_p)
+                state[k][0], state[k][1] = m, v
+        return float(out["loss"])
+    return step
+
+
+def cpu_reference_pairs_per_sec(reps=3, warmup=1):
+    """The reference arm / cpu_baseline leg: full-width (h=4096, ffn=11008, vocab=32000, CLIP-L 23 layers, 336 px)
+    config-(a) step (1 pair, 64-token responses, T=687), fp32, timed at 2 and 4 decoder layers after a warm-up pass
+    each (min of `reps`), extrapolated linearly to the 32-layer model: t32 = t4 + 28 * (t4 - t2) / 2.
+    Returns (pairs/s, threads, kind, sample description, raw timings)."""
+    from oracle import stage_ref
+    threads = pick_cpu_threads()
+    kind = "reference" if stage_ref.available() else "port"
+    make = _reference_step_fn if kind == "reference" else _port_step_fn
+    raw, best = {}, {}
+    for nl in REF_ARM_LAYERS:
+        fn = make(nl)
+        raw[nl] = _time_cpu_steps(fn, warmup, reps)
+        best[nl] = min(raw[nl])
+        del fn
+        import gc
+        gc.collect()
+    lo, hi = REF_ARM_LAYERS
+    t_layer = max((best[hi] - best[lo]) / (hi - lo), 1e-9)
+    t_full = best[hi] + (32 - hi) * t_layer
+    src = ("the unmodified reference staged under oracle/_ref (collator -> get_beta_and_logps -> dpo_loss -> backward "
+           "-> torch.optim.AdamW)" if kind == "reference" else "oracle port of the reference path (oracle/_ref not staged)")
+    sample = ("%s, torch-CPU float32, full width, config (a) shape: 1 pair, R=64 (T=687); %d warm-up + %d timed steps at "
+              "%d and %d decoder layers (min %.2fs / %.2fs), extrapolated linearly to 32 layers (%.2fs per layer => "
+              "%.1fs per step); %d torch threads (matmul calibration; os.cpu_count()=%s)"
+              % (src, warmup, reps, lo, hi, best[lo], best[hi], t_layer, t_full, threads, os.cpu_count()))
+    timings = {"layers_%d_s" % nl: [round(t, 3) for t in raw[nl]] for nl in REF_ARM_LAYERS}
+    timings.update(per_layer_s=round(t_layer, 4), extrapolated_step_s=round(t_full, 2))
+    return 1.0 / t_full, threads, kind, sample, timings
 
 
 def run_reference_arm(args, rank):
+    """`bench.py --impl reference`: rank 0 alone runs; other ranks exit 0 without work. A "step" of this arm is the
+    bounded sample described in cpu_reference_pairs_per_sec; K and W are capped (3 / 1) so that the run ends within
+    a few minutes whatever the driver passes."""
     if rank != 0:
         return
-    vals = []
-    for _ in range(max(1, min(args.steps, 1))):
-        v, cores, sample = cpu_reference_pairs_per_sec()
-        vals.append(v)
-    value = sum(vals) / len(vals)
+    reps, warm = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    value, cores, kind, sample, timings = cpu_reference_pairs_per_sec(reps=reps, warmup=warm)
     line = {"impl": "reference", "metric": "preference-pairs/sec LLaVA-1.5-7B DPO step", "value": value,
             "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "LLaVA-1.5-7B DPO step (reference CPU path via oracle port; config (a) shape, "
-                                   "extrapolated to 32 layers)"},
-            "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": "LLaVA-1.5-7B DPO step, reference CPU path (config (a) shape: 1 pair, 336px, 64-tok "
+                                   "responses; full width, 2- and 4-layer steps extrapolated to 32 layers)",
+                       "timed_steps_per_depth": reps, "warmup_steps_per_depth": warm, "same_config_as_b200_arm": False,
+                       "note": "BASELINE.json configs[0] is the reference's CPU-runnable case; configs[1] (8 pairs, "
+                               "512-tok) would take ~15 min per CPU step"},
+            "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": kind, "sample": sample,
+                             "timings": timings},
             "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def full_width_parity_report():
+    """Checker leg (not timed): oracle fp32 fwd+bwd on the full-width 1-layer model, then the CUDA path on the same
+    weights / batch."""
+    from oracle import llava_dpo_oracle as O
+    cfg, p, batch = full_width_case(1, torch.float32)
+    out = O.dpo_step(p, cfg, batch, beta=0.1)
+    out["loss"].backward()
+    try:
+        return gpu_full_width_parity(p, cfg, batch, out)
+    except Exception as exc:                      # the checker must never take the bench line down
+        return {"error": "%s: %s" % (type(exc).__name__, exc)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -576,17 +670,10 @@ def main():
             policy._stash = None
             policy._bufs.clear()
             torch.cuda.empty_cache()
-            parity = {}
-
-            def check(*a):
-                try:
-                    parity.update(gpu_full_width_parity(*a))
-                except Exception as exc:                      # the checker must never take the bench line down
-                    parity["error"] = "%s: %s" % (type(exc).__name__, exc)
-
-            v, cores, sample = cpu_reference_pairs_per_sec(check=check)
-            line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample}
-            line["parity_full_width"] = parity
+            line["parity_full_width"] = full_width_parity_report()
+            v, cores, kind, sample, timings = cpu_reference_pairs_per_sec(reps=2, warmup=1)
+            line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": kind, "sample": sample,
+                                    "timings": timings}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

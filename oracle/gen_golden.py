@@ -15,7 +15,6 @@ reference outputs it stores) the CUDA path.
 """
 import os
 import sys
-import types
 
 import numpy as np
 import torch
@@ -26,60 +25,17 @@ REF = "/root/reference"
 
 
 def import_reference():
+    """The reference's own modules, imported from /root/reference itself (golden generation never goes through the
+    staged copy)."""
     if not os.path.isdir(REF):
         raise SystemExit("reference tree %s not present (golden generation runs in the build container only)" % REF)
-    sys.dont_write_bytecode = True
-    sys.path.insert(0, REF)
-    for name in ("matplotlib", "matplotlib.pyplot"):   # utils/utils.py:19 imports it at module top
-        if name not in sys.modules:
-            sys.modules[name] = types.ModuleType(name)
-    from llava.model import LlavaLlamaForCausalLM, LlavaConfig                      # noqa
-    from llava.model.multimodal_encoder.clip_encoder import CLIPVisionTower        # noqa
-    from llava.model.multimodal_projector.builder import build_vision_projector    # noqa
-    from muffin.train.trainers import get_beta_and_logps, dpo_loss                 # noqa
-    from muffin.train.train_muffin import DataCollatorForDPODataset                # noqa
-    from muffin.eval.muffin_inference_logp import get_batch_logps                  # noqa
-    from transformers import CLIPVisionModel, CLIPVisionConfig                     # noqa
-    return dict(LlavaLlamaForCausalLM=LlavaLlamaForCausalLM, LlavaConfig=LlavaConfig,
-                CLIPVisionTower=CLIPVisionTower, build_vision_projector=build_vision_projector,
-                get_beta_and_logps=get_beta_and_logps, dpo_loss=dpo_loss,
-                DataCollatorForDPODataset=DataCollatorForDPODataset, get_batch_logps=get_batch_logps,
-                CLIPVisionModel=CLIPVisionModel, CLIPVisionConfig=CLIPVisionConfig)
+    from oracle import stage_ref
+    return stage_ref.import_reference(REF)
 
 
-def build_reference_model(R, cfg, params):
-    """SURVEY.md Appendix A recipe: random-init model, CLIP tower attached without network."""
-    lc = R["LlavaConfig"](vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size,
-                          intermediate_size=cfg.intermediate_size, num_hidden_layers=cfg.num_layers,
-                          num_attention_heads=cfg.num_heads, num_key_value_heads=cfg.kv_heads,
-                          rms_norm_eps=cfg.rms_eps, rope_theta=cfg.rope_theta, max_position_embeddings=4096,
-                          attn_implementation="eager", tie_word_embeddings=False, pad_token_id=0,
-                          bos_token_id=1, eos_token_id=2)
-    lc.pretraining_tp = 1
-    model = R["LlavaLlamaForCausalLM"](lc)
-    vt = R["CLIPVisionTower"].__new__(R["CLIPVisionTower"])
-    torch.nn.Module.__init__(vt)
-    vt.is_loaded = True
-    vt.vision_tower_name = "synthetic"
-    vt.select_layer = cfg.select_layer
-    vt.select_feature = "patch"
-    vc = R["CLIPVisionConfig"](hidden_size=cfg.clip_hidden, intermediate_size=cfg.clip_intermediate,
-                               num_hidden_layers=cfg.clip_layers, num_attention_heads=cfg.clip_heads,
-                               image_size=cfg.image_size, patch_size=cfg.patch_size, hidden_act="quick_gelu",
-                               layer_norm_eps=cfg.clip_eps, attn_implementation="eager")
-    vt.vision_tower = R["CLIPVisionModel"](vc)
-    vt.vision_tower.requires_grad_(False)
-    model.model.vision_tower = vt
-    model.config.mm_projector_type = "mlp2x_gelu"
-    model.config.mm_hidden_size = cfg.clip_hidden
-    model.model.mm_projector = R["build_vision_projector"](model.config)
-    model.config.tokenizer_model_max_length = cfg.max_len
-    model.config.tokenizer_padding_side = "right"
-    model.float()
-    missing, unexpected = model.load_state_dict({k: v.clone() for k, v in params.items()}, strict=False)
-    missing = [m for m in missing if "rotary" not in m and "position_ids" not in m]
-    assert not missing and not unexpected, (missing, unexpected)
-    return model
+def build_reference_model(R, cfg, params, load=True):
+    from oracle import stage_ref
+    return stage_ref.build_reference_model(R, cfg, params, load=load)
 
 
 def make_instances(batch, ref, B):
@@ -97,6 +53,57 @@ def make_instances(batch, ref, B):
             return d
         inst.append((one(B + i, "rej"), one(i, "win")))
     return inst
+
+
+def reference_bf16_run(R, model, data, Args):
+    """The UNMODIFIED reference evaluated the way the shipped recipe runs it: `model.bfloat16()` (DeepSpeed bf16,
+    script/zero2.json:2-4), float inputs cast to bf16 (HF Trainer._prepare_inputs under DeepSpeed-bf16,
+    HF:trainer.py:2169-2176) and the logits upcast to fp32 before the log-softmax (pinned transformers==4.35.0,
+    HF:llama/modeling_llama.py `logits = logits.float()`; 5.5.0 dropped that line, so the upcast is re-applied on
+    the forward's output here — the model code itself is untouched).  Returns the log-probs / losses / gradients
+    north_star's "1e-3 relative in bf16 vs the reference HF path" refers to."""
+    import copy
+    mb = copy.deepcopy(model).bfloat16()
+    # Environment drift, not reference code: transformers 5.5 keeps RoPE's `inv_freq` as a module buffer, so
+    # `.bfloat16()` rounds it and every angle changes; the pinned 4.35.0 builds its cos/sin cache from the fp32
+    # inv_freq at construction and only the cached cos/sin are rounded to bf16 (HF:llama/modeling_llama.py
+    # LlamaRotaryEmbedding._set_cos_sin_cache).  Restore the fp32 inv_freq to get the pinned version's angles.
+    for mod in mb.modules():
+        if hasattr(mod, "inv_freq") and hasattr(mod, "original_inv_freq"):
+            hd = mb.config.hidden_size // mb.config.num_attention_heads
+            inv = 1.0 / (mb.config.rope_theta if hasattr(mb.config, "rope_theta") and mb.config.rope_theta else 10000.0) ** (
+                torch.arange(0, hd, 2, dtype=torch.int64).float() / hd)
+            mod.inv_freq = inv
+            mod.original_inv_freq = inv.clone()
+    mb.train()
+    mb.zero_grad(set_to_none=True)
+    inner_forward = mb.forward
+
+    def forward_upcast(*a, **kw):
+        out = inner_forward(*a, **kw)
+        out.logits = out.logits.float()
+        return out
+
+    mb.forward = forward_upcast
+    d = dict(data)
+    d["images"] = data["images"].to(torch.bfloat16)
+    with torch.no_grad():
+        imgs2 = torch.cat([d["images"], d["images"]], 0)
+        _, _, _, _, emb, new_labels = mb.prepare_inputs_labels_for_multimodal(
+            input_ids=data["concatenated_input_ids"].clone(), position_ids=None, attention_mask=None,
+            past_key_values=None, labels=data["concatenated_labels"].clone(), images=imgs2)
+        logits = mb.forward(inputs_embeds=emb, labels=None).logits
+        per_tok, _, _ = R["get_batch_logps"](logits, new_labels, return_all=True)
+        feats = mb.get_model().get_vision_tower()(d["images"])
+        proj = mb.get_model().mm_projector(feats)
+    pw, pr, rw, rr, beta = R["get_beta_and_logps"](d, mb, Args(), is_llava15=True)
+    losses, cr, rj = R["dpo_loss"](pw, pr, rw, rr, beta=beta)
+    loss = losses.mean()
+    loss.backward()
+    grads = {k: v.grad.detach().float().clone() for k, v in mb.named_parameters() if v.grad is not None}
+    return dict(per_token_logps=per_tok.float(), policy_win_logp=pw.detach().float(), policy_rej_logp=pr.detach().float(),
+                losses=losses.detach().float(), chosen_rewards=cr.float(), rejected_rewards=rj.float(),
+                loss=float(loss), grads=grads, clip_features=feats.float(), projected_rows=proj.float())
 
 
 CASES = {
@@ -159,12 +166,16 @@ def main():
                 labels=keep_labels, images=torch.cat([data["images"], data["images"]], 0))
             ref_logits = model.forward(inputs_embeds=ref_embeds, labels=None).logits.float()
             ref_per_tok, _, _ = R["get_batch_logps"](ref_logits, ref_new_labels, return_all=True)
+            ref_feats = model.get_model().get_vision_tower()(data["images"])        # clip_encoder.py:46-58
+            ref_proj = model.get_model().mm_projector(ref_feats)                    # llava_arch.py:147
         pw, pr, rw, rr, beta = R["get_beta_and_logps"](dict(data), model, Args(), is_llava15=True)
         losses, cr, rj = R["dpo_loss"](pw, pr, rw, rr, beta=beta)
         loss = losses.mean()
         loss.backward()
         ref_grads = {k: v.grad.detach().clone() for k, v in model.named_parameters() if v.grad is not None}
         assert all("vision_tower" not in k for k in ref_grads), "CLIP must stay frozen"
+        model.zero_grad(set_to_none=True)
+        rb = reference_bf16_run(R, model, data, Args)       # the same unmodified reference, bf16 as shipped
         # --- oracle ---
         op = {k: v.clone().requires_grad_(k.startswith(O.TRAINABLE_PREFIXES)) for k, v in params.items()}
         ob = dict(batch, ref_win_logp=ref["ref_win_logp"], ref_rej_logp=ref["ref_rej_logp"])
@@ -207,13 +218,27 @@ def main():
             per_token_logps=ref_per_tok.numpy(), policy_win_logp=pw.detach().numpy(),
             policy_rej_logp=pr.detach().numpy(), losses=losses.detach().numpy(),
             chosen_rewards=cr.numpy(), rejected_rewards=rj.numpy(), loss=np.float64(float(loss)),
+            clip_features=ref_feats.numpy(), projected_rows=ref_proj.detach().numpy(),
+            # the reference run in bf16 (model.bfloat16(), bf16 images, fp32 logits) — reference_bf16_run
+            bf16_per_token_logps=rb["per_token_logps"].numpy(), bf16_policy_win_logp=rb["policy_win_logp"].numpy(),
+            bf16_policy_rej_logp=rb["policy_rej_logp"].numpy(), bf16_losses=rb["losses"].numpy(),
+            bf16_chosen_rewards=rb["chosen_rewards"].numpy(), bf16_rejected_rewards=rb["rejected_rewards"].numpy(),
+            bf16_loss=np.float64(rb["loss"]), bf16_clip_features=rb["clip_features"].numpy(),
+            bf16_projected_rows=rb["projected_rows"].numpy(),
         )
+        ref32 = torch.cat([pw.detach(), pr.detach()])
+        refbf = torch.cat([rb["policy_win_logp"], rb["policy_rej_logp"]])
+        print(f"    reference bf16 vs fp32: summed logp {rel(refbf, ref32):.2e}, loss {abs(rb['loss'] - float(loss)) / abs(float(loss)):.2e}")
         for k in gsel:
             gk = ref_grads[k]
             fx["gradnorm:" + k] = np.float64(float(gk.double().norm()))
             flat = gk.flatten()
             idx = torch.linspace(0, flat.numel() - 1, 64).long()
             fx["gradsample:" + k] = flat[idx].numpy()
+            gb = rb["grads"][k]
+            fx["bf16_gradnorm:" + k] = np.float64(float(gb.double().norm()))
+            fx["bf16_gradsample:" + k] = gb.flatten()[idx].numpy()
+            fx["bf16_gradrelerr:" + k] = np.float64(float((gb.double() - gk.double()).norm() / gk.double().norm()))
         np.savez_compressed(os.path.join(out_dir, name + ".npz"), **fx)
     # ---- collator fixture: the reference's DataCollatorForDPODataset on pairs that share edits ----
     g = torch.Generator().manual_seed(77)

@@ -86,60 +86,66 @@ CONFIGS = {"TINY": TINY, "TINY_GQA": TINY_GQA}
 # deterministic synthetic parameters (shared by the golden generator, the oracle tests and the GPU
 # parity tests so that no weight file has to be committed)
 # ------------------------------------------------------------------------------------------------
-def make_params(cfg: OracleConfig, seed: int = 0, std: float = 0.02, dtype=torch.float32, scale: float = 1.0):
-    """`scale` multiplies every random matrix's std (scale < 1 gives cooler logits, i.e. less bf16 noise)."""
+def iter_params(cfg: OracleConfig, seed: int = 0, std: float = 0.02, dtype=torch.float32, scale: float = 1.0):
+    """Yields (HF name, tensor) in a fixed order from ONE seeded generator, so a consumer can stream a 7B-sized
+    model to the GPU tensor by tensor (tests/test_gpu_config_a.py) and still get exactly make_params' values.
+    `scale` multiplies every random matrix's std (scale < 1 gives cooler logits, i.e. less bf16 noise)."""
     g = torch.Generator().manual_seed(seed)
-    p = {}
 
     def rnd(name, *shape, s=std):
-        p[name] = (torch.randn(*shape, generator=g) * (s * scale)).to(dtype)
+        t = torch.randn(*shape, generator=g)
+        t.mul_(s * scale)                      # in place: one fresh allocation per tensor (same fp32 product)
+        return name, t.to(dtype)
 
     def ones_ish(name, n):
-        p[name] = (1.0 + 0.1 * torch.randn(n, generator=g)).to(dtype)
+        return name, (1.0 + 0.1 * torch.randn(n, generator=g)).to(dtype)
 
     H, F_, V = cfg.hidden_size, cfg.intermediate_size, cfg.vocab_size
-    rnd("model.embed_tokens.weight", V, H)
+    yield rnd("model.embed_tokens.weight", V, H)
     for i in range(cfg.num_layers):
         pre = f"model.layers.{i}."
         Hkv = cfg.kv_heads * cfg.head_dim
-        rnd(pre + "self_attn.q_proj.weight", H, H, s=0.05)
-        rnd(pre + "self_attn.k_proj.weight", Hkv, H, s=0.05)
-        rnd(pre + "self_attn.v_proj.weight", Hkv, H, s=0.05)
-        rnd(pre + "self_attn.o_proj.weight", H, H, s=0.05)
-        rnd(pre + "mlp.gate_proj.weight", F_, H, s=0.05)
-        rnd(pre + "mlp.up_proj.weight", F_, H, s=0.05)
-        rnd(pre + "mlp.down_proj.weight", H, F_, s=0.05)
-        ones_ish(pre + "input_layernorm.weight", H)
-        ones_ish(pre + "post_attention_layernorm.weight", H)
-    ones_ish("model.norm.weight", H)
-    rnd("lm_head.weight", V, H, s=0.05)
+        yield rnd(pre + "self_attn.q_proj.weight", H, H, s=0.05)
+        yield rnd(pre + "self_attn.k_proj.weight", Hkv, H, s=0.05)
+        yield rnd(pre + "self_attn.v_proj.weight", Hkv, H, s=0.05)
+        yield rnd(pre + "self_attn.o_proj.weight", H, H, s=0.05)
+        yield rnd(pre + "mlp.gate_proj.weight", F_, H, s=0.05)
+        yield rnd(pre + "mlp.up_proj.weight", F_, H, s=0.05)
+        yield rnd(pre + "mlp.down_proj.weight", H, F_, s=0.05)
+        yield ones_ish(pre + "input_layernorm.weight", H)
+        yield ones_ish(pre + "post_attention_layernorm.weight", H)
+    yield ones_ish("model.norm.weight", H)
+    yield rnd("lm_head.weight", V, H, s=0.05)
     C = cfg.clip_hidden
-    rnd("model.mm_projector.0.weight", H, C, s=0.05)
-    rnd("model.mm_projector.0.bias", H)
-    rnd("model.mm_projector.2.weight", H, H, s=0.05)
-    rnd("model.mm_projector.2.bias", H)
+    yield rnd("model.mm_projector.0.weight", H, C, s=0.05)
+    yield rnd("model.mm_projector.0.bias", H)
+    yield rnd("model.mm_projector.2.weight", H, H, s=0.05)
+    yield rnd("model.mm_projector.2.bias", H)
     vp = "model.vision_tower.vision_tower.vision_model."
-    rnd(vp + "embeddings.class_embedding", C, s=0.5)
-    rnd(vp + "embeddings.patch_embedding.weight", C, 3, cfg.patch_size, cfg.patch_size, s=0.05)
-    rnd(vp + "embeddings.position_embedding.weight", cfg.num_patches + 1, C, s=0.1)
-    ones_ish(vp + "pre_layrnorm.weight", C)
-    rnd(vp + "pre_layrnorm.bias", C)
+    yield rnd(vp + "embeddings.class_embedding", C, s=0.5)
+    yield rnd(vp + "embeddings.patch_embedding.weight", C, 3, cfg.patch_size, cfg.patch_size, s=0.05)
+    yield rnd(vp + "embeddings.position_embedding.weight", cfg.num_patches + 1, C, s=0.1)
+    yield ones_ish(vp + "pre_layrnorm.weight", C)
+    yield rnd(vp + "pre_layrnorm.bias", C)
     for i in range(cfg.clip_layers):
         pre = vp + f"encoder.layers.{i}."
         for nm in ("q_proj", "k_proj", "v_proj", "out_proj"):
-            rnd(pre + f"self_attn.{nm}.weight", C, C, s=0.08)
-            rnd(pre + f"self_attn.{nm}.bias", C)
-        rnd(pre + "mlp.fc1.weight", cfg.clip_intermediate, C, s=0.08)
-        rnd(pre + "mlp.fc1.bias", cfg.clip_intermediate)
-        rnd(pre + "mlp.fc2.weight", C, cfg.clip_intermediate, s=0.08)
-        rnd(pre + "mlp.fc2.bias", C)
-        ones_ish(pre + "layer_norm1.weight", C)
-        rnd(pre + "layer_norm1.bias", C)
-        ones_ish(pre + "layer_norm2.weight", C)
-        rnd(pre + "layer_norm2.bias", C)
-    ones_ish(vp + "post_layernorm.weight", C)   # unused by the path (select_layer=-2); kept for HF load
-    rnd(vp + "post_layernorm.bias", C)
-    return p
+            yield rnd(pre + f"self_attn.{nm}.weight", C, C, s=0.08)
+            yield rnd(pre + f"self_attn.{nm}.bias", C)
+        yield rnd(pre + "mlp.fc1.weight", cfg.clip_intermediate, C, s=0.08)
+        yield rnd(pre + "mlp.fc1.bias", cfg.clip_intermediate)
+        yield rnd(pre + "mlp.fc2.weight", C, cfg.clip_intermediate, s=0.08)
+        yield rnd(pre + "mlp.fc2.bias", C)
+        yield ones_ish(pre + "layer_norm1.weight", C)
+        yield rnd(pre + "layer_norm1.bias", C)
+        yield ones_ish(pre + "layer_norm2.weight", C)
+        yield rnd(pre + "layer_norm2.bias", C)
+    yield ones_ish(vp + "post_layernorm.weight", C)   # unused by the path (select_layer=-2); kept for HF load
+    yield rnd(vp + "post_layernorm.bias", C)
+
+
+def make_params(cfg: OracleConfig, seed: int = 0, std: float = 0.02, dtype=torch.float32, scale: float = 1.0):
+    return dict(iter_params(cfg, seed, std, dtype, scale))
 
 
 def params_checksum(p):
@@ -313,8 +319,10 @@ def lora_linear(p, name, x, lora_scaling, x_adapter=None):
     """y = W x (+ (alpha/r) * B(A(x))) — peft 0.10.0 lora.Linear.forward with dropout p=0
     (muffin/train/train_llava15_lora.py:304-318: r=64, alpha=16; adapters live next to the base
     weight as `<name>.lora_A.weight` [r,in] / `<name>.lora_B.weight` [out,r]).
-    PARITY NOTE: peft is not installed in the build container, so this branch is a restatement of the
-    published formula and is NOT pinned against a run of the reference."""
+    PARITY: peft itself is not installed in the build container, but at dropout 0 the adapter is an exact
+    reparametrisation of the base model (W' = W + s B A), so this branch is PINNED against the unmodified reference
+    model run with merged weights — forward, losses and, through dL/dA = s B^T dL/dW', dL/dB = s dL/dW' A^T, every
+    adapter gradient (oracle/gen_golden_lora.py, worst relative error 2e-6; fixtures tests/golden/lora/)."""
     y = F.linear(x, p[name + ".weight"])
     a = p.get(name + ".lora_A.weight")
     if a is not None:

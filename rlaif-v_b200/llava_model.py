@@ -53,9 +53,8 @@ class LlavaLlamaForCausalLM:
         return self.policy.clip
 
     def state_dict(self):
-        if self.policy.param_ready is not None:          # pending ZeRO-2 parameter all-gathers
-            for b in self.policy.store.buckets:
-                self.policy.param_ready(b.name)
+        for b in self.policy.store.buckets:              # pending ZeRO-2 parameter all-gathers
+            self.policy._need(b.name)
         return {k: v for k, v in self.policy.store.hf_views().items()}
 
     def load_state_dict(self, state, strict=True):

@@ -553,7 +553,7 @@ class LlavaDPOPolicy:
         scale = hd ** -0.5
         keep_stash = st is not None
         for i in range(d.num_layers):
-            self._need("layer%d" % i)
+            self._need(self.layer_bucket_name(i))
             ls = None
             if keep_stash:
                 ls = {"x": x}
@@ -749,8 +749,13 @@ class LlavaDPOPolicy:
     param_ready = None          # callable(bucket_name): wait for that bucket's parameter all-gather (ZeRO-2)
 
     def _need(self, bucket):
-        if self.param_ready is not None:
-            self.param_ready(bucket)
+        """Order the current stream after `bucket`'s ZeRO-2 parameter all-gather. Frozen buckets (LoRA: embed / head /
+        base layers) are not the optimizer's and need no wait; an unknown trainable name is a bug and raises."""
+        if self.param_ready is None:
+            return
+        if self.lora is not None and not (bucket.startswith("lora") or bucket in ("projector", "resampler")):
+            return
+        self.param_ready(bucket)
 
     def finalize_embed_grad(self):
         """fp32 embedding-row accumulator -> bf16 flat gradient (once per optimizer step)."""

@@ -165,14 +165,49 @@ def init_distributed():
     return int(os.environ.get("LOCAL_RANK", "0"))
 
 
+def dims_from_checkpoint(model_dir, vision_tower_dir, select_layer, max_len):
+    """LlavaDims from the checkpoint's config.json (+ the CLIP directory's config.json) — what
+    `LlavaLlamaForCausalLM.from_pretrained` / `CLIPVisionModel.from_pretrained` read in the reference
+    (muffin/train/train_llava15.py:206-214, llava/model/multimodal_encoder/clip_encoder.py:25-34).
+    Missing files / keys fall back to the LLaVA-1.5-7B + CLIP-ViT-L/14-336 defaults."""
+    from .model import LlavaDims
+    kw = dict(select_layer=select_layer, max_len=max_len)
+
+    def read(d):
+        p = os.path.join(d, "config.json") if d and os.path.isdir(d) else None
+        if p and os.path.exists(p):
+            with open(p) as f:
+                return json.load(f)
+        return {}
+    c = read(model_dir)
+    for src, dst in (("vocab_size", "vocab_size"), ("hidden_size", "hidden_size"),
+                     ("intermediate_size", "intermediate_size"), ("num_hidden_layers", "num_layers"),
+                     ("num_attention_heads", "num_heads"), ("rms_norm_eps", "rms_eps"), ("rope_theta", "rope_theta")):
+        if c.get(src) is not None:
+            kw[dst] = c[src]
+    if c.get("num_key_value_heads") and c["num_key_value_heads"] != c.get("num_attention_heads"):
+        kw["num_kv_heads"] = c["num_key_value_heads"]
+    v = read(vision_tower_dir)
+    v = v.get("vision_config", v)
+    for src, dst in (("hidden_size", "clip_hidden"), ("intermediate_size", "clip_intermediate"),
+                     ("num_hidden_layers", "clip_layers"), ("num_attention_heads", "clip_heads"),
+                     ("image_size", "image_size"), ("patch_size", "patch_size"), ("layer_norm_eps", "clip_eps")):
+        if v.get(src) is not None:
+            kw[dst] = v[src]
+    return LlavaDims(**kw)
+
+
 def init_model(model_args, data_args, training_args, attn_implementation=None):
     """muffin/train/train_llava15.py:198-281: policy model (+ frozen reference used once for the
     log-prob pre-pass inside the dataset), tokenizer, data module."""
     from .llava_model import LlavaLlamaForCausalLM
     from .model import LlavaDims
     from .data import make_dpo_data_module, load_tokenizer, load_hf_checkpoint
+    from .image_processing import ClipImageProcessor, PixelValues
     local_rank = init_distributed()
-    dims = LlavaDims(select_layer=model_args.mm_vision_select_layer, max_len=training_args.model_max_length)
+    dims = dims_from_checkpoint(model_args.model_name_or_path, model_args.vision_tower,
+                                select_layer=model_args.mm_vision_select_layer,
+                                max_len=training_args.model_max_length)
     state = load_hf_checkpoint(model_args.model_name_or_path, model_args.vision_tower)
     model = LlavaLlamaForCausalLM(dims, torch.device("cuda", local_rank), hf_state=state)
     model.config.use_cache = False
@@ -187,6 +222,9 @@ def init_model(model_args, data_args, training_args, attn_implementation=None):
     tokenizer = load_tokenizer(model_args.model_name_or_path, training_args.model_max_length)
     data_args.is_multimodal = True
     data_args.image_token_len = dims.num_patches
+    # muffin/train/train_llava15.py:244: `lambda x: vision_tower.image_processor(x)['pixel_values'][0]`
+    data_args.image_processor = PixelValues(ClipImageProcessor.from_pretrained(model_args.vision_tower,
+                                                                               dims.image_size))
     data_module = make_dpo_data_module(tokenizer=tokenizer, data_args=data_args, reference_model=model)
     return model, data_module, tokenizer
 
@@ -199,6 +237,11 @@ def train(attn_implementation=None, argv=None):
         data_args.eval_data_source_names = data_args.eval_data_source_names.split("#")
     if zero_stage(training_args.deepspeed) not in (0, 2):
         raise NotImplementedError("only ZeRO stage 2 (script/zero2.json) is implemented natively")
+    if training_args.gradient_accumulation_steps != 1:
+        # the shipped recipes use 1 (script/train/llava15_train.sh:33); inside one step the engine's own
+        # --micro_pairs splits the per-device batch with gradient accumulation in the wgrad epilogues
+        raise NotImplementedError("gradient_accumulation_steps=%d: use --micro_pairs to split the per-device batch"
+                                  % training_args.gradient_accumulation_steps)
     model, data_module, tokenizer = init_model(model_args, data_args, training_args, attn_implementation)
     if training_args.task != "DPO":
         raise NotImplementedError

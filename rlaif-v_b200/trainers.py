@@ -282,9 +282,13 @@ class LLaVA15DPOTrainer:
                                            pin_memory=True)
 
     def _steps_per_epoch(self):
+        """Batches one epoch's loader yields on this rank: DistributedSampler (drop_last=False) pads every rank to
+        ceil(len / world) samples, the DataLoader then drops the ragged last batch."""
         if not hasattr(self.train_dataset, "__len__"):
             return 1 << 60
-        n = len(self.train_dataset) // max(1, self.world)
+        n = len(self.train_dataset)
+        if self.world > 1:
+            n = -(-n // self.world)
         return n // self.args.per_device_train_batch_size
 
     def train(self, resume_from_checkpoint=None):
@@ -294,6 +298,12 @@ class LLaVA15DPOTrainer:
         self.model.train()
         step = self.state["global_step"]
         self.engine.global_step = step
+        pol = self.model.policy
+        if pol.lora is not None:
+            # LoRA dropout streams are a function of (optimisation step, forward count): restore both so a resumed
+            # run draws the masks the uninterrupted run would have drawn
+            pol.lora.step = step
+            pol._fwd_count = self.state.get("fwd_count", pol._fwd_count)
         t0 = time.time()
         while step < a.max_steps:
             loader = self._dataloader(epoch=step // max(1, self._steps_per_epoch()))
@@ -304,9 +314,10 @@ class LLaVA15DPOTrainer:
                 m = self.training_step(self.model, batch)
                 step += 1
                 self.state["global_step"] = step
+                self.state["fwd_count"] = self.model.policy._fwd_count
                 if a.logging_steps and step % a.logging_steps == 0:
                     logs = self.engine.metrics_dict(m)
-                    logs["learning_rate"] = self.engine.opt.lr if self.engine.constant_lr else None
+                    logs["learning_rate"] = self.engine.opt._lr       # the rate begin_step() was given this step
                     logs["elapsed_s"] = time.time() - t0
                     self.log(logs)
                 if getattr(a, "save_strategy", "no") == "steps" and a.save_steps and step % a.save_steps == 0:
@@ -372,12 +383,18 @@ class LLaVA15DPOTrainer:
                 json.dump(self.state, f)
 
     def _save_checkpoint(self, path):
+        # every rank writes its optimizer shard: the tail buckets' reduce-scatter wait / AdamW / all-gather of the
+        # last step may still be queued on the optimizer side stream — drain them first on ALL ranks
+        self.engine.opt.wait_all()
+        torch.cuda.synchronize()
         os.makedirs(path, exist_ok=True)
         if self.args.should_save:
             self._save(path)
             with open(os.path.join(path, "trainer_state.json"), "w") as f:
                 json.dump(self.state, f)
         torch.save(self.engine.opt.state_dict(), os.path.join(path, f"optimizer_rank{self.rank}.pt"))
+        if self.world > 1:
+            dist.barrier()        # pruning / a resume must never see a half-written checkpoint
         limit = getattr(self.args, "save_total_limit", None)
         if limit and self.args.should_save:
             ck = sorted(glob.glob(os.path.join(self.args.output_dir, "checkpoint-*")),

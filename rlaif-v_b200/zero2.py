@@ -172,7 +172,10 @@ class Zero2AdamW:
     def wait_bucket(self, bucket_index):
         """Make the current stream wait for bucket's parameter all-gather of the last step (no-op if none)."""
         if isinstance(bucket_index, str):
-            bucket_index = self.index.get(bucket_index, -1)
+            if bucket_index not in self.index:
+                raise KeyError("wait_bucket: %r is not a bucket of this optimizer (%s ...)"
+                               % (bucket_index, ", ".join(list(self.index)[:4])))
+            bucket_index = self.index[bucket_index]
         ev = self._gathered.pop(bucket_index, None)
         if ev is not None:
             torch.cuda.current_stream().wait_event(ev)

@@ -51,6 +51,20 @@ def test_thread_calibration(bench_mod):
     assert 1 <= t <= n and torch.get_num_threads() == t
 
 
+def test_reference_arm_step_functions_run_at_tiny_dims(bench_mod):
+    """Both step functions of the CPU arm (the staged unmodified reference, and the oracle-port fallback) complete an
+    optimisation step; the reference one only where oracle/_ref has been staged (build() does it in the build
+    container, the copy travels to the GPU box)."""
+    from oracle import llava_dpo_oracle as O
+    from oracle import stage_ref
+    if stage_ref.available():
+        fn = bench_mod._reference_step_fn(2, cfg=O.TINY)
+        l0, l1 = fn(), fn()
+        assert l0 == l0 and l1 == l1 and l0 != l1            # finite, and the AdamW step changed the model
+        ts = bench_mod._time_cpu_steps(fn, 1, 2)
+        assert len(ts) == 2 and all(t > 0 for t in ts)
+
+
 def test_reference_arm_other_ranks_exit_quietly():
     """Under torchrun only rank 0 runs the CPU reference arm; the other ranks exit 0 without output."""
     env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")

@@ -1,6 +1,11 @@
 """-m gpu: LoRA-DPO path (BASELINE config e) — adapters on q,k,v,o,gate,up,down, base frozen, projector
-trainable — against the oracle's restatement of peft's `W x + (alpha/r) B(A(x))` (dropout 0).
-Parity note: peft is absent in the build container, so this branch of the oracle is unpinned."""
+trainable — against the oracle's restatement of peft's `W x + (alpha/r) B(A(x))` (dropout 0) and against fixtures of the
+UNMODIFIED reference model run with merged weights W' = W + s B A (tests/golden/lora/, oracle/gen_golden_lora.py:
+log-probs, losses and — via dA = s B^T dW', dB = s dW' A^T — every adapter gradient)."""
+import glob
+import os
+
+import numpy as np
 import pytest
 import torch
 
@@ -201,3 +206,60 @@ def test_lora_trainer_checkpoint_layout_and_resume(tmp_path):
     # same data order, same optimizer state => same adapters (fp32 atomics in the backward may flip a last bit)
     assert float((m_res.policy.lora.flat == want).float().mean()) > 0.99
     assert float((m_res.policy.store.flat == m_full.policy.store.flat).float().mean()) > 0.999
+
+
+LORA_GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "lora", "*.npz")))
+
+
+@pytest.mark.parametrize("path", LORA_GOLDEN, ids=[os.path.basename(p) for p in LORA_GOLDEN])
+def test_lora_matches_merged_weight_reference_fixture(path):
+    """CUDA LoRA path vs the reference fixture: summed log-probs 1e-3 (north_star), losses, rewards, gradient norms of
+    all 28 adapter matrices + the projector within 3 %, gradient samples within 6 % of the tensor's max."""
+    from rlaifv_b200 import ops
+    from rlaifv_b200.model import LlavaDims, LlavaDPOPolicy
+    fx = np.load(path)
+    c = O.TINY
+    dims = LlavaDims(vocab_size=c.vocab_size, hidden_size=c.hidden_size, intermediate_size=c.intermediate_size,
+                     num_layers=c.num_layers, num_heads=c.num_heads, clip_hidden=c.clip_hidden,
+                     clip_intermediate=c.clip_intermediate, clip_layers=c.clip_layers, clip_heads=c.clip_heads,
+                     image_size=c.image_size, patch_size=c.patch_size)
+    params = O.make_params(c, seed=0, scale=float(fx["param_scale"]))
+    lora = O.make_lora_params(c, r=int(fx["r"]), seed=int(fx["lora_seed"]), b_std=float(fx["lora_b_std"]))
+    assert abs(O.params_checksum(lora) - float(fx["lora_checksum"])) <= 1e-9 * float(fx["lora_checksum"])
+    pol = LlavaDPOPolicy(dims, "cuda", hf_state=params)
+    pol.enable_lora(r=int(fx["r"]), alpha=float(fx["alpha"])).load_hf(lora)
+    ids, labels = torch.from_numpy(fx["concatenated_input_ids"]), torch.from_numpy(fx["concatenated_labels"])
+    out = pol.forward_logps(ids, labels, torch.from_numpy(fx["images"]), keep_stash=True)
+    B = int(fx["B"])
+    assert torch.equal(out["labels"].cpu(), torch.from_numpy(fx["spliced_labels"]))
+    ref = torch.cat([torch.from_numpy(fx["policy_win_logp"]), torch.from_numpy(fx["policy_rej_logp"])])
+    e_sum = rel(out["logp"], ref)
+    losses, cr, rj, dpw, dpr, out9 = ops.dpo_loss(out["logp"][:B].contiguous(), out["logp"][B:].contiguous(),
+                                                  torch.from_numpy(fx["ref_win_logp"]).cuda(),
+                                                  torch.from_numpy(fx["ref_rej_logp"]).cuda(), float(fx["beta"]))
+    pol.store.grad.zero_()
+    pol.lora.grad.zero_()
+    pol.backward_logps(torch.cat([dpw, dpr]).contiguous())
+    torch.cuda.synchronize()
+    e_loss = rel(losses, fx["losses"])
+    print(f"summed logp rel err vs merged-weight reference {e_sum:.2e}; losses {e_loss:.2e}")
+    assert e_sum <= 1e-3
+    assert e_loss <= 5e-3
+    assert rel(cr, fx["chosen_rewards"]) <= 5e-3
+    gl = dict(pol.lora.hf_views(grads=True))
+    gl.update({k: v for k, v in pol.store.hf_grad_views().items() if "mm_projector" in k})
+    worst_n = worst_s = 0.0
+    for key in fx.files:
+        if not key.startswith("gradsample:"):
+            continue
+        name = key.split(":", 1)[1]
+        g = gl[name].float().flatten().cpu()
+        idx = torch.linspace(0, g.numel() - 1, 64).long()
+        refs = torch.from_numpy(fx[key])
+        gn = float(fx["gradnorm:" + name])
+        en = abs(float(g.double().norm()) - gn) / gn
+        es = float((g[idx] - refs).abs().max()) / (float(refs.abs().max()) + 1e-12)
+        worst_n, worst_s = max(worst_n, en), max(worst_s, es)
+        assert en <= 3e-2, (name, en)
+        assert es <= 6e-2, (name, es)
+    print(f"adapter + projector gradients: worst norm err {worst_n:.2e}, worst sample err {worst_s:.2e}")

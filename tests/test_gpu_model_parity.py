@@ -1,10 +1,17 @@
 """-m gpu parity tests: the CUDA path (through the C ABI) vs the oracle and the golden fixtures that
 were produced by the unmodified reference (oracle/gen_golden.py).
 
-Tolerances: index work bit-exact; per-token / summed logps and DPO loss <= 1e-3
-relative vs the bf16-op-order oracle and the fp32 reference fixture at <= 5e-3 (the fixture is
-fp32 math, the CUDA path is bf16 storage: bf16 has 8 bits of mantissa, so fp32-vs-bf16 agreement is
-bounded by the reference's own bf16 rounding, not by the kernels).
+The fixtures hold the outputs of the unmodified reference twice: in fp32, and AS SHIPPED — `model.bfloat16()`, bf16
+images, fp32 logits (gen_golden.reference_bf16_run; keys `bf16_*`).  The bf16-op-order oracle reproduces that bf16
+reference run bit-for-bit on the ragged fixtures, so it is a pinned yardstick, not a guess.
+
+Tolerances (north_star: "within 1e-3 relative in bf16 vs the reference HF path, bit-exact for token-index gathers"):
+  splice labels                              bit-exact
+  summed log-probs vs the bf16 reference     <= 1e-3   (and vs the bf16-order oracle; vs fp32: the reference's own gap)
+  DPO losses vs the bf16 reference           <= 1e-3 of max(|loss|) on the realistically scaled fixtures
+  per-token log-probs                        within 2.5x of the reference's OWN bf16-vs-fp32 gap, never worse than 1e-2
+  CLIP features / projected image rows       vs the bf16 reference (mean abs error <= 2e-3 of the mean magnitude)
+  gradients                                  norm within 1e-2, samples within 2.5x of the reference's own bf16-vs-fp32 gap
 """
 import glob
 import os
@@ -78,6 +85,12 @@ def test_forward_matches_reference_fixture(path):
     print(f"summed logp rel err: cuda-vs-fp32ref {e_sum_ref:.2e}, cuda-vs-bf16oracle {e_sum_orc:.2e}, "
           f"inherent {inherent_sum:.2e}")
     assert e_sum_orc <= 1e-3
+    # the reference as shipped (model.bfloat16(), fp32 logits): north_star's 1e-3 on the summed log-probs
+    ref_bf16 = torch.cat([torch.from_numpy(fx["bf16_policy_win_logp"]), torch.from_numpy(fx["bf16_policy_rej_logp"])])
+    e_sum_bf = rel(logp, ref_bf16)
+    print(f"summed logp rel err vs the bf16 reference run {e_sum_bf:.2e} (bf16-order oracle vs that run "
+          f"{rel(ob['logp'], ref_bf16):.2e})")
+    assert e_sum_bf <= 1e-3
     if float(fx["param_scale"]) < 1.0:
         assert e_sum_ref <= 1e-3                   # strict gate on realistically scaled logits
     else:
@@ -96,6 +109,35 @@ def test_forward_matches_reference_fixture(path):
           f"bf16oracle-vs-fp32ref (inherent) {inherent:.2e}")
     assert e_ref <= max(1e-3, 2.5 * inherent) and e_ref <= 1e-2
     assert e_orc <= max(1e-3, 2.5 * inherent) and e_orc <= 1e-2
+    bf_pt = torch.from_numpy(fx["bf16_per_token_logps"])
+    e_bf = rel(pt[mask], bf_pt[mask])
+    print(f"per-token rel err vs the bf16 reference run {e_bf:.2e}; mean abs {float((pt[mask] - bf_pt[mask]).abs().mean()):.2e}")
+    assert e_bf <= max(1e-3, 2.5 * inherent) and e_bf <= 1e-2
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_clip_features_and_projected_rows_match_reference_fixture(path):
+    """SURVEY §8 a3 / a4 on their own: CLIP tower output (layer -2, CLS dropped) and mm_projector rows against the
+    reference's `get_vision_tower()(images)` / `mm_projector(...)` (clip_encoder.py:46-58, llava_arch.py:141-148)."""
+    fx = np.load(path)
+    cfg = cfg_of(fx)
+    pol, params = policy_for(float(fx["param_scale"]), cfg)
+    images = torch.from_numpy(fx["images"])
+    feats = pol.encode_images(images).float().cpu()
+    proj = pol._frontend_fwd(images, None).float().cpu()
+    torch.cuda.synchronize()
+    for got, key in ((feats, "clip_features"), (proj, "projected_rows")):
+        ref_bf = torch.from_numpy(fx["bf16_" + key]).reshape(got.shape)
+        ref_32 = torch.from_numpy(fx[key]).reshape(got.shape)
+        own = float((ref_bf - ref_32).abs().mean() / ref_32.abs().mean())      # the reference's bf16-vs-fp32 gap
+        e_bf = float((got - ref_bf).abs().mean() / ref_bf.abs().mean())
+        e_32 = float((got - ref_32).abs().mean() / ref_32.abs().mean())
+        e_max = rel(got, ref_bf)
+        print(f"{key}: mean-abs rel err vs bf16 reference {e_bf:.2e} (max {e_max:.2e}), vs fp32 {e_32:.2e}; "
+              f"reference bf16-vs-fp32 {own:.2e}")
+        assert e_bf <= 2e-3
+        assert e_32 <= 2.0 * max(own, 1e-3)
+        assert e_max <= 3e-2
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
@@ -115,9 +157,21 @@ def test_dpo_loss_and_grads_match_reference_fixture(path):
     pol.backward_logps(torch.cat([dpw, dpr]).contiguous())
     pol.finalize_embed_grad()
     torch.cuda.synchronize()
-    assert rel(losses, fx["losses"]) <= 2e-2          # loss depends on a difference of logps: looser
-    assert rel(out9[0], fx["loss"]) <= 2e-2
-    assert rel(cr, fx["chosen_rewards"]) <= 5e-3
+    # DPO loss against the reference run in bf16 (as shipped). The loss is -logsigmoid(beta * (difference of summed
+    # log-probs)): on the realistically scaled ("cool") fixtures the 1e-3 of north_star holds; on the hot random
+    # networks (scale 1.0: logits of std ~10, an ill-conditioned case no checkpoint looks like) the reference's own
+    # two evaluation orders already disagree by more, so the gate there is the reference's own bf16-vs-fp32 gap.
+    e_loss_bf = rel(losses, fx["bf16_losses"])
+    e_loss_32 = rel(losses, fx["losses"])
+    own_loss = rel(fx["bf16_losses"], fx["losses"])
+    print(f"DPO losses rel err: vs bf16 reference {e_loss_bf:.2e}, vs fp32 reference {e_loss_32:.2e}; "
+          f"reference bf16-vs-fp32 {own_loss:.2e}")
+    if float(fx["param_scale"]) < 1.0:
+        assert e_loss_bf <= 1e-3
+    else:
+        assert e_loss_bf <= max(1e-3, 1.5 * own_loss)
+    assert e_loss_32 <= max(1e-3, 2.0 * own_loss)
+    assert rel(cr, fx["bf16_chosen_rewards"]) <= 2e-3
     grads = pol.store.hf_grad_views()
     for key in fx.files:
         if not key.startswith("gradsample:"):
@@ -131,6 +185,9 @@ def test_dpo_loss_and_grads_match_reference_fixture(path):
         err = float((got - ref).abs().max())
         scale = float(ref.abs().max()) + 1e-12
         nrm = float(g.double().norm())
-        print(f"{name}: sample max err {err:.3e} (ref max {scale:.3e}); norm {nrm:.4e} vs ref {gn:.4e}")
-        assert abs(nrm - gn) <= 3e-2 * gn, name
-        assert err <= 6e-2 * scale, name
+        own_s = float(np.abs(fx["bf16_gradsample:" + name] - fx[key]).max()) / scale   # reference bf16 vs fp32
+        own_n = abs(float(fx["bf16_gradnorm:" + name]) - gn) / gn
+        print(f"{name}: sample err {err / scale:.2e} (reference's own bf16-vs-fp32 {own_s:.2e}); "
+              f"norm err {abs(nrm - gn) / gn:.2e} (own {own_n:.2e})")
+        assert abs(nrm - gn) <= 1e-2 * gn, name
+        assert err <= max(2.5 * own_s, 2e-2) * scale, name

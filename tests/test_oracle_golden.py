@@ -154,3 +154,40 @@ def test_splice_edge_cases_match_reference_fixture():
         assert np.array_equal(new_labels.numpy(), fx[name + ":ref_labels"]), name            # bit-exact
         assert T <= max_len
         assert np.allclose(emb.double().sum(-1).numpy(), fx[name + ":ref_embeds_rowsum"], rtol=1e-6, atol=1e-6), name
+
+
+LORA_GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "lora", "*.npz")))
+
+
+@pytest.mark.parametrize("path", LORA_GOLDEN, ids=[os.path.basename(p) for p in LORA_GOLDEN])
+def test_lora_oracle_matches_merged_weight_reference(path):
+    """The oracle's LoRA branch (unmerged W x + s B(A x), what peft executes) against the unmodified reference model
+    run with merged weights W' = W + s B A; adapter gradients via dA = s B^T dW', dB = s dW' A^T
+    (oracle/gen_golden_lora.py)."""
+    fx = np.load(path)
+    cfg = O.TINY
+    params = O.make_params(cfg, seed=0, scale=float(fx["param_scale"]))
+    lora = O.make_lora_params(cfg, r=int(fx["r"]), seed=int(fx["lora_seed"]), b_std=float(fx["lora_b_std"]))
+    assert abs(O.params_checksum(lora) - float(fx["lora_checksum"])) <= 1e-9 * float(fx["lora_checksum"])
+    p = {k: v.clone().requires_grad_(k.startswith("model.mm_projector.")) for k, v in params.items()}
+    p.update({k: v.clone().requires_grad_(True) for k, v in lora.items()})
+    batch = dict(concatenated_input_ids=torch.from_numpy(fx["concatenated_input_ids"]),
+                 concatenated_labels=torch.from_numpy(fx["concatenated_labels"]), images=torch.from_numpy(fx["images"]),
+                 ref_win_logp=torch.from_numpy(fx["ref_win_logp"]), ref_rej_logp=torch.from_numpy(fx["ref_rej_logp"]))
+    out = O.dpo_step(p, cfg, batch, beta=float(fx["beta"]))     # lora_scaling default 0.25 = alpha / r of the fixture
+    assert float(fx["alpha"]) / int(fx["r"]) == 0.25
+    assert torch.equal(out["labels"], torch.from_numpy(fx["spliced_labels"]))
+    assert rel(out["per_token_logps"].detach(), fx["per_token_logps"]) < 5e-5
+    assert rel(out["policy_win_logp"].detach(), fx["policy_win_logp"]) < 5e-5
+    assert rel(out["losses"].detach(), fx["losses"]) < 5e-5
+    out["loss"].backward()
+    n = 0
+    for key in fx.files:
+        if key.startswith("gradsample:"):
+            name = key.split(":", 1)[1]
+            g = p[name].grad.flatten()
+            idx = torch.linspace(0, g.numel() - 1, 64).long()
+            assert rel(g[idx], fx[key]) < 1e-4, name
+            assert abs(float(g.double().norm()) - float(fx["gradnorm:" + name])) < 1e-4 * float(fx["gradnorm:" + name])
+            n += 1
+    assert n == 2 * len(O.LORA_TARGETS) * cfg.num_layers + 4

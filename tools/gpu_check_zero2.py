@@ -49,9 +49,29 @@ if rank == 0:
     upd_ref = (b - p0)
     err = (a - b).abs().max().item()
     rel_upd = ((a - b).norm() / (upd_ref.norm() + 1e-12)).item()
-    print("loss dp %.6f single %.6f | max |dW| %.3e, update-relative diff %.3e, update norm %.3e" %
-          (md["loss"], md1["loss"], err, rel_upd, upd_ref.norm().item()), flush=True)
-    ok = abs(md["loss"] - md1["loss"]) <= 1e-3 * max(1.0, abs(md1["loss"])) and rel_upd <= 5e-2 and upd_ref.norm().item() > 0
+    # fp32 MASTER weights of the slices this rank owns vs the same elements of the single-GPU run's master copy.
+    # (The bf16 parameter copies are the wrong thing to compare at 1e-3: one bf16 ulp of a 0.03-sized weight is
+    # 1.2e-4 = 6 % of the 2-step update of 2e-3, so a few rounding-boundary flips dominate `rel_upd` above.)
+    num = den = 0.0
+    for (bk, s0, s1, o), (bk1, t0, t1, o1) in zip(eng.opt.slices, eng1.opt.slices):
+        n = s1 - s0
+        m_dp = eng.opt.master[o:o + n]
+        m_1 = eng1.opt.master[o1 + s0:o1 + s1]           # world=1: the slice covers the whole bucket
+        start = (bk1.flat.data_ptr() - pol1.store.flat.data_ptr()) // 2
+        init = p0[start + s0:start + s1]
+        num += float(((m_dp - m_1).double() ** 2).sum())
+        den += float(((m_1 - init).double() ** 2).sum())
+    rel_master = (num / (den + 1e-300)) ** 0.5
+    print("loss dp %.6f single %.6f | bf16 params: max |dW| %.3e, update-relative diff %.3e | fp32 master shard: "
+          "update-relative diff %.3e (update norm %.3e)" % (md["loss"], md1["loss"], err, rel_upd, rel_master,
+                                                            upd_ref.norm().item()), flush=True)
+    # Bound on the master update: the two runs see gradients that differ by at most one bf16 rounding
+    # (DP: bf16(bf16 g_a + bf16 g_b) from the reduce-scatter; 1 GPU: bf16(fp32 g_b + bf16 g_a) from the accumulating
+    # wgrad epilogue), i.e. <= 2^-8 = 3.9e-3 relative per element, and Adam's update lr*m/(sqrt(v)+eps) is
+    # homogeneous of degree 0 in the gradient scale, so an element-wise relative perturbation d changes it by at
+    # most ~d (mixed signs across the two steps): ||du|| / ||u|| <= 3.9e-3, typically half of that.
+    ok = (abs(md["loss"] - md1["loss"]) <= 1e-3 * max(1.0, abs(md1["loss"])) and rel_master <= 4e-3
+          and upd_ref.norm().item() > 0)
 # all ranks must hold identical parameters after the all-gather
 chk = pol.store.flat.float().clone()
 dist.all_reduce(chk)
