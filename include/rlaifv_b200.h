@@ -175,6 +175,28 @@ int rlaifv_splice_gather(const int* src, const long long* ids, const void* embed
 int rlaifv_splice_scatter(const int* src, const long long* ids, const void* dx, float* d_embed, float* d_feat,
                           int nseq, int L, int T, int H, void* stream);
 int rlaifv_f32_to_bf16(const float* in, void* out, long long n, int accumulate, void* stream);
+/* Strided form: fp32 [rows, cols] (row stride ld_in) -> bf16 column block (row stride ld_out); used where an fp32
+ * atomic accumulator (attention dQ) lands in the q columns of a fused dqkv buffer without RoPE (EVA tower). */
+int rlaifv_f32_to_bf16_2d(const float* in, long long ld_in, void* out, long long ld_out, long long rows, int cols,
+                          int accumulate, void* stream);
+
+/* ---- compact lm_head: only positions whose next token is supervised reach the head -----------------
+ * get_batch_logps (muffin/eval/muffin_inference_logp.py:93-104) multiplies the per-token log-probs by
+ * loss_mask = labels[:, 1:] != -100 before summing, so in TRAINING the final norm, lm_head GEMM (fwd, dgrad, wgrad) and
+ * the log-softmax only need those rows (512 of 1135 per config-(b) sequence). row_pos int32 [nseq*cap]:
+ * row_pos[s*cap + j] = s*T + t of sequence s's j-th supervised position, -1 in unused slots (cap >= labels per row).
+ * rows_gather: out[r] = x[row_pos[r]] (zeros for -1); rows_scatter: dx[row_pos[r]] = dy[r] (dx pre-zeroed).
+ * logp_fwd_rows / logp_bwd_rows: the log-prob gather and its in-place backward on logits [n_rows][ld] of the gathered
+ * rows; per_tok [nseq][T-1] pre-zeroed, lse [n_rows]; token_weight / norm nullable (token-weighted and average modes). */
+int rlaifv_supervised_rows(const long long* labels, int nseq, int T, int cap, int* row_pos, void* stream);
+int rlaifv_rows_gather(const int* row_pos, const void* x, void* out, long long n_rows, int H, void* stream);
+int rlaifv_rows_scatter(const int* row_pos, const void* dy, void* dx, long long n_rows, int H, void* stream);
+int rlaifv_logp_fwd_rows(const void* logits, long long ld, const long long* labels, const int* row_pos, long long n_rows,
+                         int nseq, int T, int V, float* per_tok, float* lse, float* logp_sum, float* logp_avg,
+                         float* count, void* stream);
+int rlaifv_logp_bwd_rows(void* logits, long long ld, const long long* labels, const int* row_pos, long long n_rows,
+                         const float* lse, const float* d_logp, const float* token_weight, const float* norm, int nseq,
+                         int T, int V, void* stream);
 
 /* ---- per-token log-prob gather (muffin/eval/muffin_inference_logp.py:82-115) ---------------------
  * logits bf16 [nseq*T][ld] (upcast to fp32 inside, as pinned transformers 4.35 does), labels = spliced

@@ -740,6 +740,29 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ in, bf16* __restric
   }
 }
 
+// strided variant: rows x cols fp32 (row stride ld_in) -> bf16 column block of a wider buffer (row stride ld_out)
+__global__ void f32_to_bf16_2d_kernel(const float* __restrict__ in, long long ld_in, bf16* __restrict__ out,
+                                      long long ld_out, long long rows, int cols8, int accumulate) {
+  const long long total = rows * cols8;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / cols8;
+    const int c = (int)(idx - r * cols8) * 8;
+    const float* src = in + r * ld_in + c;
+    float4 a = *reinterpret_cast<const float4*>(src);
+    float4 b = *reinterpret_cast<const float4*>(src + 4);
+    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    bf16* dst = out + r * ld_out + c;
+    if (accumulate) {
+      float o[8];
+      load8(dst, o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += o[j];
+    }
+    store8(dst, v);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Per-token log-prob gather (muffin/eval/muffin_inference_logp.py:82-115).
 // Row r = (b, t), t in [0, T-1): label = labels[b][t+1]; mask = label != -100; label(-100) -> 0;
@@ -749,13 +772,27 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ in, bf16* __restric
 constexpr int LOGP_THREADS = 256;
 __global__ void __launch_bounds__(LOGP_THREADS)
 logp_fwd_kernel(const bf16* __restrict__ logits, long long ld, const long long* __restrict__ labels,
-                int nseq, int T, int V, float* __restrict__ per_tok, float* __restrict__ lse_out) {
-  const long long rows = (long long)nseq * (T - 1);
+                int nseq, int T, int V, float* __restrict__ per_tok, float* __restrict__ lse_out,
+                const int* __restrict__ row_pos, long long n_compact) {
+  // row_pos != nullptr: COMPACT head — logits row r belongs to flat position row_pos[r] = b*T + t (t < T-1), or is a
+  // padding slot (-1, skipped); lse_out is then indexed by the compact row. nullptr: dense [nseq*T] logits.
+  const long long rows = row_pos ? n_compact : (long long)nseq * (T - 1);
   __shared__ float sm[32], ss[32];
   for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
-    const int b = (int)(r / (T - 1));
-    const int t = (int)(r % (T - 1));
-    const bf16* lr = logits + ((long long)b * T + t) * ld;
+    int b, t;
+    long long lrow;
+    if (row_pos) {
+      const int pos = row_pos[r];
+      if (pos < 0) continue;          // uniform over the block
+      b = pos / T;
+      t = pos % T;
+      lrow = r;
+    } else {
+      b = (int)(r / (T - 1));
+      t = (int)(r % (T - 1));
+      lrow = (long long)b * T + t;
+    }
+    const bf16* lr = logits + lrow * ld;
     float m = -INFINITY, s = 0.f;
     const int nch = V >> 3;
     for (int c = threadIdx.x; c < nch; c += LOGP_THREADS) {
@@ -801,7 +838,7 @@ logp_fwd_kernel(const bf16* __restrict__ logits, long long ld, const long long* 
         if (lab == IGNORE_INDEX) lab = 0;
         const float z = __bfloat162float(lr[lab]);
         per_tok[(long long)b * (T - 1) + t] = z - lse;
-        lse_out[(long long)b * T + t] = lse;
+        lse_out[row_pos ? r : lrow] = lse;
       }
     }
   }
@@ -888,12 +925,21 @@ __global__ void __launch_bounds__(LOGP_THREADS)
 logp_bwd_weighted_kernel(bf16* __restrict__ logits, long long ld, const long long* __restrict__ labels,
                          const float* __restrict__ lse, const float* __restrict__ d_logp,
                          const float* __restrict__ token_weight, const float* __restrict__ wsum, int nseq, int T,
-                         int V) {
-  const long long rows = (long long)nseq * T;
+                         int V, const int* __restrict__ row_pos, long long n_compact) {
+  // token_weight may be nullptr (plain sum / average: wsum is then the label count); row_pos: compact head (see
+  // logp_fwd_kernel) — logits row r is position row_pos[r], padding slots and unsupervised rows are zeroed.
+  const long long rows = row_pos ? n_compact : (long long)nseq * T;
   const int nch = V >> 3;
   for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
-    const int b = (int)(r / T);
-    const int t = (int)(r % T);
+    int b, t;
+    if (row_pos) {
+      const int pos = row_pos[r];
+      b = pos < 0 ? 0 : pos / T;
+      t = pos < 0 ? T - 1 : pos % T;
+    } else {
+      b = (int)(r / T);
+      t = (int)(r % T);
+    }
     bf16* lr = logits + r * ld;
     long long lab = (t < T - 1) ? labels[(long long)b * T + t + 1] : IGNORE_INDEX;
     if (lab == IGNORE_INDEX) {
@@ -901,7 +947,7 @@ logp_bwd_weighted_kernel(bf16* __restrict__ logits, long long ld, const long lon
         *reinterpret_cast<uint4*>(lr + c * 8) = make_uint4(0, 0, 0, 0);
       continue;
     }
-    float g = d_logp[b] * token_weight[(long long)b * (T - 1) + t];
+    float g = d_logp[b] * (token_weight ? token_weight[(long long)b * (T - 1) + t] : 1.f);
     if (wsum) g /= wsum[b];
     const float l = lse[r];
     for (int c = threadIdx.x; c < nch; c += LOGP_THREADS) {
@@ -914,6 +960,56 @@ logp_bwd_weighted_kernel(bf16* __restrict__ logits, long long ld, const long lon
       }
       store8(lr + c * 8, v);
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Compact lm_head: only positions whose NEXT token carries a label contribute to get_batch_logps
+// (muffin/eval/muffin_inference_logp.py:93-104: loss_mask = labels[:, 1:] != -100), i.e. 512 of the 1135 positions
+// of a config-(b) sequence. row_pos[s*cap + j] = s*T + t of the j-th such position of sequence s (ascending t),
+// -1 for the unused slots of the sequence's `cap`-sized segment (cap >= number of labels of a row, e.g. L).
+// One warp per sequence, ballot-scan over T.
+// ------------------------------------------------------------------------------------------------
+__global__ void supervised_rows_kernel(const long long* __restrict__ labels, int nseq, int T, int cap,
+                                       int* __restrict__ row_pos) {
+  const int s = blockIdx.x;
+  const int lane = threadIdx.x;
+  int base = 0;
+  for (int t0 = 0; t0 < T - 1; t0 += 32) {
+    const int t = t0 + lane;
+    const bool on = t < T - 1 && labels[(long long)s * T + t + 1] != IGNORE_INDEX;
+    const unsigned m = __ballot_sync(0xffffffffu, on);
+    const int idx = base + __popc(m & ((1u << lane) - 1u));
+    if (on && idx < cap) row_pos[(long long)s * cap + idx] = s * T + t;
+    base += __popc(m);
+  }
+  for (int j = min(base, cap) + lane; j < cap; j += 32) row_pos[(long long)s * cap + j] = -1;
+}
+// out[r] = x[row_pos[r]] (zeros for padding slots)
+__global__ void rows_gather_kernel(const int* __restrict__ row_pos, const bf16* __restrict__ x, bf16* __restrict__ out,
+                                   long long n_rows, int H8) {
+  const long long total = n_rows * H8;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / H8;
+    const int c = (int)(idx - r * H8);
+    const int pos = row_pos[r];
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (pos >= 0) v = *reinterpret_cast<const uint4*>(x + ((long long)pos * H8 + c) * 8);
+    *reinterpret_cast<uint4*>(out + idx * 8) = v;
+  }
+}
+// dx[row_pos[r]] = dy[r] (dx zero-filled by the caller; every position appears at most once)
+__global__ void rows_scatter_kernel(const int* __restrict__ row_pos, const bf16* __restrict__ dy,
+                                    bf16* __restrict__ dx, long long n_rows, int H8) {
+  const long long total = n_rows * H8;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / H8;
+    const int c = (int)(idx - r * H8);
+    const int pos = row_pos[r];
+    if (pos >= 0)
+      *reinterpret_cast<uint4*>(dx + ((long long)pos * H8 + c) * 8) = *reinterpret_cast<const uint4*>(dy + idx * 8);
   }
 }
 
@@ -1273,15 +1369,70 @@ extern "C" int rlaifv_f32_to_bf16(const float* in, void* out, long long n, int a
   return 0;
 }
 
+extern "C" int rlaifv_f32_to_bf16_2d(const float* in, long long ld_in, void* out, long long ld_out, long long rows,
+                                     int cols, int accumulate, void* stream) {
+  B200_REQUIRE(cols % 8 == 0 && ld_in % 4 == 0 && ld_out % 8 == 0 && rows > 0, "f32_to_bf16_2d: bad shape");
+  f32_to_bf16_2d_kernel<<<grid_for(rows * (cols / 8), 256), 256, 0, ST>>>(in, ld_in, (bf16*)out, ld_out, rows,
+                                                                         cols / 8, accumulate);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int rlaifv_logp_fwd(const void* logits, long long ld, const long long* labels, int nseq, int T, int V,
                                float* per_tok, float* lse, float* logp_sum, float* logp_avg, float* count,
                                void* stream) {
   B200_REQUIRE(V % 8 == 0 && T >= 2, "logp_fwd: V %% 8 != 0 or T < 2");
   const long long rows = (long long)nseq * (T - 1);
   const int grid = (int)(rows < (long long)num_sms() * 8 ? rows : (long long)num_sms() * 8);
-  logp_fwd_kernel<<<grid, LOGP_THREADS, 0, ST>>>((const bf16*)logits, ld, labels, nseq, T, V, per_tok, lse);
+  logp_fwd_kernel<<<grid, LOGP_THREADS, 0, ST>>>((const bf16*)logits, ld, labels, nseq, T, V, per_tok, lse, nullptr, 0);
   B200_CHECK_CUDA(cudaGetLastError());
   logp_reduce_kernel<<<nseq, 256, 0, ST>>>(per_tok, labels, nseq, T, logp_sum, logp_avg, count);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+// ---- compact lm_head (supervised positions only) ----
+extern "C" int rlaifv_supervised_rows(const long long* labels, int nseq, int T, int cap, int* row_pos, void* stream) {
+  B200_REQUIRE(nseq > 0 && T >= 2 && cap > 0, "supervised_rows: bad shape");
+  B200_REQUIRE((long long)nseq * T < 2147483647LL, "supervised_rows: nseq*T overflows int32");
+  supervised_rows_kernel<<<nseq, 32, 0, ST>>>(labels, nseq, T, cap, row_pos);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int rlaifv_rows_gather(const int* row_pos, const void* x, void* out, long long n_rows, int H, void* stream) {
+  B200_REQUIRE(H % 8 == 0 && n_rows > 0, "rows_gather: bad shape");
+  rows_gather_kernel<<<grid_for(n_rows * (H / 8), 256), 256, 0, ST>>>(row_pos, (const bf16*)x, (bf16*)out, n_rows, H / 8);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int rlaifv_rows_scatter(const int* row_pos, const void* dy, void* dx, long long n_rows, int H, void* stream) {
+  B200_REQUIRE(H % 8 == 0 && n_rows > 0, "rows_scatter: bad shape");
+  rows_scatter_kernel<<<grid_for(n_rows * (H / 8), 256), 256, 0, ST>>>(row_pos, (const bf16*)dy, (bf16*)dx, n_rows, H / 8);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+// logits bf16 [n_rows][ld] = head applied to the gathered rows; per_tok [nseq][T-1] must be zero-filled by the caller
+// (unsupervised positions stay 0); lse fp32 [n_rows].
+extern "C" int rlaifv_logp_fwd_rows(const void* logits, long long ld, const long long* labels, const int* row_pos,
+                                    long long n_rows, int nseq, int T, int V, float* per_tok, float* lse,
+                                    float* logp_sum, float* logp_avg, float* count, void* stream) {
+  B200_REQUIRE(V % 8 == 0 && T >= 2 && n_rows > 0 && row_pos, "logp_fwd_rows: bad arguments");
+  const int grid = (int)(n_rows < (long long)num_sms() * 8 ? n_rows : (long long)num_sms() * 8);
+  logp_fwd_kernel<<<grid, LOGP_THREADS, 0, ST>>>((const bf16*)logits, ld, labels, nseq, T, V, per_tok, lse, row_pos,
+                                                 n_rows);
+  B200_CHECK_CUDA(cudaGetLastError());
+  logp_reduce_kernel<<<nseq, 256, 0, ST>>>(per_tok, labels, nseq, T, logp_sum, logp_avg, count);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+// in place on the compact logits: d loss / d logits. token_weight (nullable) [nseq][T-1]; norm (nullable) [nseq] =
+// label count (average mode) or weight sum (weighted average mode).
+extern "C" int rlaifv_logp_bwd_rows(void* logits, long long ld, const long long* labels, const int* row_pos,
+                                    long long n_rows, const float* lse, const float* d_logp, const float* token_weight,
+                                    const float* norm, int nseq, int T, int V, void* stream) {
+  B200_REQUIRE(V % 8 == 0 && n_rows > 0 && row_pos, "logp_bwd_rows: bad arguments");
+  const int grid = (int)(n_rows < (long long)num_sms() * 8 ? n_rows : (long long)num_sms() * 8);
+  logp_bwd_weighted_kernel<<<grid, LOGP_THREADS, 0, ST>>>((bf16*)logits, ld, labels, lse, d_logp, token_weight, norm,
+                                                          nseq, T, V, row_pos, n_rows);
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1311,7 +1462,7 @@ extern "C" int rlaifv_logp_bwd_weighted(void* logits, long long ld, const long l
   const long long rows = (long long)nseq * T;
   const int grid = (int)(rows < (long long)num_sms() * 8 ? rows : (long long)num_sms() * 8);
   logp_bwd_weighted_kernel<<<grid, LOGP_THREADS, 0, ST>>>((bf16*)logits, ld, labels, lse, d_logp, token_weight,
-                                                          wsum_or_null, nseq, T, V);
+                                                          wsum_or_null, nseq, T, V, nullptr, 0);
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

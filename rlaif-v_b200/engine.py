@@ -53,6 +53,8 @@ class DPOStepEngine:
         # ZeRO-2 overlap: reduce a layer's bucket as soon as its backward finished (last micro-batch only)
         policy.on_layer_grads_ready = self._layer_ready
         policy.on_head_grads_ready = self._head_ready
+        if hasattr(policy, "on_bucket_grads_ready"):      # front-end buckets that finish inside the backward (EVA tower)
+            policy.on_bucket_grads_ready = self._bucket_ready
         policy.param_ready = self.opt.wait_bucket
 
     def _layer_ready(self, layer):
@@ -61,6 +63,12 @@ class DPOStepEngine:
             self.opt.reduce_bucket(name)
             if self._stepping:            # gradients final, weights no longer read this step: update now,
                 self.opt.step_bucket(name)    # overlapped with the rest of the backward
+
+    def _bucket_ready(self, name):
+        if self._last_micro and name not in self.policy.tail_bucket_names():
+            self.opt.reduce_bucket(name)
+            if self._stepping:
+                self.opt.step_bucket(name)
 
     def _head_ready(self):
         if self._last_micro:

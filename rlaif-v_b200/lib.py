@@ -53,6 +53,14 @@ _SIGNATURES = {
     "rlaifv_splice_scatter": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                               c_void_p],
     "rlaifv_f32_to_bf16": [c_void_p, c_void_p, c_ll, c_int, c_void_p],
+    "rlaifv_f32_to_bf16_2d": [c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_int, c_void_p],
+    "rlaifv_supervised_rows": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
+    "rlaifv_rows_gather": [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p],
+    "rlaifv_rows_scatter": [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p],
+    "rlaifv_logp_fwd_rows": [c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                             c_void_p, c_void_p, c_void_p],
+    "rlaifv_logp_bwd_rows": [c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                             c_int, c_int, c_void_p],
     "rlaifv_logp_fwd": [c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                         c_void_p, c_void_p, c_void_p],
     "rlaifv_logp_bwd": [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,

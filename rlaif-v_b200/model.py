@@ -357,6 +357,10 @@ class LlavaDPOPolicy:
         # True: also stash the normalised inputs and the SwiGLU product (22 KB/token/layer more memory,
         # 3 fewer row passes per layer in the backward). The engine turns it on when HBM allows.
         self.stash_extra = False
+        # training forward sends only the supervised positions through final norm / lm_head / log-softmax
+        # (forward_logps); inference / the reference log-prob pre-pass keep the full head (per-token values of every
+        # position are part of the parquet contract)
+        self.compact_head = True
         self.embed_grad_f32 = None   # fp32 scatter target for embedding rows (allocated lazily)
         self._stash = None
         self.lora = None             # LoraStore: base weights frozen, adapters + mm_projector trainable
@@ -634,6 +638,21 @@ class LlavaDPOPolicy:
                       n_feat_rows=proj.shape[0])
         x = self._run_layers(x, nseq, T, st)
         self._need("head")
+        compact = keep_stash and self.compact_head
+        if compact:
+            # training: only the positions whose next token is supervised reach the final norm / lm_head / log-softmax
+            # (get_batch_logps masks the rest out of the sum, muffin_inference_logp.py:93-104). A row of the collator
+            # holds at most L labels, so L slots per sequence always suffice — no host sync for the count.
+            row_pos = ops.supervised_rows(new_labels, input_ids.shape[1])
+            R = row_pos.numel()
+            xc = ops.rows_gather(row_pos, x, out=self.buf("xc", (R, H)))
+            rstd_f = torch.empty(R, dtype=_F32, device=dev)
+            hn = ops.rmsnorm_fwd(xc, P["norm"], d.rms_eps, out=self.buf("hn_c", (R, H)), rstd=rstd_f)
+            logits = ops.gemm(hn, P["lm_head"], self.buf("logits_c", (R, V)))
+            per_tok, lse_v, logp, avg, count = ops.logp_fwd_rows(logits, new_labels, row_pos, nseq, T)
+            st.update(x_final=xc, rstd_f=rstd_f, hn=hn, logits=logits, lse_v=lse_v, count=count, row_pos=row_pos)
+            self._stash = st
+            return dict(per_token_logps=per_tok, logp=logp, avg_logp=avg, labels=new_labels, T=T)
         rstd_f = torch.empty(M, dtype=_F32, device=dev) if keep_stash else None
         hn = ops.rmsnorm_fwd(x, P["norm"], d.rms_eps, out=self.buf("hn", (M, H)), rstd=rstd_f)
         logits = ops.gemm(hn, P["lm_head"], self.buf("logits", (M, V)))
@@ -660,8 +679,14 @@ class LlavaDPOPolicy:
         cos, sin = self.rope_tables(T)
         acc = bool(accumulate)
 
+        row_pos = st.get("row_pos")
         if token_weight is not None:
             assert not use_average or weight_sum is not None
+        if row_pos is not None:                   # compact head (training): logits hold the supervised rows only
+            norm = (weight_sum if token_weight is not None else st["count"]) if use_average else None
+            dlogits = ops.logp_bwd_rows(st["logits"], st["labels"], row_pos, st["lse_v"], d_logp, nseq, T,
+                                        token_weight=token_weight, norm=norm)
+        elif token_weight is not None:
             dlogits = ops.logp_bwd_weighted(st["logits"], st["labels"], st["lse_v"], d_logp, token_weight, nseq, T,
                                             wsum=weight_sum if use_average else None)
         else:
@@ -669,11 +694,17 @@ class LlavaDPOPolicy:
                                    count=st["count"] if use_average else None)
         frozen = self.lora is not None            # LoRA: lm_head / norms / embeddings / base matrices are frozen
         scratch_h = self.buf("frozen_dw", (H,)) if frozen else None
+        Mh = dlogits.shape[0]                     # rows that went through the head (M, or the compact row count)
         if not frozen:
             ops.gemm(dlogits, st["hn"], G["lm_head"], a_mn=True, b_mn=True, accumulate=acc)    # dW = dlogits^T hn
-        dhn = ops.gemm(dlogits, P["lm_head"], self.buf("dn", (M, H)), b_mn=True)                # dhn = dlogits W
-        dx = ops.rmsnorm_bwd(dhn, st["x_final"], P["norm"], st["rstd_f"], self.buf("dx_a", (M, H)),
+        dhn = ops.gemm(dlogits, P["lm_head"], self.buf("dn_c" if row_pos is not None else "dn", (Mh, H)), b_mn=True)               # dhn = dlogits W
+        dx = ops.rmsnorm_bwd(dhn, st["x_final"], P["norm"], st["rstd_f"],
+                             self.buf("dx_c" if row_pos is not None else "dx_a", (Mh, H)),
                              scratch_h if frozen else G["norm"], dw_accumulate=acc and not frozen)
+        if row_pos is not None:                   # back to the [M, H] residual stream (zeros at unsupervised positions)
+            full = self.buf("dx_a", (M, H))
+            full.zero_()
+            dx = ops.rows_scatter(row_pos, dx, full)
         if self.on_head_grads_ready is not None:
             self.on_head_grads_ready()
         for i in reversed(range(d.num_layers)):

@@ -335,6 +335,15 @@ def f32_to_bf16(src, dst, accumulate=False):
     return dst
 
 
+def f32_to_bf16_2d(src, dst, accumulate=False):
+    """fp32 [rows, cols] -> bf16 [rows, cols]; either side may be a column block of a wider buffer."""
+    _chk(src, _f32), _chk(dst)
+    assert src.shape == dst.shape and src.dim() == 2 and src.stride(1) == 1 and dst.stride(1) == 1
+    _l.call("rlaifv_f32_to_bf16_2d", _l.ptr(src), src.stride(0), _l.ptr(dst), dst.stride(0), src.shape[0], src.shape[1],
+            int(accumulate), _l.stream_ptr())
+    return dst
+
+
 def logp_fwd(logits, labels, nseq, T):
     """logits [nseq*T, V] bf16 (row stride may exceed V); labels [nseq, T] int64 (spliced).
     Returns per_tok [nseq, T-1], lse [nseq, T], logp_sum, logp_avg, count [nseq] (all fp32)."""
@@ -350,6 +359,58 @@ def logp_fwd(logits, labels, nseq, T):
     _l.call("rlaifv_logp_fwd", _l.ptr(logits), logits.stride(0), _l.ptr(labels), nseq, T, V, _l.ptr(per_tok),
             _l.ptr(lse), _l.ptr(s), _l.ptr(a), _l.ptr(c), _l.stream_ptr())
     return per_tok, lse, s, a, c
+
+
+def supervised_rows(labels, cap):
+    """labels [nseq, T] int64 (spliced) -> row_pos int32 [nseq*cap]: flat positions s*T+t whose NEXT token is
+    supervised (the rows get_batch_logps keeps), -1 in the unused slots of each sequence's cap-sized segment."""
+    assert labels.dtype == torch.int64 and labels.is_cuda and labels.is_contiguous()
+    nseq, T = labels.shape
+    row_pos = torch.empty(nseq * cap, dtype=torch.int32, device=labels.device)
+    _l.call("rlaifv_supervised_rows", _l.ptr(labels), nseq, T, int(cap), _l.ptr(row_pos), _l.stream_ptr())
+    return row_pos
+
+
+def rows_gather(row_pos, x, out=None):
+    _chk(x)
+    assert x.is_contiguous() and row_pos.dtype == torch.int32
+    n, H = row_pos.numel(), x.shape[1]
+    if out is None:
+        out = torch.empty((n, H), dtype=torch.bfloat16, device=x.device)
+    _l.call("rlaifv_rows_gather", _l.ptr(row_pos), _l.ptr(x), _l.ptr(out), n, H, _l.stream_ptr())
+    return out
+
+
+def rows_scatter(row_pos, dy, dx):
+    """dx[row_pos[r]] = dy[r]; dx must be zero-filled by the caller."""
+    _chk(dy), _chk(dx)
+    assert dy.is_contiguous() and dx.is_contiguous() and dy.shape[1] == dx.shape[1]
+    _l.call("rlaifv_rows_scatter", _l.ptr(row_pos), _l.ptr(dy), _l.ptr(dx), row_pos.numel(), dy.shape[1], _l.stream_ptr())
+    return dx
+
+
+def logp_fwd_rows(logits, labels, row_pos, nseq, T):
+    """Compact-head form of logp_fwd: logits [n_rows, V] of the gathered rows. Returns per_tok [nseq, T-1] (zeros at
+    unsupervised positions), lse [n_rows], logp_sum, logp_avg, count."""
+    _chk(logits)
+    V, dev, n = logits.shape[1], logits.device, row_pos.numel()
+    assert logits.shape[0] == n
+    per_tok = torch.zeros((nseq, T - 1), dtype=_f32, device=dev)
+    lse = torch.zeros(n, dtype=_f32, device=dev)
+    s = torch.empty(nseq, dtype=_f32, device=dev)
+    a = torch.empty(nseq, dtype=_f32, device=dev)
+    c = torch.empty(nseq, dtype=_f32, device=dev)
+    _l.call("rlaifv_logp_fwd_rows", _l.ptr(logits), logits.stride(0), _l.ptr(labels), _l.ptr(row_pos), n, nseq, T, V,
+            _l.ptr(per_tok), _l.ptr(lse), _l.ptr(s), _l.ptr(a), _l.ptr(c), _l.stream_ptr())
+    return per_tok, lse, s, a, c
+
+
+def logp_bwd_rows(logits, labels, row_pos, lse, d_logp, nseq, T, token_weight=None, norm=None):
+    """In place on the compact logits: logits <- d loss / d logits (token_weight [nseq, T-1] / norm [nseq] optional)."""
+    _chk(logits), _chk(lse, _f32), _chk(d_logp, _f32)
+    _l.call("rlaifv_logp_bwd_rows", _l.ptr(logits), logits.stride(0), _l.ptr(labels), _l.ptr(row_pos), row_pos.numel(),
+            _l.ptr(lse), _l.ptr(d_logp), _l.ptr(token_weight), _l.ptr(norm), nseq, T, logits.shape[1], _l.stream_ptr())
+    return logits
 
 
 def logp_bwd(logits, labels, lse, d_logp, nseq, T, count=None):

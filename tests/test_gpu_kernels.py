@@ -360,3 +360,77 @@ def test_experimental_split_k_matches_single_pass(a_mn, b_mn):
             assert rel(acc, 2 * ref.float()) < 2e-2
     finally:
         L.rlaifv_gemm_set_split_k(0, 0)
+
+
+# --------------------------------------------------------------------------------------------
+# compact lm_head (supervised positions only)
+# --------------------------------------------------------------------------------------------
+def test_supervised_rows_index_bit_exact():
+    from rlaifv_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    nseq, T, cap = 5, 200, 64
+    labels = torch.full((nseq, T), -100, dtype=torch.int64)
+    for s in range(nseq):
+        n = int(torch.randint(0, cap + 1, (1,), generator=g))
+        idx = torch.randperm(T - 1, generator=g)[:n] + 1           # label positions 1..T-1 (position 0 is never a target)
+        labels[s, idx] = torch.randint(3, 1000, (n,), generator=g)
+    labels[0, 0] = 7                                               # a label at position 0 supervises nothing
+    want = torch.full((nseq, cap), -1, dtype=torch.int32)
+    for s in range(nseq):
+        pos = [t for t in range(T - 1) if int(labels[s, t + 1]) != -100]
+        want[s, :len(pos)] = torch.tensor([s * T + t for t in pos], dtype=torch.int32)
+    got = ops.supervised_rows(labels.cuda(), cap).cpu().view(nseq, cap)
+    assert torch.equal(got, want)
+
+
+def test_compact_head_equals_full_head():
+    """forward_logps(keep_stash=True) sends only supervised rows through norm / lm_head / log-softmax: summed log-probs
+    are bit-identical to the full head's, per-token values agree on the supervised positions, gradients agree."""
+    from oracle import llava_dpo_oracle as O
+    from rlaifv_b200 import ops
+    from rlaifv_b200.model import LlavaDims, LlavaDPOPolicy
+    c = O.TINY
+    dims = LlavaDims(vocab_size=c.vocab_size, hidden_size=c.hidden_size, intermediate_size=c.intermediate_size,
+                     num_layers=c.num_layers, num_heads=c.num_heads, clip_hidden=c.clip_hidden,
+                     clip_intermediate=c.clip_intermediate, clip_layers=c.clip_layers, clip_heads=c.clip_heads,
+                     image_size=c.image_size, patch_size=c.patch_size)
+    pol = LlavaDPOPolicy(dims, "cuda", hf_state=O.make_params(c, seed=0, scale=0.4))
+    batch = O.synthetic_pair_batch(c, 3, 24, 40, seed=9, image_pos=6, ragged=True)
+    ids, labels, images = batch["concatenated_input_ids"], batch["concatenated_labels"], batch["images"]
+    d_logp = torch.randn(6, generator=torch.Generator().manual_seed(1)).cuda()
+    grads = {}
+    outs = {}
+    for compact in (False, True):
+        pol.compact_head = compact
+        out = pol.forward_logps(ids, labels, images, keep_stash=True)
+        assert ("row_pos" in pol._stash) == compact
+        pol.store.grad.zero_()
+        pol.backward_logps(d_logp.clone())
+        pol.finalize_embed_grad()
+        torch.cuda.synchronize()
+        grads[compact] = pol.store.grad.float().clone()
+        outs[compact] = out
+    assert torch.equal(outs[True]["logp"], outs[False]["logp"]) and torch.equal(outs[True]["avg_logp"], outs[False]["avg_logp"])
+    mask = outs[False]["labels"][:, 1:] != -100
+    assert torch.equal(outs[True]["per_token_logps"][mask], outs[False]["per_token_logps"][mask])
+    assert float(outs[True]["per_token_logps"][~mask].abs().max()) == 0.0
+    a, b = grads[True], grads[False]
+    assert float((a - b).norm() / b.norm()) <= 2e-3
+    assert float((a - b).abs().max()) <= 2e-2 * float(b.abs().max())
+    # average mode + token weights take the same compact path
+    pol.compact_head = True
+    out = pol.forward_logps(ids, labels, images, keep_stash=True)
+    tw = (torch.rand(6, out["labels"].shape[1] - 1, generator=torch.Generator().manual_seed(2)) + 0.5).cuda()
+    lw, aw, ws = ops.logp_weighted_reduce(out["per_token_logps"], out["labels"], tw)
+    pol.store.grad.zero_()
+    pol.backward_logps(d_logp.clone(), use_average=True, token_weight=tw, weight_sum=ws)
+    pol.finalize_embed_grad()
+    gc = pol.store.grad.float().clone()
+    pol.compact_head = False
+    pol.forward_logps(ids, labels, images, keep_stash=True)
+    pol.store.grad.zero_()
+    pol.backward_logps(d_logp.clone(), use_average=True, token_weight=tw, weight_sum=ws)
+    pol.finalize_embed_grad()
+    torch.cuda.synchronize()
+    gf = pol.store.grad.float()
+    assert float((gc - gf).norm() / gf.norm()) <= 2e-3
