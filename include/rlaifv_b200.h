@@ -62,6 +62,11 @@ int rlaifv_gemm_set_tuning(int group_m, int debug);
  * (passes 2.. with C +=) so each pass's operand slabs fit the L2. n <= 1 switches it off. */
 int rlaifv_gemm_set_split_k(int n, int min_k);
 
+/* Forward-kernel selection (tuning / A-B only): 1 (default) = two query tiles per CTA ping-ponging between the
+ * softmax warpgroups and the tensor pipe, P kept in TMEM as the A operand of the PV MMA; 0 = the round-1 single-tile
+ * kernel (P through shared memory). Results agree to fp32 rounding of the online softmax. */
+int rlaifv_attention_set_variant(int fwd_variant);
+
 /* ---- attention (tcgen05, S/O accumulators in TMEM) ---------------------------------------------
  * q/k/v/out: [nseq*S][ld] bf16, head h at columns [h*head_dim, (h+1)*head_dim); lse fp32
  * [nseq][n_heads][S]. head_dim 128 (Llama, causal) or 64 (CLIP, non-causal).

@@ -267,6 +267,287 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 }
 
 // ================================================================================================
+// forward, ping-pong form (default): one CTA owns TWO adjacent 128-row query tiles (A, B) of one (sequence, head) and
+// shares their K/V stream. While the 128 softmax threads of tile A work on S_A, the tensor pipe runs the MMAs of tile B
+// and vice versa, so neither unit waits for the other any more (the single-tile kernel above is a strict
+// MMA -> softmax -> MMA chain: sm__pipe_tensor_cycles_active 21 %).
+//   warps 0-3  softmax / epilogue of tile A (thread = query row = TMEM lane)
+//   warps 4-7  softmax / epilogue of tile B
+//   warp  8    TMA producer (Q_A, Q_B once; K/V ring)
+//   warp  9    MMA issuer, TMEM owner            (warps 10-11 only complete the third warpgroup)
+// Register budget: the producer warpgroup gives its registers back (setmaxnreg.dec 56) and the two softmax warpgroups
+// take 224 each (8*32*224 + 4*32*56 = 64512 = the 168 x 384 registers the CTA was launched with), so the 128-column row stays in registers with room to pipeline.
+// TMEM (512 columns): S_A [0,128) S_B [128,256) O_A [256,256+D) O_B [384,384+D). P = exp2(S - m) is written back
+// as packed bf16 into the first 64 columns of its own S buffer and consumed from there as the A operand of the PV MMA
+// (tcgen05.mma with A in TMEM) — no shared-memory round trip, no proxy fence. The next S MMA of the same tile is issued
+// after that PV (same issuing thread => pipeline order), which is what makes the aliasing safe.
+// ================================================================================================
+template <int D>
+struct AttFwd2Cfg {
+  static constexpr int STAGES = (D == 128) ? 2 : 4;
+  static constexpr uint32_t Q_BYTES = ATT_BQ * D * 2;
+  static constexpr uint32_t KV_BYTES = ATT_BKV * D * 2;   // one of K or V
+  static constexpr uint32_t OFF_Q = 0;                      // [2]
+  static constexpr uint32_t OFF_K = 2 * Q_BYTES;            // [STAGES]
+  static constexpr uint32_t OFF_V = OFF_K + STAGES * KV_BYTES;
+  static constexpr uint32_t OFF_BAR = OFF_V + STAGES * KV_BYTES;
+  static constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static constexpr uint32_t TMEM_COLS = 512;
+};
+
+template <int D, bool CAUSAL>
+__global__ void __launch_bounds__(384, 1)
+attention_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                      const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ out, long long ld_out,
+                      float* __restrict__ lse_out, int Sq, int Skv, int n_heads, int kv_group, int q_shared,
+                      float scale) {
+  using Cfg = AttFwd2Cfg<D>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* q_full = bars + 0;               // [2]
+  uint64_t* kv_full = bars + 2;              // [STAGES]
+  uint64_t* kv_empty = bars + 2 + STAGES;    // [STAGES]
+  uint64_t* s_full = bars + 2 + 2 * STAGES;  // [2]
+  uint64_t* p_full = s_full + 2;             // [2]
+  uint64_t* o_final = p_full + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_q_tiles = (Sq + ATT_BQ - 1) / ATT_BQ;
+  const int pair = (int)gridDim.x - 1 - (int)blockIdx.x;   // heavy (late) tiles first
+  const int qt[2] = {2 * pair, 2 * pair + 1};
+  const bool has_b = qt[1] < num_q_tiles;
+  const int head = blockIdx.y, seq = blockIdx.z;
+  const int q_seq = q_shared ? 0 : seq;
+  const int kv_head = head / kv_group;
+  const int n_kv_all = (Skv + ATT_BKV - 1) / ATT_BKV;
+  const int n_of[2] = {CAUSAL ? qt[0] + 1 : n_kv_all, has_b ? (CAUSAL ? qt[1] + 1 : n_kv_all) : 0};
+  const int n_kv = n_of[0] > n_of[1] ? n_of[0] : n_of[1];
+
+  if (warp == 9) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmK);
+      tma_prefetch_desc(&tmV);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&q_full[i], 1);
+        mbar_init(&s_full[i], 1);
+        mbar_init(&p_full[i], 128);
+        mbar_init(&o_final[i], 1);
+      }
+      for (int i = 0; i < STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 8) {
+   setmaxnreg_dec<56>();      // inside the role branch: ptxas budgets registers per region from here on
+   if (warp == 8) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      for (int x = 0; x < 2; ++x) {
+        if (x == 1 && !has_b) break;
+        mbar_arrive_expect_tx(&q_full[x], Cfg::Q_BYTES);
+#pragma unroll
+        for (int a = 0; a < D / 64; ++a)
+          tma_load_3d(smem + Cfg::OFF_Q + x * Cfg::Q_BYTES + a * (ATT_BQ * 128), &tmQ, &q_full[x], head * D + a * 64,
+                      qt[x] * ATT_BQ, q_seq);
+      }
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j % STAGES;
+        if (j >= STAGES) mbar_wait(&kv_empty[s], ((j / STAGES) - 1) & 1);
+        mbar_arrive_expect_tx(&kv_full[s], 2 * Cfg::KV_BYTES);
+#pragma unroll
+        for (int a = 0; a < D / 64; ++a) {
+          tma_load_3d(smem + Cfg::OFF_K + s * Cfg::KV_BYTES + a * (ATT_BKV * 128), &tmK, &kv_full[s],
+                      kv_head * D + a * 64, j * ATT_BKV, seq);
+          tma_load_3d(smem + Cfg::OFF_V + s * Cfg::KV_BYTES + a * (ATT_BKV * 128), &tmV, &kv_full[s],
+                      kv_head * D + a * 64, j * ATT_BKV, seq);
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, ATT_BKV, false, false);
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, D, false, true);
+      int kv_ready = 0;                      // K/V stages 0 .. kv_ready-1 have been waited for
+      auto need_kv = [&](int j) {
+        while (kv_ready <= j) {
+          mbar_wait(&kv_full[kv_ready % STAGES], (kv_ready / STAGES) & 1);
+          ++kv_ready;
+        }
+        tc_fence_after();
+      };
+      auto issue_s = [&](int x, int j) {
+        need_kv(j);
+        const uint32_t q_addr = smem_u32(smem + Cfg::OFF_Q + x * Cfg::Q_BYTES);
+        const uint32_t k_addr = smem_u32(smem + Cfg::OFF_K + (j % STAGES) * Cfg::KV_BYTES);
+#pragma unroll
+        for (int k16 = 0; k16 < D / 16; ++k16) {
+          const uint64_t ad = desc_kmajor(q_addr + (k16 >> 2) * (ATT_BQ * 128), k16 & 3);
+          const uint64_t bd = desc_kmajor(k_addr + (k16 >> 2) * (ATT_BKV * 128), k16 & 3);
+          umma_ss(tmem_base + x * 128, ad, bd, idesc_s, k16 > 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[x]);
+      };
+      auto issue_pv = [&](int x, int j) {
+        const uint32_t v_addr = smem_u32(smem + Cfg::OFF_V + (j % STAGES) * Cfg::KV_BYTES);
+#pragma unroll
+        for (int k16 = 0; k16 < ATT_BKV / 16; ++k16) {
+          // A = P (bf16 pairs, 8 TMEM columns per 16 kv), B = V tile read MN-major
+          umma_ts(tmem_base + 256 + x * 128, tmem_base + x * 128 + k16 * 8, desc_mnmajor(v_addr, k16, ATT_BKV),
+                  idesc_o, (j > 0 || k16 > 0) ? 1u : 0u);
+        }
+      };
+      mbar_wait(&q_full[0], 0);
+      if (has_b) mbar_wait(&q_full[1], 0);
+      issue_s(0, 0);
+      if (has_b) issue_s(1, 0);
+      for (int j = 0; j < n_kv; ++j) {
+        for (int x = 0; x < 2; ++x) {
+          if (j >= n_of[x]) continue;
+          mbar_wait(&p_full[x], j & 1);
+          tc_fence_after();
+          issue_pv(x, j);
+          if (j + 1 < n_of[x]) issue_s(x, j + 1);
+          else umma_commit(&o_final[x]);
+        }
+        umma_commit(&kv_empty[j % STAGES]);
+      }
+    }
+   }
+  } else {
+    // ------------------------------ softmax / epilogue: one thread per query row ------------------------------
+    setmaxnreg_inc<224>();
+    const int x = warp >> 2;                 // 0: tile A, 1: tile B
+    const int nx = n_of[x];
+    if (nx > 0) {
+      const int r = (warp & 3) * 32 + lane;  // row in tile == TMEM lane
+      const int q_idx = qt[x] * ATT_BQ + r;
+      const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+      const uint32_t tS = tmem_base + x * 128 + lane_off;
+      const uint32_t tO = tmem_base + 256 + x * 128 + lane_off;
+      const float c = scale * LOG2E;
+      float m_used = -INFINITY, l = 0.f;
+      for (int j = 0; j < nx; ++j) {
+        mbar_wait(&s_full[x], j & 1);
+        tc_fence_after();
+        const int kv0 = j * ATT_BKV;
+        const bool need_mask = (kv0 + ATT_BKV > Skv) || (CAUSAL && j == qt[x]);
+        uint32_t v[128];
+        tmem_ld_32x32b_x64(tS, v);
+        tmem_ld_32x32b_x64(tS + 64, v + 64);
+        tmem_wait_ld();
+        if (need_mask) {
+#pragma unroll
+          for (int i = 0; i < 128; ++i) {
+            const int kv = kv0 + i;
+            if ((kv >= Skv) || (CAUSAL && kv > q_idx)) v[i] = 0xff800000u;   // -inf
+          }
+        }
+        // row max: four independent chains (the serial 128-deep FMNMX chain was latency, not throughput)
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int i = 0; i < 128; i += 4) {
+          mx4[0] = fmaxf(mx4[0], __uint_as_float(v[i]));
+          mx4[1] = fmaxf(mx4[1], __uint_as_float(v[i + 1]));
+          mx4[2] = fmaxf(mx4[2], __uint_as_float(v[i + 2]));
+          mx4[3] = fmaxf(mx4[3], __uint_as_float(v[i + 3]));
+        }
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        float m_new = fmaxf(m_used, mx * c);
+        if (m_new == -INFINITY) m_new = 0.f;
+        if (j == 0) {
+          m_used = m_new;
+        } else {
+          // S_x(j) is complete => PV_x(j-1), issued before it by the same thread, is complete too: O is readable
+          const bool need = (m_new - m_used) > 8.0f;
+          if (__any_sync(0xffffffffu, need)) {
+            const float alpha = need ? fast_exp2(m_used - m_new) : 1.f;
+            if (need) { m_used = m_new; l *= alpha; }
+#pragma unroll 1
+            for (int ch = 0; ch < D / 32; ++ch) {
+              uint32_t o[32];
+              tmem_ld_32x32b_x32(tO + ch * 32, o);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st_32x32b_x32(tO + ch * 32, o);
+            }
+          }
+        }
+        // P = exp2(s*c - m) -> packed bf16 pairs -> the first 64 columns of this tile's S buffer.
+        // Explicit phases over the register-resident row (in place, no extra registers): all FFMAs, then all MUFU.EX2
+        // back to back (the XU pipe is the scarce unit: keep it streaming), then sums on four accumulators + packing.
+        const float neg_m = -m_used;
+#pragma unroll
+        for (int i = 0; i < 128; ++i) v[i] = __float_as_uint(fmaf(__uint_as_float(v[i]), c, neg_m));
+#pragma unroll
+        for (int i = 0; i < 128; ++i) v[i] = __float_as_uint(fast_exp2(__uint_as_float(v[i])));   // exp2(-inf) = 0
+        float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = __uint_as_float(v[g * 32 + 2 * i]), p1 = __uint_as_float(v[g * 32 + 2 * i + 1]);
+            rs4[i & 3] += p0 + p1;
+            pk[i] = pack_bf16(p0, p1);
+          }
+          tmem_st_32x32b_x16(tS + g * 16, pk);
+        }
+        const float rs = (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+        l += rs;
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(&p_full[x]);
+      }
+      // epilogue
+      mbar_wait(&o_final[x], 0);
+      tc_fence_after();
+      const float inv = 1.f / l;
+      const bool row_ok = q_idx < Sq;
+      bf16* o_row = out + ((long long)seq * Sq + q_idx) * ld_out + head * D;
+#pragma unroll 1
+      for (int ch = 0; ch < D / 32; ++ch) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tO + ch * 32, v);
+        tmem_wait_ld();
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 u;
+            u.x = pack_bf16(__uint_as_float(v[g * 8 + 0]) * inv, __uint_as_float(v[g * 8 + 1]) * inv);
+            u.y = pack_bf16(__uint_as_float(v[g * 8 + 2]) * inv, __uint_as_float(v[g * 8 + 3]) * inv);
+            u.z = pack_bf16(__uint_as_float(v[g * 8 + 4]) * inv, __uint_as_float(v[g * 8 + 5]) * inv);
+            u.w = pack_bf16(__uint_as_float(v[g * 8 + 6]) * inv, __uint_as_float(v[g * 8 + 7]) * inv);
+            *reinterpret_cast<uint4*>(o_row + ch * 32 + g * 8) = u;
+          }
+        }
+      }
+      if (row_ok && lse_out)
+        lse_out[((long long)seq * n_heads + head) * Sq + q_idx] = (m_used + log2f(l)) * LN2;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ================================================================================================
 // backward (D = 128; causal self-attention, or non-causal cross-attention with Sq != Skv)
 // ================================================================================================
 // delta[seq][head][q] = sum_d dO * O   (fp32)
@@ -572,13 +853,23 @@ static int launch_att_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CU
                           int q_shared, float scale, cudaStream_t st) {
   using Cfg = AttFwdCfg<D>;
   auto kern = attention_fwd_kernel<D, CAUSAL>;
-  static bool configured = false;
-  if (!configured) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
-    configured = true;
-  }
+  B200_CHECK_CUDA(configure_smem_once((const void*)kern, (int)Cfg::SMEM_BYTES));
   dim3 grid((Sq + ATT_BQ - 1) / ATT_BQ, n_heads, nseq);
   kern<<<grid, 160, Cfg::SMEM_BYTES, st>>>(tq, tk, tv, out, ld_out, lse, Sq, Skv, n_heads, kv_group, q_shared, scale);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int D, bool CAUSAL>
+static int launch_att_fwd2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, bf16* out,
+                           long long ld_out, float* lse, int nseq, int Sq, int Skv, int n_heads, int kv_group,
+                           int q_shared, float scale, cudaStream_t st) {
+  using Cfg = AttFwd2Cfg<D>;
+  auto kern = attention_fwd2_kernel<D, CAUSAL>;
+  B200_CHECK_CUDA(configure_smem_once((const void*)kern, (int)Cfg::SMEM_BYTES));
+  const int num_q_tiles = (Sq + ATT_BQ - 1) / ATT_BQ;
+  dim3 grid((num_q_tiles + 1) / 2, n_heads, nseq);
+  kern<<<grid, 384, Cfg::SMEM_BYTES, st>>>(tq, tk, tv, out, ld_out, lse, Sq, Skv, n_heads, kv_group, q_shared, scale);
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -586,6 +877,13 @@ static int launch_att_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CU
 }  // namespace b200
 
 using namespace b200;
+
+// 0: single-tile kernel (round 1), 1 (default): two-tile ping-pong kernel with P in TMEM
+static int g_att_fwd_variant = 1;
+extern "C" int rlaifv_attention_set_variant(int fwd_variant) {
+  g_att_fwd_variant = fwd_variant;
+  return 0;
+}
 
 static int attention_fwd_impl(const void* q, long long ld_q, const void* k, const void* v, long long ld_kv, void* out,
                               long long ld_out, float* lse, int nseq, int Sq, int Skv, int n_heads, int n_kv_heads,
@@ -604,6 +902,13 @@ static int attention_fwd_impl(const void* q, long long ld_q, const void* k, cons
   cudaStream_t st = (cudaStream_t)stream;
   const int g = n_heads / n_kv_heads;
   bf16* o = (bf16*)out;
+  if (g_att_fwd_variant == 1) {
+    if (head_dim == 128)
+      return causal ? launch_att_fwd2<128, true>(tq, tk, tv, o, ld_out, lse, nseq, Sq, Skv, n_heads, g, q_shared, scale, st)
+                    : launch_att_fwd2<128, false>(tq, tk, tv, o, ld_out, lse, nseq, Sq, Skv, n_heads, g, q_shared, scale, st);
+    return causal ? launch_att_fwd2<64, true>(tq, tk, tv, o, ld_out, lse, nseq, Sq, Skv, n_heads, g, q_shared, scale, st)
+                  : launch_att_fwd2<64, false>(tq, tk, tv, o, ld_out, lse, nseq, Sq, Skv, n_heads, g, q_shared, scale, st);
+  }
   if (head_dim == 128) {
     return causal ? launch_att_fwd<128, true>(tq, tk, tv, o, ld_out, lse, nseq, Sq, Skv, n_heads, g, q_shared, scale, st)
                   : launch_att_fwd<128, false>(tq, tk, tv, o, ld_out, lse, nseq, Sq, Skv, n_heads, g, q_shared, scale, st);
@@ -660,12 +965,7 @@ static int attention_bwd_impl(const void* q, long long ld_q, const void* k, cons
   if ((rc = make_qkv_tmap(&tk, k, ld_kv, nseq, Skv, n_kv_heads * head_dim))) return rc;
   if ((rc = make_qkv_tmap(&tv, v, ld_kv, nseq, Skv, n_kv_heads * head_dim))) return rc;
   if ((rc = make_qkv_tmap(&tdo, d_out, ld_dout, nseq, Sq, n_heads * head_dim))) return rc;
-  static bool configured = false;
-  if (!configured) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)AttBwdCfg::SMEM_BYTES));
-    configured = true;
-  }
+  B200_CHECK_CUDA(configure_smem_once((const void*)attention_bwd_kernel, (int)AttBwdCfg::SMEM_BYTES));
   dim3 grid((Skv + 127) / 128, n_kv_heads, nseq);
   attention_bwd_kernel<<<grid, 160, AttBwdCfg::SMEM_BYTES, st>>>(tq, tk, tv, tdo, lse, delta_ws, dq_f32, (bf16*)dk,
                                                                  (bf16*)dv, ld_dkv, Sq, Skv, n_heads,

@@ -577,12 +577,7 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
                         const CUtensorMap& tmB2, int M, int N, int K, const GemmSecondSource& src2,
                         const GemmEpilogue& epi, cudaStream_t stream) {
   auto kern = gemm2_bf16_kernel<A_MN, B_MN>;
-  static bool configured = false;
-  if (!configured) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)GEMM2_SMEM_BYTES));
-    configured = true;
-  }
+  B200_CHECK_CUDA(configure_smem_once((const void*)kern, (int)GEMM2_SMEM_BYTES));
   const int num_tiles = ((M + 255) / 256) * ((N + 255) / 256);
   int clusters = num_sms() / 2;
   if (num_tiles < clusters) clusters = num_tiles;
@@ -599,12 +594,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
                        const GemmEpilogue& epi, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_bf16_kernel<A_MN, B_MN, BN>;
-  static bool configured = false;
-  if (!configured) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)Cfg::SMEM_BYTES));
-    configured = true;
-  }
+  B200_CHECK_CUDA(configure_smem_once((const void*)kern, (int)Cfg::SMEM_BYTES));
   const int num_tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
   if (!g_counter_pool) B200_CHECK_CUDA(cudaGetSymbolAddress((void**)&g_counter_pool, g_tile_counters));

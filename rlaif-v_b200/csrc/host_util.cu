@@ -3,6 +3,10 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <mutex>
+#include <set>
+#include <utility>
+
 namespace b200 {
 
 static thread_local char g_last_error[1024] = "";
@@ -16,16 +20,30 @@ void set_last_error(const char* fmt, ...) {
 const char* get_last_error() { return g_last_error; }
 
 int num_sms() {
-  static int cached = -1;
-  if (cached < 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
+  static int cached[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int slot = (dev >= 0 && dev < 64) ? dev : 0;
+  if (cached[slot] <= 0) {
     int n = 0;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
       n = 148;
-    cached = n;
+    cached[slot] = n;
   }
-  return cached;
+  return cached[slot];
+}
+
+cudaError_t configure_smem_once(const void* func, int bytes) {
+  static std::mutex mu;
+  static std::set<std::pair<int, const void*>> done;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  const std::pair<int, const void*> key(dev, func);
+  if (done.count(key)) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done.insert(key);
+  return e;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,

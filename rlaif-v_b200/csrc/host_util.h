@@ -10,7 +10,10 @@
 namespace b200 {
 
 void set_last_error(const char* fmt, ...);
-int num_sms();
+int num_sms();   // of the CURRENT device (cached per device)
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel): the attribute is per device, so a
+// process that drives several devices must set it on each of them
+cudaError_t configure_smem_once(const void* func, int bytes);
 
 #define B200_CHECK_CUDA(expr)                                                         \
   do {                                                                                \

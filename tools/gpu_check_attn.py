@@ -6,6 +6,10 @@ from rlaifv_b200 import ops
 
 torch.manual_seed(0)
 dev = "cuda"
+from rlaifv_b200 import lib as _lib
+_variant = int(os.environ.get("RLAIFV_ATT_VARIANT", "1"))
+_lib.load().rlaifv_attention_set_variant(_variant)
+print("attention forward variant", _variant, flush=True)
 fails = 0
 
 def check(name, got, ref, tol):
@@ -56,6 +60,7 @@ cases = [
     (1, 128, 1, 128, True, False, 1.0), (1, 128, 1, 128, False, False, 1.0), (1, 256, 2, 128, True, False, 1.0),
     (2, 300, 2, 128, True, False, 1.0), (2, 1135, 4, 128, True, False, 1.0), (2, 1135, 4, 128, True, False, 4.0),
     (1, 128, 1, 64, False, False, 1.0), (2, 577, 4, 64, False, False, 1.0), (3, 5, 2, 64, False, False, 1.0),
+    (2, 1025, 2, 128, False, False, 1.0), (1, 1135, 2, 128, True, False, 8.0), (2, 384, 2, 128, True, False, 1.0),
     (1, 128, 1, 128, True, True, 1.0), (1, 256, 2, 128, True, True, 1.0), (2, 300, 2, 128, True, True, 1.0),
     (2, 1135, 4, 128, True, True, 1.0), (2, 687, 4, 128, True, True, 3.0),
 ]
