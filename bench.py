@@ -426,59 +426,55 @@ def full_width_parity_report():
 
 
 # ------------------------------------------------------------------------------------------------
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--micro-pairs", type=int, default=0, help="pairs per micro-batch (0 = auto)")
-    ap.add_argument("--layers", type=int, default=32, help="debug only; anything but 32 is not the benchmark")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-stash-extra", action="store_true")
-    ap.add_argument("--lora", action="store_true", help="BASELINE config (e): LoRA-DPO r=64 (not the headline line)")
-    ap.add_argument("--omnilmm", action="store_true",
-                    help="BASELINE config (d) downstream of the vision tower: resampler + Mistral-7B GQA decoder "
-                         "(not the headline line; the EVA-02 tower is not built)")
-    args = ap.parse_args()
+def eva_flops_per_image(e, batch_tokens=None):
+    """Algorithmic forward FLOPs of the EVA tower for one 448 px image (63 live blocks, 1025 tokens)."""
+    C, Hd, S = e.embed_dim, e.mlp_hidden, e.n_tokens + 1
+    per_block = 2 * S * (4 * C * C + 2 * C * Hd) + 4 * S * S * C
+    return e.live_blocks * per_block + 2 * e.n_tokens * e.patch_k * C
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.impl == "reference":
-        run_reference_arm(args, rank)
-        return
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+def run_workload(args, rank, local_rank, world, lora=False, omnilmm=False, steps=None, warmup=None, extras=False):
+    """One measured workload -> the JSON line (dict). `extras`: a reduced run used for the `extra` sub-records."""
     from rlaifv_b200 import lib, ops
     from rlaifv_b200.engine import DPOStepEngine
     from rlaifv_b200.model import LlavaDims, LlavaDPOPolicy
-
+    steps = args.steps if steps is None else steps
+    warmup = args.warmup if warmup is None else warmup
     B = PAIRS_PER_GPU
     micro = args.micro_pairs or B
-    if args.omnilmm:
+    eva = None
+    if omnilmm:
         from rlaifv_b200.omnilmm_model import OmniLMMDPOPolicy, omnilmm_dims
         dims = omnilmm_dims(num_layers=args.layers)
-        policy = OmniLMMDPOPolicy(dims, torch.device("cuda", local_rank), seed=0)
+        if not args.omnilmm_no_tower:
+            from rlaifv_b200.eva_tower import EvaDims
+            eva = EvaDims() if args.layers == 32 else EvaDims(depth=max(2, args.layers * 2))
+            if not args.micro_pairs:
+                micro = max(1, B // 2)        # whole-batch tower + decoder activations do not fit beside 12 B params
+        policy = OmniLMMDPOPolicy(dims, torch.device("cuda", local_rank), seed=0, eva_dims=eva)
     else:
         dims = LlavaDims(num_layers=args.layers)
         policy = LlavaDPOPolicy(dims, torch.device("cuda", local_rank), seed=0)
-    if args.lora:
+    if lora:
         policy.enable_lora(r=64, alpha=16)
-    engine = DPOStepEngine(policy, lr=1e-5 if args.lora else 5e-7, weight_decay=0.01, total_steps=2672, micro_pairs=micro,
+    engine = DPOStepEngine(policy, lr=1e-5 if lora else 5e-7, weight_decay=0.01, total_steps=2672, micro_pairs=micro,
                            rank=rank, world=world)
     # HBM plan: with the optimizer state sharded over >= 2 GPUs there is room to stash the normalised inputs
     # and the SwiGLU product (no recompute in the backward); one GPU holds the unsharded 81 GB state.
-    policy.stash_extra = world > 1 and not args.no_stash_extra
-    T = PROMPT_LEN + RESP_LEN - 1 + (dims.num_query + 2 if args.omnilmm else dims.num_patches)
+    policy.stash_extra = world > 1 and not args.no_stash_extra and not (omnilmm and eva is not None)
+    T = PROMPT_LEN + RESP_LEN - 1 + (dims.num_query + 2 if omnilmm else dims.num_patches)
+
+    def make_host_batch(s):
+        if not omnilmm:
+            return synthetic_batch(rank, s, B)
+        hb = synthetic_omni_batch(rank, s, B, dims)
+        if eva is not None:                   # the whole config (d): pixels in, 448 px
+            g = torch.Generator().manual_seed(4321 + 1000 * rank + s)
+            hb["images"] = torch.randn(B, 3, eva.img_size, eva.img_size, generator=g).pin_memory()
+        return hb
 
     # frozen-reference log-probs = initial policy log-probs (step-0 loss = ln 2 known answer)
-    host_batches = [synthetic_omni_batch(rank, s, B, dims) if args.omnilmm else synthetic_batch(rank, s, B)
-                    for s in range(2)]
+    host_batches = [make_host_batch(s) for s in range(2)]
     for hb in host_batches:
         rw, rr = [], []
         for lo in range(0, B, micro):
@@ -511,18 +507,18 @@ def main():
         step0 = engine.train_step(dev_batches[0], optimizer_step=False)   # known-answer check (no update)
         loss0 = float(step0[0].item())
     except torch.OutOfMemoryError:
-        # whole-batch activations did not fit next to the optimizer state: fall back to 2 micro-batches
+        # whole-batch activations did not fit next to the optimizer state: fall back to smaller micro-batches
         policy._stash = None
         policy._bufs.clear()
         policy.stash_extra = False
         torch.cuda.empty_cache()
-        micro = max(1, B // 2)
+        micro = max(1, micro // 2)
         engine.micro_pairs = micro
         step0 = engine.train_step(dev_batches[0], optimizer_step=False)
         loss0 = float(step0[0].item())
 
     # ---- device-resident timing (value) ----
-    run_steps(dev_batches, args.warmup, False)
+    run_steps(dev_batches, warmup, False)
     sampler = ClockSampler(local_rank)
     launches0 = lib.launch_count()
     barrier()
@@ -530,20 +526,20 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     t_host0 = time.perf_counter()
-    run_steps(dev_batches, args.steps, False)
-    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps   # CPU time to enqueue one step
+    run_steps(dev_batches, steps, False)
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / steps   # CPU time to enqueue one step
     e1.record()
     barrier()
-    ms_dev = e0.elapsed_time(e1) / args.steps
-    launches = (lib.launch_count() - launches0) // max(1, args.steps)
+    ms_dev = e0.elapsed_time(e1) / steps
+    launches = (lib.launch_count() - launches0) // max(1, steps)
     # ---- end-to-end timing through the public call with host buffers (e2e) ----
     run_steps(host_batches, 1, True)
     barrier()
     e0.record()
-    run_steps(host_batches, args.steps, True)
+    run_steps(host_batches, steps, True)
     e1.record()
     barrier()
-    ms_e2e = e0.elapsed_time(e1) / args.steps
+    ms_e2e = e0.elapsed_time(e1) / steps
     clocks = sampler.stop()
     t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -606,47 +602,58 @@ def main():
     gemm_flops = sum(f for _, _, f in gemm_events)
     peak_sus, peak_burst, peak_kind = measured_peaks()
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
-    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (bytes per launch of the
-    # forward qkv GEMM; the same capture lists dgrad / wgrad) — profiles/ncu_gemm_traffic.json
+    # DRAM traffic of the dominant kernel: NOT measured in this run — read from the committed `ncu --set full` capture
+    # (bytes per launch of the forward qkv GEMM; the same capture lists dgrad / wgrad) — profiles/ncu_gemm_traffic.json
     traffic, traffic_note = None, None
     tp = os.path.join(REPO, "profiles", "ncu_gemm_traffic.json")
     if os.path.exists(tp):
         with open(tp) as f:
             tj = json.load(f)["gemm"][0]
         traffic = tj["dram_bytes_per_launch"]
-        traffic_note = "%s: %.3g B DRAM per launch vs %.3g B algorithmic (ncu)" % (
-            tj["launch"], tj["dram_bytes_per_launch"], tj["algorithmic_bytes"])
+        traffic_note = "from profiles/ncu_gemm_traffic.json (ncu --set full, not measured in this run): %s: %.3g B DRAM " \
+                       "per launch vs %.3g B algorithmic" % (tj["launch"], tj["dram_bytes_per_launch"],
+                                                             tj["algorithmic_bytes"])
 
     total_pairs = B * world
     value = total_pairs / (ms_dev * 1e-3)
     e2e_value = total_pairs / (ms_e2e * 1e-3)
     hb = host_batches[0]
     h2d = sum(v.numel() * v.element_size() for v in hb.values() if torch.is_tensor(v))
-    f_pair = omni_flops_per_pair(dims, T) if args.omnilmm else flops_per_pair(T)
-    if args.lora:   # base wgrad skipped, adapters (159 907 840 params) added
+    f_pair = omni_flops_per_pair(dims, T) if omnilmm else flops_per_pair(T)
+    if omnilmm and eva is not None:
+        f_pair += 3 * eva_flops_per_image(eva)             # trainable tower: fwd + bwd = 3 x fwd, one image per pair
+    if lora:   # base wgrad skipped, adapters (159 907 840 params) added
         n_dec = 32 * (4 * 4096 ** 2 + 3 * 4096 * 11008)
         n_head = 4096 * 32000
         attn_seq = 32 * 4 * T * T * 4096 * 0.5
         f_clip = 2 * 23 * (4 * 1024 ** 2 + 2 * 1024 * 4096) * 577 + 23 * 4 * 577 ** 2 * 1024 + 2 * 588 * 1024 * 576
         f_proj = 2 * (1024 * 4096 + 4096 ** 2) * 576
         f_pair = 2 * T * (4 * (n_dec + n_head) + 6 * 159907840) + 3 * 2 * attn_seq + f_clip + 3 * f_proj
+    if omnilmm:
+        wl = ("OmniLMM-12B (RLAIF-V-12B) DPO bf16: EVA tower 448px (63 blocks, trainable) + resampler + Mistral-7B GQA "
+              "decoder, %d pairs/GPU, 512-tok responses (T=%d), ZeRO-2 AdamW" % (B, T)) if eva is not None else \
+             ("OmniLMM-12B DPO DOWNSTREAM OF THE VISION TOWER (resampler + Mistral-7B GQA decoder) bf16, %d pairs/GPU, "
+              "1024 vision tokens, 512-tok responses (T=%d), ZeRO-2 AdamW" % (B, T))
+        metric = "preference-pairs/sec OmniLMM-12B DPO step" + ("" if eva is not None else " (downstream of the vision tower)")
+    else:
+        wl = "LLaVA-1.5-7B %sDPO bf16, %d pairs/GPU, 336px, 512-tok responses (T=%d), ZeRO-2 AdamW" % (
+            "LoRA(r=64)-" if lora else "", B, T)
+        metric = "preference-pairs/sec LLaVA-1.5-7B %sDPO step" % ("LoRA-" if lora else "")
     line = {
-        "metric": ("preference-pairs/sec OmniLMM-12B DPO step (downstream of the vision tower)" if args.omnilmm
-                   else "preference-pairs/sec LLaVA-1.5-7B DPO step"), "value": value, "unit": "pairs/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev,
+        "metric": metric, "value": value, "unit": "pairs/s",
+        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_dev,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": (("OmniLMM-12B DPO DOWNSTREAM OF THE VISION TOWER (resampler + Mistral-7B GQA decoder; "
-                                 "EVA-02 tower not built) bf16, %d pairs/GPU, 1024 vision tokens, 512-tok responses "
-                                 "(T=%d), ZeRO-2 AdamW" % (B, T)) if args.omnilmm else
-                                ("LLaVA-1.5-7B %sDPO bf16, %d pairs/GPU, 336px, 512-tok responses (T=%d), ZeRO-2 AdamW"
-                                 % ("LoRA(r=64)-" if args.lora else "", B, T))),
+        "config": {"workload": wl,
                    "layers": args.layers, "pairs_per_gpu": B, "micro_pairs": micro, "parallelism": "dp%d" % world,
+                   "stash_extra": bool(policy.stash_extra), "compact_head": bool(policy.compact_head),
                    "l2": "per-step working set (>100 GB of weights/activations) is far larger than the 126 MB L2",
                    "step0_loss": loss0, "step0_loss_expected": math.log(2.0)},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 36,
                 "ms_per_step": ms_e2e},
         "hbm_peak_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
         "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms,
+        "host_enqueue_note": "wall time of the enqueue loop INCLUDING blocking on the full launch queue; the real host "
+                             "work is ~12 us per launch (profiles/r02_host_overhead.log: 13 ms per step)",
         "clocks": clocks,
         "model_flops_per_pair": f_pair,
         "step_tflops_per_gpu": value / world * f_pair / 1e12,
@@ -665,11 +672,78 @@ def main():
                          "note": "28 algorithmic bytes per parameter; timed on the optimizer side stream while the "
                                  "backward's GEMMs run concurrently"},
     }
+    # release everything this workload holds (the next workload / the checker legs need the HBM)
+    policy._stash = None
+    policy._bufs.clear()
+    engine.opt.wait_all()
+    torch.cuda.synchronize()
+    del engine, policy, dev_batches, host_batches
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    torch.cuda.reset_peak_memory_stats()
+    return line
+
+
+EXTRA_KEYS = ("metric", "value", "unit", "ms_per_step", "steps", "warmup", "e2e", "gpu_launches", "hbm_peak_gb",
+              "model_flops_per_pair", "step_tflops_per_gpu", "step_frac_of_peak", "config")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--micro-pairs", type=int, default=0, help="pairs per micro-batch (0 = auto)")
+    ap.add_argument("--layers", type=int, default=32, help="debug only; anything but 32 is not the benchmark")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stash-extra", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the `extra` sub-records (configs e and d)")
+    ap.add_argument("--lora", action="store_true", help="BASELINE config (e): LoRA-DPO r=64 as the (only) workload")
+    ap.add_argument("--omnilmm", action="store_true",
+                    help="BASELINE config (d) as the (only) workload: EVA tower + resampler + Mistral-7B GQA decoder "
+                         "(11.6 B trainable parameters: needs >= 2 GPUs for the ZeRO-2 sharded fp32 optimizer state)")
+    ap.add_argument("--omnilmm-no-tower", action="store_true",
+                    help="with --omnilmm: feed the tower's output tokens (the round-1 boundary; fits one GPU)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    line = run_workload(args, rank, local_rank, world, lora=args.lora, omnilmm=args.omnilmm)
+    headline = not (args.lora or args.omnilmm)
+    if headline and not args.no_extras:
+        # BASELINE configs (e) and (d) as driver-visible sub-records of the same run (short: 3 timed steps each).
+        # Every rank runs them (collectives inside); a failure is recorded, never raised.
+        extra = {}
+        plan = [("lora_dpo_config_e", dict(lora=True, omnilmm=False))]
+        if world >= 2:
+            plan.append(("omnilmm_12b_config_d", dict(lora=False, omnilmm=True)))
+        else:
+            extra["omnilmm_12b_config_d"] = {
+                "unavailable": "11.6 B trainable parameters x 16 B (bf16 param + grad, fp32 master/m/v) = 186 GB do not "
+                               "fit one 180 GB GPU; measured at N >= 2 (ZeRO-2 shards the 139 GB optimizer state)"}
+        for name, kw in plan:
+            try:
+                sub = run_workload(args, rank, local_rank, world, steps=3, warmup=2, extras=True, **kw)
+                extra[name] = {k: sub[k] for k in EXTRA_KEYS if k in sub}
+            except Exception as exc:                       # noqa: BLE001 - the headline line must survive
+                extra[name] = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:300])}
+                torch.cuda.empty_cache()
+        line["extra"] = extra
     if rank == 0:
-        if not args.no_cpu_baseline and world == 1 and not args.omnilmm:
-            policy._stash = None
-            policy._bufs.clear()
-            torch.cuda.empty_cache()
+        if headline and not args.no_cpu_baseline and world == 1:
             line["parity_full_width"] = full_width_parity_report()
             v, cores, kind, sample, timings = cpu_reference_pairs_per_sec(reps=2, warmup=1)
             line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": kind, "sample": sample,

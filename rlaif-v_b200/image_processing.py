@@ -92,3 +92,26 @@ class PixelValues:
     def __call__(self, image):
         import torch
         return torch.from_numpy(self.processor(image)["pixel_values"][0])
+
+
+class SquareResizeProcessor:
+    """OmniLMM's evaluation transform (`build_transform(is_train=False, input_size, std_mode='OPENAI_CLIP')`,
+    omnilmm/model/utils.py:455-460): resize to input_size x input_size (bicubic, aspect ratio NOT kept) -> [0,1] ->
+    CLIP mean/std. The training transform of the reference is the same resize preceded by a RandomResizedCrop of
+    scale (0.9999, 1) — i.e. the whole image — so the deterministic form is used for both."""
+
+    def __init__(self, input_size=448, image_mean=OPENAI_CLIP_MEAN, image_std=OPENAI_CLIP_STD):
+        self.input_size = int(input_size)
+        self.crop_size = {"height": self.input_size, "width": self.input_size}
+        self.image_mean = [float(x) for x in image_mean]
+        self.image_std = [float(x) for x in image_std]
+
+    def __call__(self, image):
+        import torch
+        from PIL import Image
+        if not isinstance(image, Image.Image):
+            image = Image.fromarray(np.asarray(image))
+        image = image.convert("RGB").resize((self.input_size, self.input_size), resample=Image.BICUBIC)
+        x = np.asarray(image, dtype=np.float32) / np.float32(255.0)
+        x = (x - np.asarray(self.image_mean, dtype=np.float32)) / np.asarray(self.image_std, dtype=np.float32)
+        return torch.from_numpy(np.ascontiguousarray(x.transpose(2, 0, 1)))

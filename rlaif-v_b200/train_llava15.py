@@ -197,7 +197,7 @@ def dims_from_checkpoint(model_dir, vision_tower_dir, select_layer, max_len):
     return LlavaDims(**kw)
 
 
-def init_model(model_args, data_args, training_args, attn_implementation=None):
+def init_model(model_args, data_args, training_args, attn_implementation=None, source_rows=None):
     """muffin/train/train_llava15.py:198-281: policy model (+ frozen reference used once for the
     log-prob pre-pass inside the dataset), tokenizer, data module."""
     from .llava_model import LlavaLlamaForCausalLM
@@ -225,11 +225,14 @@ def init_model(model_args, data_args, training_args, attn_implementation=None):
     # muffin/train/train_llava15.py:244: `lambda x: vision_tower.image_processor(x)['pixel_values'][0]`
     data_args.image_processor = PixelValues(ClipImageProcessor.from_pretrained(model_args.vision_tower,
                                                                                dims.image_size))
-    data_module = make_dpo_data_module(tokenizer=tokenizer, data_args=data_args, reference_model=model)
+    data_module = make_dpo_data_module(tokenizer=tokenizer, data_args=data_args, reference_model=model,
+                                       source_rows=source_rows)
     return model, data_module, tokenizer
 
 
-def train(attn_implementation=None, argv=None):
+def train(attn_implementation=None, argv=None, source_rows=None):
+    """`source_rows`: raw preference rows for the reference-log-prob pre-pass when `data_dir` holds no *logp* parquet
+    yet (the reference downloads openbmb/RLAIF-V-Dataset from the hub at this point, muffin/data/datasets.py:38-50)."""
     model_args, data_args, training_args = parse_args_into_dataclasses(argv)
     data_args.data_source_names = data_args.data_source_names.split("#")
     data_args.data_source_weights = [int(x) for x in data_args.data_source_weights.split("#")]
@@ -242,7 +245,7 @@ def train(attn_implementation=None, argv=None):
         # --micro_pairs splits the per-device batch with gradient accumulation in the wgrad epilogues
         raise NotImplementedError("gradient_accumulation_steps=%d: use --micro_pairs to split the per-device batch"
                                   % training_args.gradient_accumulation_steps)
-    model, data_module, tokenizer = init_model(model_args, data_args, training_args, attn_implementation)
+    model, data_module, tokenizer = init_model(model_args, data_args, training_args, attn_implementation, source_rows)
     if training_args.task != "DPO":
         raise NotImplementedError
     from .trainers import LLaVA15DPOTrainer
@@ -256,6 +259,7 @@ def train(attn_implementation=None, argv=None):
         trainer.train()
     trainer.save_state()
     safe_save_model_for_hf_trainer(trainer=trainer, output_dir=training_args.output_dir)
+    return trainer
 
 
 if __name__ == "__main__":

@@ -2,6 +2,8 @@
 backward against the restated timm model (oracle/eva_oracle.py, parity-unpinned: timm is absent), then the WHOLE
 config-(d) policy (tower -> resampler -> in-place splice -> GQA decoder -> log-probs -> DPO loss -> backward -> AdamW)
 against the composed oracle (tower restatement + the pinned OmniLMM oracle)."""
+import os
+
 import pytest
 import torch
 
@@ -157,3 +159,55 @@ def test_engine_step_trains_the_tower_too():
     eng.micro_pairs = 1
     m2 = float(eng.train_step(batch)[0])
     assert m2 == m2
+
+
+def test_train_omnilmm_entry_end_to_end(tmp_path, monkeypatch):
+    """The OmniLMM entry point on a tiny random-init checkpoint directory: reference-log-prob pre-pass -> parquet ->
+    omni_preprocess encoding (<im_start><im_patch>*Q<im_end> in place) -> collator -> trainer -> two optimisation steps
+    of the WHOLE model (tower + resampler + decoder), first loss = ln 2 (policy == reference)."""
+    import io
+    import json
+    from PIL import Image
+    from oracle.toy_tokenizer import CharChatTokenizer
+    from rlaifv_b200 import train_omnilmm as TO
+
+    class Tok(CharChatTokenizer):
+        SPECIALS = {"<im_patch>": 500, "<im_start>": 501, "<im_end>": 502, "</s>": 2}
+        unk_token = pad_token = "<unk>"
+
+        def convert_tokens_to_ids(self, toks):
+            return [self.SPECIALS[t] for t in toks]
+
+    monkeypatch.setattr(TO, "load_tokenizer", lambda path, max_len: Tok())
+    ckpt = tmp_path / "ckpt"
+    ckpt.mkdir()
+    t = E.TINY_EVA
+    (ckpt / "config.json").write_text(json.dumps({
+        "vocab_size": 512, "hidden_size": 512, "intermediate_size": 768, "num_hidden_layers": 2,
+        "num_attention_heads": 4, "num_key_value_heads": 2, "rms_norm_eps": 1e-5, "num_query": 16, "image_size": t.img_size,
+        "im_patch_token": 500, "im_start_token": 501, "im_end_token": 502,
+        "vision_tower_config": {"embed_dim": t.embed_dim, "depth": t.depth, "num_heads": t.num_heads,
+                                "mlp_hidden": t.mlp_hidden, "patch_size": t.patch_size, "pretrain_img": t.pretrain_img}}))
+    g = torch.Generator().manual_seed(0)
+    rows = []
+    words = "a red bus on the street near two small dogs and one cat under blue sky".split()
+    for i in range(4):
+        arr = (torch.rand(40 + 8 * i, 52, 3, generator=g) * 255).to(torch.uint8).numpy()
+        buf = io.BytesIO()
+        Image.fromarray(arr).save(buf, format="PNG")
+        rows.append({"image": {"bytes": buf.getvalue()}, "question": "what is in picture %d ?" % i,
+                     "chosen": " ".join(words[i:i + 5]), "rejected": " ".join(words[::-1][i:i + 3]), "idx": i,
+                     "origin_dataset": "synthetic", "origin_split": "train", "image_path": "img%d" % i})
+    out_dir = tmp_path / "out"
+    tr = TO.train(argv=["--model_name_or_path", str(ckpt), "--data_dir", str(tmp_path / "data"), "--task", "DPO",
+                        "--dpo_beta", "0.1", "--dpo_token_weight", "1.0", "--learning_rate", "1e-3", "--max_steps", "2",
+                        "--per_device_train_batch_size", "2", "--logging_steps", "1", "--save_strategy", "no",
+                        "--lr_scheduler_type", "constant", "--model_max_length", "1024", "--output_dir", str(out_dir),
+                        "--bf16", "True", "--num_query", "16", "--image_size", str(t.img_size)], source_rows=rows)
+    torch.cuda.synchronize()
+    assert sorted(os.listdir(tmp_path / "data")) == ["RLAIF-V-Dataset-withlogp_000-4.parquet"]
+    losses = [h["loss"] for h in tr.state["log_history"] if "loss" in h]
+    assert len(losses) == 2 and abs(losses[0] - 0.693147) < 5e-3 and all(l == l for l in losses)
+    sd = torch.load(out_dir / "pytorch_model.bin")
+    assert any(k.startswith("model.vision_tower.blocks.0.attn.qkv.weight") for k in sd) and "model.resampler.query" in sd
+    assert sd["model.vision_tower.blocks.0.attn.qkv.weight"].shape == (3 * t.embed_dim, t.embed_dim)    # timm layout, unpadded

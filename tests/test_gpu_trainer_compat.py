@@ -126,3 +126,58 @@ def test_train_loop_checkpoint_resume(tmp_path):
     assert float((w2.float() - w0.float()).abs().max()) > 0     # parameters moved
     t2.save_state()
     assert os.path.exists(tmp_path / "trainer_state.json")
+
+
+def test_train_llava15_entry_end_to_end(tmp_path, monkeypatch):
+    """The shipped entry point (script/train/llava15_train.sh -> rlaifv_b200.train_llava15.train) on a tiny checkpoint:
+    config.json-driven dimensions, CLIP image processor built from the vision tower's preprocessor_config.json
+    (muffin/train/train_llava15.py:244), reference-log-prob pre-pass, dataset, collator, two optimisation steps."""
+    import io
+    import json
+    from PIL import Image
+    from oracle.toy_tokenizer import ToyTokenizer
+    from rlaifv_b200 import data as D
+    from rlaifv_b200 import train_llava15 as TL
+    c = O.TINY
+    params = O.make_params(c, seed=0, scale=0.4)
+    ckpt, vt = tmp_path / "ckpt", tmp_path / "clip"
+    ckpt.mkdir()
+    vt.mkdir()
+    vp = "model.vision_tower.vision_tower."
+    torch.save({k: v for k, v in params.items() if not k.startswith(vp)}, ckpt / "pytorch_model.bin")
+    torch.save({k[len(vp):]: v for k, v in params.items() if k.startswith(vp)}, vt / "pytorch_model.bin")
+    (ckpt / "config.json").write_text(json.dumps({
+        "vocab_size": c.vocab_size, "hidden_size": c.hidden_size, "intermediate_size": c.intermediate_size,
+        "num_hidden_layers": c.num_layers, "num_attention_heads": c.num_heads, "rms_norm_eps": c.rms_eps}))
+    (vt / "config.json").write_text(json.dumps({"vision_config": {
+        "hidden_size": c.clip_hidden, "intermediate_size": c.clip_intermediate, "num_hidden_layers": c.clip_layers,
+        "num_attention_heads": c.clip_heads, "image_size": c.image_size, "patch_size": c.patch_size}}))
+    (vt / "preprocessor_config.json").write_text(json.dumps({
+        "size": {"shortest_edge": c.image_size}, "crop_size": {"height": c.image_size, "width": c.image_size},
+        "image_mean": [0.48145466, 0.4578275, 0.40821073], "image_std": [0.26862954, 0.26130258, 0.27577711]}))
+    monkeypatch.setattr(D, "load_tokenizer", lambda path, max_len: ToyTokenizer())
+    g = torch.Generator().manual_seed(1)
+    words = "a red bus on the street near two small dogs and one cat under blue sky with trees".split()
+    rows = []
+    for i in range(6):
+        arr = (torch.rand(70 + 10 * i, 90, 3, generator=g) * 255).to(torch.uint8).numpy()      # non-square: resize + crop
+        buf = io.BytesIO()
+        Image.fromarray(arr).save(buf, format="PNG")
+        rows.append({"image": {"bytes": buf.getvalue()}, "question": "what is shown in picture %d ?" % i,
+                     "chosen": " ".join(words[i:i + 6]), "rejected": " ".join(words[::-1][i:i + 4]), "idx": i,
+                     "origin_dataset": "synthetic", "origin_split": "train", "image_path": "img%d" % i})
+    out_dir = tmp_path / "out"
+    tr = TL.train(argv=["--model_name_or_path", str(ckpt), "--vision_tower", str(vt), "--mm_vision_select_layer", "-2",
+                        "--data_dir", str(tmp_path / "data"), "--data_source_names", "", "--data_source_weights", "1",
+                        "--task", "DPO", "--dpo_beta", "0.1", "--dpo_token_weight", "1.0", "--learning_rate", "1e-3",
+                        "--max_steps", "2", "--per_device_train_batch_size", "3", "--logging_steps", "1",
+                        "--save_strategy", "no", "--lr_scheduler_type", "constant", "--model_max_length", "2048",
+                        "--output_dir", str(out_dir), "--bf16", "True", "--image_aspect_ratio", "pad"], source_rows=rows)
+    torch.cuda.synchronize()
+    assert sorted(os.listdir(tmp_path / "data")) == ["RLAIF-V-Dataset-withlogp_000-6.parquet"]
+    losses = [h["loss"] for h in tr.state["log_history"] if "loss" in h]
+    assert len(losses) == 2 and abs(losses[0] - 0.693147) < 5e-3 and all(l == l for l in losses)
+    assert all(h.get("learning_rate") == 1e-3 for h in tr.state["log_history"] if "loss" in h)
+    assert os.path.exists(out_dir / "pytorch_model.bin") and os.path.exists(out_dir / "trainer_state.json")
+    rej, win = tr.train_dataset[0]
+    assert tuple(win["image"].shape) == (3, c.image_size, c.image_size) and win["image"].dtype == torch.float32

@@ -175,3 +175,42 @@ def test_zero2_partition_and_collectives_gloo_world2(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "RESULT" in o
+
+
+def test_clip_image_processor_matches_hf_processor():
+    """rlaifv_b200.image_processing.ClipImageProcessor against transformers' CLIPImageProcessor (what the reference
+    binds as `vision_tower.image_processor`, clip_encoder.py:29) with the clip-vit-large-patch14-336 settings."""
+    import numpy as np
+    from PIL import Image
+    from transformers import CLIPImageProcessor
+    from rlaifv_b200.image_processing import ClipImageProcessor, PixelValues, SquareResizeProcessor
+    hf = CLIPImageProcessor(size={"shortest_edge": 336}, crop_size={"height": 336, "width": 336}, do_resize=True,
+                            do_center_crop=True, do_normalize=True, do_convert_rgb=True, resample=3)
+    ours = ClipImageProcessor(336, 336)
+    rng = np.random.RandomState(0)
+    for (h, w) in ((500, 375), (336, 336), (200, 640), (1000, 900)):
+        img = Image.fromarray(rng.randint(0, 256, (h, w, 3), dtype=np.uint8))
+        want = np.asarray(hf(img)["pixel_values"][0])
+        got = ours(img)["pixel_values"][0]
+        assert got.shape == want.shape == (3, 336, 336) and got.dtype == np.float32
+        # transformers 5.5 resizes through its own (torch) backend; the pinned 4.35.0 processor — and this one — call
+        # PIL's bicubic resize. The two agree to fp32 rounding except for < 1 % of the pixels, which land on the other
+        # side of a uint8 rounding boundary (one or two grey levels = 0.015 / 0.03 after normalisation).
+        d = np.abs(got - want)
+        assert float(d.max()) <= 0.032 and float((d > 1e-4).mean()) <= 0.01 and float(d.mean()) <= 2e-4, (h, w)
+    pv = PixelValues(ours)
+    t = pv(Image.fromarray(rng.randint(0, 256, (50, 70), dtype=np.uint8)))       # grayscale -> RGB
+    assert tuple(t.shape) == (3, 336, 336) and pv.crop_size == {"height": 336, "width": 336}
+    sq = SquareResizeProcessor(448)(Image.fromarray(rng.randint(0, 256, (300, 500, 3), dtype=np.uint8)))
+    assert tuple(sq.shape) == (3, 448, 448) and sq.dtype == torch.float32
+
+
+def test_dims_from_checkpoint_reads_config(tmp_path):
+    import json
+    from rlaifv_b200.train_llava15 import dims_from_checkpoint
+    d = dims_from_checkpoint("liuhaotian/llava-v1.5-7b", "openai/clip-vit-large-patch14-336", -2, 2048)   # hub names: defaults
+    assert (d.hidden_size, d.num_layers, d.clip_hidden, d.image_size, d.select_layer, d.max_len) == (4096, 32, 1024, 336, -2, 2048)
+    (tmp_path / "config.json").write_text(json.dumps({"hidden_size": 256, "num_hidden_layers": 2, "num_attention_heads": 2,
+                                                      "intermediate_size": 512, "vocab_size": 512}))
+    d = dims_from_checkpoint(str(tmp_path), None, -2, 512)
+    assert (d.hidden_size, d.num_layers, d.num_heads, d.vocab_size, d.clip_hidden) == (256, 2, 2, 512, 1024)
