@@ -67,6 +67,19 @@ int rlaifv_gemm_set_split_k(int n, int min_k);
  * kernel (P through shared memory). Results agree to fp32 rounding of the online softmax. */
 int rlaifv_attention_set_variant(int fwd_variant);
 
+/* Split attention backward (default for self-attention; replaces HF autograd through the eager attention of
+ * llama/modeling_llama.py:199-222): attention_bwd_dkv_kernel (dK, dV per 128-row K/V tile) + attention_bwd_dq_kernel
+ * (dQ per 128-row Q tile, written once as bf16 — no fp32 atomics, no zero-fill). dq may be the q column block of a
+ * fused dqkv buffer (row stride ld_dq); rlaifv_rope_bwd* accepts dq_f32 == NULL to rotate that block in place.
+ * head_dim 128; causal (Sq == Skv) or not; n_kv_heads < n_heads = grouped-query attention. delta_ws fp32
+ * [nseq*n_heads*Sq]. */
+int rlaifv_attention_bwd_split(const void* q, long long ld_q, const void* k, const void* v, long long ld_kv,
+                               const void* out, long long ld_out, const void* d_out, long long ld_dout, const float* lse,
+                               void* dq, long long ld_dq, void* dk, void* dv, long long ld_dkv, float* delta_ws, int nseq,
+                               int Sq, int Skv, int n_heads, int n_kv_heads, int head_dim, int causal, float scale,
+                               void* stream);
+
+
 /* ---- attention (tcgen05, S/O accumulators in TMEM) ---------------------------------------------
  * q/k/v/out: [nseq*S][ld] bf16, head h at columns [h*head_dim, (h+1)*head_dim); lse fp32
  * [nseq][n_heads][S]. head_dim 128 (Llama, causal) or 64 (CLIP, non-causal).

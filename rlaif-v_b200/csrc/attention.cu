@@ -377,9 +377,13 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
   } else if (warp == 9) {
     // ------------------------------ MMA issuer ------------------------------
-    if (lane == 0) {
+    // The WHOLE warp runs this loop (uniform control flow, so descriptors and addresses live in uniform registers)
+    // and one elected lane issues each tcgen05 instruction. With `if (lane == 0)` around the loop every operand went
+    // through R2UR moves and ~100 cycles of single-thread address arithmetic per MMA — longer than the 64-cycle MMA.
+    {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, ATT_BKV, false, false);
       constexpr uint32_t idesc_o = make_idesc_bf16(128, D, false, true);
+      const bool leader = elect_one();
       int kv_ready = 0;                      // K/V stages 0 .. kv_ready-1 have been waited for
       auto need_kv = [&](int j) {
         while (kv_ready <= j) {
@@ -392,22 +396,30 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         need_kv(j);
         const uint32_t q_addr = smem_u32(smem + Cfg::OFF_Q + x * Cfg::Q_BYTES);
         const uint32_t k_addr = smem_u32(smem + Cfg::OFF_K + (j % STAGES) * Cfg::KV_BYTES);
+        const uint64_t qd = desc_kmajor(q_addr, 0), kd = desc_kmajor(k_addr, 0);
+        if (leader) {
 #pragma unroll
-        for (int k16 = 0; k16 < D / 16; ++k16) {
-          const uint64_t ad = desc_kmajor(q_addr + (k16 >> 2) * (ATT_BQ * 128), k16 & 3);
-          const uint64_t bd = desc_kmajor(k_addr + (k16 >> 2) * (ATT_BKV * 128), k16 & 3);
-          umma_ss(tmem_base + x * 128, ad, bd, idesc_s, k16 > 0 ? 1u : 0u);
+          for (int k16 = 0; k16 < D / 16; ++k16) {
+            // start-address field counts 16-byte units: +2 per 32-byte K step, +(rows*128/16) per 64-column atom
+            const uint64_t off = (uint64_t)((k16 >> 2) * (ATT_BQ * 128 / 16) + (k16 & 3) * 2);
+            umma_ss(tmem_base + x * 128, qd + off, kd + off, idesc_s, k16 > 0 ? 1u : 0u);
+          }
+          umma_commit(&s_full[x]);
         }
-        umma_commit(&s_full[x]);
+        __syncwarp();
       };
       auto issue_pv = [&](int x, int j) {
         const uint32_t v_addr = smem_u32(smem + Cfg::OFF_V + (j % STAGES) * Cfg::KV_BYTES);
+        const uint64_t vd = desc_mnmajor(v_addr, 0, ATT_BKV);
+        if (leader) {
 #pragma unroll
-        for (int k16 = 0; k16 < ATT_BKV / 16; ++k16) {
-          // A = P (bf16 pairs, 8 TMEM columns per 16 kv), B = V tile read MN-major
-          umma_ts(tmem_base + 256 + x * 128, tmem_base + x * 128 + k16 * 8, desc_mnmajor(v_addr, k16, ATT_BKV),
-                  idesc_o, (j > 0 || k16 > 0) ? 1u : 0u);
+          for (int k16 = 0; k16 < ATT_BKV / 16; ++k16) {
+            // A = P (bf16 pairs, 8 TMEM columns per 16 kv), B = V tile read MN-major (+2048 bytes per 16 kv rows)
+            umma_ts(tmem_base + 256 + x * 128, tmem_base + x * 128 + k16 * 8, vd + (uint64_t)(k16 * (2048 / 16)),
+                    idesc_o, (j > 0 || k16 > 0) ? 1u : 0u);
+          }
         }
+        __syncwarp();
       };
       mbar_wait(&q_full[0], 0);
       if (has_b) mbar_wait(&q_full[1], 0);
@@ -420,9 +432,10 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           tc_fence_after();
           issue_pv(x, j);
           if (j + 1 < n_of[x]) issue_s(x, j + 1);
-          else umma_commit(&o_final[x]);
+          else if (leader) umma_commit(&o_final[x]);
         }
-        umma_commit(&kv_empty[j % STAGES]);
+        if (leader) umma_commit(&kv_empty[j % STAGES]);
+        __syncwarp();
       }
     }
    }
@@ -840,6 +853,459 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   }
 }
 
+// ================================================================================================
+// backward, split form (default for self-attention): two kernels, no atomics, no fp32 dQ buffer.
+//   attention_bwd_dkv_kernel : one CTA per (128-row K/V tile, kv head, sequence); streams 64-row chunks of Q / dO;
+//                              dV += P^T dO and dK += dS^T Q accumulate in TMEM (4 MMAs per chunk).
+//   attention_bwd_dq_kernel  : one CTA per (128-row Q tile, head, sequence); streams 64-row chunks of K / V;
+//                              dQ += dS K accumulates in TMEM (3 MMAs per chunk) and is written once as bf16.
+// The fused round-1 kernel did 5 MMAs per tile pair but reduced dQ with 64 KB of fp32 red.global per pair, drained
+// through the same TMEM columns the next S^T needed: a strictly serial chain (tensor pipe 19 % active). Here the
+// recomputation of S / dP is paid twice (7 MMAs instead of 5) and everything else is pipelined:
+//   * S^T / dP^T (resp. S / dP) are 64-column chunks, double-buffered in TMEM, so the MMAs of chunk c+1 run while the
+//     compute threads turn chunk c into P / dS;
+//   * two compute warpgroups take alternate chunks;
+//   * P^T and dS^T (resp. dS) go back into the TMEM columns they came from as packed bf16 and are consumed from there
+//     as the A operand (tcgen05.mma with A in TMEM): no shared-memory staging, no proxy fence;
+//   * warps 0-3 / 4-7 = compute groups, warp 8 = TMA, warp 9 = MMA issuer; setmaxnreg moves registers to the groups.
+// ================================================================================================
+struct AttBwd2Cfg {
+  static constexpr int D = 128;
+  static constexpr int CH = 64;                                   // rows per streamed chunk
+  static constexpr int STAGES = 4;
+  static constexpr uint32_t TILE_BYTES = 128 * D * 2;             // resident [128 x 128] tile
+  static constexpr uint32_t CHUNK_BYTES = CH * D * 2;             // streamed [64 x 128] chunk
+  static constexpr uint32_t OFF_RES0 = 0;                         // dkv: K   | dq: Q
+  static constexpr uint32_t OFF_RES1 = TILE_BYTES;                // dkv: V   | dq: dO
+  static constexpr uint32_t OFF_RING = 2 * TILE_BYTES;            // [STAGES][2 chunks]: dkv Q,dO | dq K,V
+  static constexpr uint32_t OFF_STAT = OFF_RING + STAGES * 2 * CHUNK_BYTES;   // dkv: [2 groups][lse 64 | delta 64] fp32
+  static constexpr uint32_t OFF_BAR = OFF_STAT + 2 * 2 * CH * 4;
+  static constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static constexpr uint32_t TMEM_COLS = 512;
+};
+
+// K-major [rows x 128] tile made of two 64-column atoms of `rows` rows each
+__device__ __forceinline__ uint64_t desc_k_tile(uint32_t tile_addr, int k16, int rows) {
+  return desc_kmajor(tile_addr + (k16 >> 2) * (rows * 128), k16 & 3);
+}
+
+__global__ void __launch_bounds__(384, 1)
+attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                         const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                         const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dk,
+                         bf16* __restrict__ dv, long long ld_dkv, int Sq, int Skv, int n_heads, int kv_group,
+                         int causal, float scale) {
+  using Cfg = AttBwd2Cfg;
+  constexpr int D = Cfg::D, CH = Cfg::CH, STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* ring_full = bars + 1;                 // [STAGES]
+  uint64_t* ring_empty = bars + 1 + STAGES;       // [STAGES]
+  uint64_t* st_full = bars + 1 + 2 * STAGES;      // [2]  S^T / dP^T chunk ready
+  uint64_t* pt_full = st_full + 2;                // [2]  P^T / dS^T written (128 arrivals)
+  uint64_t* acc_done = pt_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kv_tile = blockIdx.x, kv_head = blockIdx.y, seq = blockIdx.z;
+  const int kv0 = kv_tile * 128;
+  const int q_begin = causal ? kv0 : 0;                            // first query row that can see this K/V tile
+  const int n_ch = (Sq - q_begin + CH - 1) / CH;                   // chunks per query head
+  const int n_it = n_ch * kv_group;
+
+  if (warp == 9) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
+      mbar_init(kv_full, 1);
+      for (int i = 0; i < STAGES; ++i) { mbar_init(&ring_full[i], 1); mbar_init(&ring_empty[i], 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&st_full[i], 1); mbar_init(&pt_full[i], 128); }
+      mbar_init(acc_done, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // columns: S^T[b] = b*64, dP^T[b] = 128 + b*64, dV = 256, dK = 384
+
+  if (warp >= 8) {
+   setmaxnreg_dec<56>();
+   if (warp == 8) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      mbar_arrive_expect_tx(kv_full, 2 * Cfg::TILE_BYTES);
+      for (int a = 0; a < 2; ++a) {
+        tma_load_3d(smem + Cfg::OFF_RES0 + a * 16384, &tmK, kv_full, kv_head * D + a * 64, kv0, seq);
+        tma_load_3d(smem + Cfg::OFF_RES1 + a * 16384, &tmV, kv_full, kv_head * D + a * 64, kv0, seq);
+      }
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it % STAGES;
+        if (it >= STAGES) mbar_wait(&ring_empty[s], ((it / STAGES) - 1) & 1);
+        const int head = kv_head * kv_group + it / n_ch;
+        const int q0 = q_begin + (it % n_ch) * CH;
+        uint8_t* dst = smem + Cfg::OFF_RING + s * 2 * Cfg::CHUNK_BYTES;
+        mbar_arrive_expect_tx(&ring_full[s], 2 * Cfg::CHUNK_BYTES);
+        for (int a = 0; a < 2; ++a) {
+          tma_load_3d(dst + a * (CH * 128), &tmQ, &ring_full[s], head * D + a * 64, q0, seq);
+          tma_load_3d(dst + Cfg::CHUNK_BYTES + a * (CH * 128), &tmDO, &ring_full[s], head * D + a * 64, q0, seq);
+        }
+      }
+    }
+   } else if (warp == 9) {
+    // ------------------------------ MMA issuer (whole warp, elected lane issues) ------------------------------
+    {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, CH, false, false);    // [128 kv x 64 q] = K-major x K-major
+      constexpr uint32_t idesc_acc = make_idesc_bf16(128, D, false, true);    // A from TMEM, B = chunk read MN-major
+      const bool leader = elect_one();
+      const uint64_t kd = desc_kmajor(smem_u32(smem + Cfg::OFF_RES0), 0), vd = desc_kmajor(smem_u32(smem + Cfg::OFF_RES1), 0);
+      auto issue_s = [&](int it) {
+        const int s = it % STAGES, b = it & 1;
+        mbar_wait(&ring_full[s], (it / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t q_addr = smem_u32(smem + Cfg::OFF_RING + s * 2 * Cfg::CHUNK_BYTES);
+        const uint64_t qd = desc_kmajor(q_addr, 0), dod = desc_kmajor(q_addr + Cfg::CHUNK_BYTES, 0);
+        if (leader) {
+#pragma unroll
+          for (int k16 = 0; k16 < D / 16; ++k16) {    // S^T = K Q^T   (16-byte units: +2 per K step, +rows*8 per atom)
+            const uint64_t oa = (uint64_t)((k16 >> 2) * (128 * 8) + (k16 & 3) * 2), ob = (uint64_t)((k16 >> 2) * (CH * 8) + (k16 & 3) * 2);
+            umma_ss(tmem_base + b * CH, kd + oa, qd + ob, idesc_s, k16 > 0);
+          }
+#pragma unroll
+          for (int k16 = 0; k16 < D / 16; ++k16) {    // dP^T = V dO^T
+            const uint64_t oa = (uint64_t)((k16 >> 2) * (128 * 8) + (k16 & 3) * 2), ob = (uint64_t)((k16 >> 2) * (CH * 8) + (k16 & 3) * 2);
+            umma_ss(tmem_base + 128 + b * CH, vd + oa, dod + ob, idesc_s, k16 > 0);
+          }
+          umma_commit(&st_full[b]);
+        }
+        __syncwarp();
+      };
+      mbar_wait(kv_full, 0);
+      issue_s(0);
+      for (int it = 0; it < n_it; ++it) {
+        if (it + 1 < n_it) issue_s(it + 1);
+        const int s = it % STAGES, b = it & 1;
+        mbar_wait(&pt_full[b], (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t q_addr = smem_u32(smem + Cfg::OFF_RING + s * 2 * Cfg::CHUNK_BYTES);
+        const uint64_t qm = desc_mnmajor(q_addr, 0, CH), dom = desc_mnmajor(q_addr + Cfg::CHUNK_BYTES, 0, CH);
+        if (leader) {
+#pragma unroll
+          for (int k16 = 0; k16 < CH / 16; ++k16)     // dV += P^T dO     (A = P^T: 8 TMEM columns per 16 q)
+            umma_ts(tmem_base + 256, tmem_base + b * CH + k16 * 8, dom + (uint64_t)(k16 * 128), idesc_acc,
+                    (it > 0 || k16 > 0));
+#pragma unroll
+          for (int k16 = 0; k16 < CH / 16; ++k16)     // dK += dS^T Q
+            umma_ts(tmem_base + 384, tmem_base + 128 + b * CH + k16 * 8, qm + (uint64_t)(k16 * 128), idesc_acc,
+                    (it > 0 || k16 > 0));
+          umma_commit(&ring_empty[s]);
+        }
+        __syncwarp();
+      }
+      if (leader) umma_commit(acc_done);
+      __syncwarp();
+    }
+   }
+  } else {
+    // ------------------------------ compute groups: thread = kv row ------------------------------
+    setmaxnreg_inc<224>();
+    const int g = warp >> 2;                       // group g takes iterations it = g, g+2, ... (TMEM buffer b = g)
+    const int r = (warp & 3) * 32 + lane;
+    const int kv_idx = kv0 + r;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tST = tmem_base + g * CH + lane_off, tDPT = tmem_base + 128 + g * CH + lane_off;
+    float* s_lse = reinterpret_cast<float*>(smem + Cfg::OFF_STAT) + g * 2 * CH;
+    float* s_delta = s_lse + CH;
+    const float c = scale * LOG2E;
+    const int tid_g = threadIdx.x & 127;
+    for (int it = g; it < n_it; it += 2) {
+      const int head = kv_head * kv_group + it / n_ch;
+      const int q0 = q_begin + (it % n_ch) * CH;
+      // stage lse / delta of the 64 query rows of this chunk (named barrier per group: ids 1, 2)
+      asm volatile("bar.sync %0, 128;" ::"r"(g + 1));
+      {
+        const int j = tid_g & 63;
+        const int q = q0 + j;
+        const long long base = ((long long)seq * n_heads + head) * Sq;
+        if (tid_g < 64) s_lse[j] = q < Sq ? lse[base + q] * LOG2E : INFINITY;     // exp2(x - inf) = 0 for padded rows
+        else s_delta[j] = q < Sq ? delta[base + q] : 0.f;
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(g + 1));
+      mbar_wait(&st_full[g], (it >> 1) & 1);
+      tc_fence_after();
+      uint32_t sv[64], dpv[64];
+      tmem_ld_32x32b_x64(tST, sv);
+      tmem_ld_32x32b_x64(tDPT, dpv);
+      tmem_wait_ld();
+      const bool diag = causal && (q0 < kv0 + 128);      // chunk overlaps the tile's diagonal block (uniform)
+      // masked keys (row beyond Skv, or above the causal diagonal) get s = -inf => p = exp2(-inf) = 0; the mask is a
+      // per-row column bound applied BEFORE the arithmetic, in a branch that only the diagonal chunks take
+      const int first_visible = kv_idx >= Skv ? 64 : (diag ? max(0, kv_idx - q0) : 0);   // columns < this are masked
+      if (first_visible > 0) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (i < first_visible) sv[i] = 0xff800000u;
+      }
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        const float pv = fast_exp2(fmaf(__uint_as_float(sv[i]), c, -s_lse[i]));
+        sv[i] = __float_as_uint(pv);
+        dpv[i] = __float_as_uint(pv * (__uint_as_float(dpv[i]) - s_delta[i]) * scale);
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t pk[16], dk_[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          pk[i] = pack_bf16(__uint_as_float(sv[h * 32 + 2 * i]), __uint_as_float(sv[h * 32 + 2 * i + 1]));
+          dk_[i] = pack_bf16(__uint_as_float(dpv[h * 32 + 2 * i]), __uint_as_float(dpv[h * 32 + 2 * i + 1]));
+        }
+        tmem_st_32x32b_x16(tST + h * 16, pk);
+        tmem_st_32x32b_x16(tDPT + h * 16, dk_);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(&pt_full[g]);
+    }
+    // epilogue: group 0 stores dV, group 1 stores dK (kv row r)
+    mbar_wait(acc_done, 0);
+    tc_fence_after();
+    {
+      const bool row_ok = kv_idx < Skv;
+      bf16* o_row = (g == 0 ? dv : dk) + ((long long)seq * Skv + kv_idx) * ld_dkv + kv_head * D;
+      const uint32_t tA = tmem_base + 256 + g * 128 + lane_off;
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t a[32];
+        tmem_ld_32x32b_x32(tA + ch * 32, a);
+        tmem_wait_ld();
+        if (row_ok) {
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            uint4 u;
+            u.x = pack_bf16(__uint_as_float(a[q4 * 8 + 0]), __uint_as_float(a[q4 * 8 + 1]));
+            u.y = pack_bf16(__uint_as_float(a[q4 * 8 + 2]), __uint_as_float(a[q4 * 8 + 3]));
+            u.z = pack_bf16(__uint_as_float(a[q4 * 8 + 4]), __uint_as_float(a[q4 * 8 + 5]));
+            u.w = pack_bf16(__uint_as_float(a[q4 * 8 + 6]), __uint_as_float(a[q4 * 8 + 7]));
+            *reinterpret_cast<uint4*>(o_row + ch * 32 + q4 * 8) = u;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+__global__ void __launch_bounds__(384, 1)
+attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                        const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dq,
+                        long long ld_dq, int Sq, int Skv, int n_heads, int kv_group, int causal, float scale) {
+  using Cfg = AttBwd2Cfg;
+  constexpr int D = Cfg::D, CH = Cfg::CH, STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* ring_full = bars + 1;
+  uint64_t* ring_empty = bars + 1 + STAGES;
+  uint64_t* s_full = bars + 1 + 2 * STAGES;       // [2]
+  uint64_t* ds_full = s_full + 2;                 // [2]  (128 arrivals)
+  uint64_t* acc_done = ds_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_q_tiles = (Sq + 127) / 128;
+  const int q_tile = num_q_tiles - 1 - (int)blockIdx.x;            // heavy (late) tiles first
+  const int head = blockIdx.y, seq = blockIdx.z;
+  const int kv_head = head / kv_group;
+  const int q0 = q_tile * 128;
+  const int kv_end = causal ? min(Skv, q0 + 128) : Skv;            // keys [0, kv_end) are visible to this tile
+  const int n_it = (kv_end + CH - 1) / CH;
+
+  if (warp == 9) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
+      mbar_init(q_full, 1);
+      for (int i = 0; i < STAGES; ++i) { mbar_init(&ring_full[i], 1); mbar_init(&ring_empty[i], 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&ds_full[i], 128); }
+      mbar_init(acc_done, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // columns: S[b] = b*64, dP[b] = 128 + b*64, dQ = 256
+
+  if (warp >= 8) {
+   setmaxnreg_dec<56>();
+   if (warp == 8) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, 2 * Cfg::TILE_BYTES);
+      for (int a = 0; a < 2; ++a) {
+        tma_load_3d(smem + Cfg::OFF_RES0 + a * 16384, &tmQ, q_full, head * D + a * 64, q0, seq);
+        tma_load_3d(smem + Cfg::OFF_RES1 + a * 16384, &tmDO, q_full, head * D + a * 64, q0, seq);
+      }
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it % STAGES;
+        if (it >= STAGES) mbar_wait(&ring_empty[s], ((it / STAGES) - 1) & 1);
+        uint8_t* dst = smem + Cfg::OFF_RING + s * 2 * Cfg::CHUNK_BYTES;
+        mbar_arrive_expect_tx(&ring_full[s], 2 * Cfg::CHUNK_BYTES);
+        for (int a = 0; a < 2; ++a) {
+          tma_load_3d(dst + a * (CH * 128), &tmK, &ring_full[s], kv_head * D + a * 64, it * CH, seq);
+          tma_load_3d(dst + Cfg::CHUNK_BYTES + a * (CH * 128), &tmV, &ring_full[s], kv_head * D + a * 64, it * CH, seq);
+        }
+      }
+    }
+   } else if (warp == 9) {
+    {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, CH, false, false);
+      constexpr uint32_t idesc_acc = make_idesc_bf16(128, D, false, true);
+      const bool leader = elect_one();
+      const uint64_t qd = desc_kmajor(smem_u32(smem + Cfg::OFF_RES0), 0), dod = desc_kmajor(smem_u32(smem + Cfg::OFF_RES1), 0);
+      auto issue_s = [&](int it) {
+        const int s = it % STAGES, b = it & 1;
+        mbar_wait(&ring_full[s], (it / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(smem + Cfg::OFF_RING + s * 2 * Cfg::CHUNK_BYTES);
+        const uint64_t kd = desc_kmajor(k_addr, 0), vd = desc_kmajor(k_addr + Cfg::CHUNK_BYTES, 0);
+        if (leader) {
+#pragma unroll
+          for (int k16 = 0; k16 < D / 16; ++k16) {    // S = Q K^T
+            const uint64_t oa = (uint64_t)((k16 >> 2) * (128 * 8) + (k16 & 3) * 2), ob = (uint64_t)((k16 >> 2) * (CH * 8) + (k16 & 3) * 2);
+            umma_ss(tmem_base + b * CH, qd + oa, kd + ob, idesc_s, k16 > 0);
+          }
+#pragma unroll
+          for (int k16 = 0; k16 < D / 16; ++k16) {    // dP = dO V^T
+            const uint64_t oa = (uint64_t)((k16 >> 2) * (128 * 8) + (k16 & 3) * 2), ob = (uint64_t)((k16 >> 2) * (CH * 8) + (k16 & 3) * 2);
+            umma_ss(tmem_base + 128 + b * CH, dod + oa, vd + ob, idesc_s, k16 > 0);
+          }
+          umma_commit(&s_full[b]);
+        }
+        __syncwarp();
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int it = 0; it < n_it; ++it) {
+        if (it + 1 < n_it) issue_s(it + 1);
+        const int s = it % STAGES, b = it & 1;
+        mbar_wait(&ds_full[b], (it >> 1) & 1);
+        tc_fence_after();
+        const uint64_t km = desc_mnmajor(smem_u32(smem + Cfg::OFF_RING + s * 2 * Cfg::CHUNK_BYTES), 0, CH);
+        if (leader) {
+#pragma unroll
+          for (int k16 = 0; k16 < CH / 16; ++k16)     // dQ += dS K   (A = dS in TMEM, B = K chunk read MN-major)
+            umma_ts(tmem_base + 256, tmem_base + 128 + b * CH + k16 * 8, km + (uint64_t)(k16 * 128), idesc_acc,
+                    (it > 0 || k16 > 0));
+          umma_commit(&ring_empty[s]);
+        }
+        __syncwarp();
+      }
+      if (leader) umma_commit(acc_done);
+      __syncwarp();
+    }
+   }
+  } else {
+    // ------------------------------ compute groups: thread = query row ------------------------------
+    setmaxnreg_inc<224>();
+    const int g = warp >> 2;
+    const int r = (warp & 3) * 32 + lane;
+    const int q_idx = q0 + r;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem_base + g * CH + lane_off, tDP = tmem_base + 128 + g * CH + lane_off;
+    const float c = scale * LOG2E;
+    const long long sbase = ((long long)seq * n_heads + head) * Sq;
+    const float my_lse = q_idx < Sq ? lse[sbase + q_idx] * LOG2E : INFINITY;
+    const float my_delta = q_idx < Sq ? delta[sbase + q_idx] : 0.f;
+    for (int it = g; it < n_it; it += 2) {
+      const int kvc = it * CH;
+      mbar_wait(&s_full[g], (it >> 1) & 1);
+      tc_fence_after();
+      uint32_t sv[64], dpv[64];
+      tmem_ld_32x32b_x64(tS, sv);
+      tmem_ld_32x32b_x64(tDP, dpv);
+      tmem_wait_ld();
+      const bool need_mask = (kvc + CH > Skv) || (causal && kvc + CH > q0);     // uniform: last chunks only
+      if (need_mask) {
+        int last_visible = Skv - 1 - kvc;                                       // columns > this are masked
+        if (causal) last_visible = min(last_visible, q_idx - kvc);
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (i > last_visible) sv[i] = 0xff800000u;                            // -inf => p = 0
+      }
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        const float pv = fast_exp2(fmaf(__uint_as_float(sv[i]), c, -my_lse));
+        dpv[i] = __float_as_uint(pv * (__uint_as_float(dpv[i]) - my_delta) * scale);
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          pk[i] = pack_bf16(__uint_as_float(dpv[h * 32 + 2 * i]), __uint_as_float(dpv[h * 32 + 2 * i + 1]));
+        tmem_st_32x32b_x16(tDP + h * 16, pk);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(&ds_full[g]);
+    }
+    // epilogue: group g stores dQ columns [g*64, g*64+64) of its row
+    mbar_wait(acc_done, 0);
+    tc_fence_after();
+    {
+      const bool row_ok = q_idx < Sq;
+      bf16* o_row = dq + ((long long)seq * Sq + q_idx) * ld_dq + head * D + g * 64;
+      const uint32_t tA = tmem_base + 256 + g * 64 + lane_off;
+#pragma unroll 1
+      for (int ch = 0; ch < 2; ++ch) {
+        uint32_t a[32];
+        tmem_ld_32x32b_x32(tA + ch * 32, a);
+        tmem_wait_ld();
+        if (row_ok) {
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            uint4 u;
+            u.x = pack_bf16(__uint_as_float(a[q4 * 8 + 0]), __uint_as_float(a[q4 * 8 + 1]));
+            u.y = pack_bf16(__uint_as_float(a[q4 * 8 + 2]), __uint_as_float(a[q4 * 8 + 3]));
+            u.z = pack_bf16(__uint_as_float(a[q4 * 8 + 4]), __uint_as_float(a[q4 * 8 + 5]));
+            u.w = pack_bf16(__uint_as_float(a[q4 * 8 + 6]), __uint_as_float(a[q4 * 8 + 7]));
+            *reinterpret_cast<uint4*>(o_row + ch * 32 + q4 * 8) = u;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+static int make_qkv_tmap_rows(CUtensorMap* tm, const void* ptr, long long ld, int nseq, int S, int cols, int box_rows) {
+  uint64_t dims[3] = {(uint64_t)cols, (uint64_t)S, (uint64_t)nseq};
+  uint64_t str[2] = {(uint64_t)ld * 2, (uint64_t)S * ld * 2};
+  uint32_t box[3] = {64, (uint32_t)box_rows, 1};
+  return make_tmap_bf16(tm, ptr, 3, dims, str, box);
+}
+
 static int make_qkv_tmap(CUtensorMap* tm, const void* ptr, long long ld, int nseq, int S, int cols) {
   uint64_t dims[3] = {(uint64_t)cols, (uint64_t)S, (uint64_t)nseq};
   uint64_t str[2] = {(uint64_t)ld * 2, (uint64_t)S * ld * 2};
@@ -971,6 +1437,59 @@ static int attention_bwd_impl(const void* q, long long ld_q, const void* k, cons
                                                                  (bf16*)dv, ld_dkv, Sq, Skv, n_heads,
                                                                  n_heads / n_kv_heads, causal, q_shared, scale);
   B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Split backward for self-attention (causal or not, Sq == Skv or not; per-sequence queries): dq is written as bf16
+// [nseq*Sq rows][ld_dq] (it may be the q column block of a fused dqkv buffer), dk/dv as before; no zero-fill needed.
+extern "C" int rlaifv_attention_bwd_split(const void* q, long long ld_q, const void* k, const void* v, long long ld_kv,
+                                          const void* out, long long ld_out, const void* d_out, long long ld_dout,
+                                          const float* lse, void* dq, long long ld_dq, void* dk, void* dv,
+                                          long long ld_dkv, float* delta_ws, int nseq, int Sq, int Skv, int n_heads,
+                                          int n_kv_heads, int head_dim, int causal, float scale, void* stream) {
+  B200_REQUIRE(head_dim == 128, "attention_bwd_split: head_dim must be 128 (got %d)", head_dim);
+  B200_REQUIRE(n_kv_heads > 0 && n_heads % n_kv_heads == 0, "attention_bwd_split: bad head counts %d / %d", n_heads,
+               n_kv_heads);
+  B200_REQUIRE(!causal || Sq == Skv, "attention_bwd_split: causal needs Sq == Skv (%d vs %d)", Sq, Skv);
+  B200_REQUIRE(nseq > 0 && Sq > 0 && Skv > 0, "attention_bwd_split: empty problem");
+  B200_REQUIRE(ld_dq % 8 == 0 && ld_dkv % 8 == 0 && ((uintptr_t)dq & 15) == 0, "attention_bwd_split: dq alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  {
+    const long long total = (long long)nseq * Sq * n_heads;
+    long long blocks = (total + 7) / 8;
+    if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
+    attention_delta_kernel<<<(int)blocks, 256, 0, st>>>((const bf16*)out, ld_out, (const bf16*)d_out, ld_dout,
+                                                        delta_ws, nseq, Sq, n_heads, head_dim);
+    B200_CHECK_CUDA(cudaGetLastError());
+  }
+  const int g = n_heads / n_kv_heads;
+  int rc;
+  CUtensorMap tq, tk, tv, tdo;
+  // dK / dV: K, V resident (128-row boxes), Q / dO streamed in 64-row chunks
+  if ((rc = make_qkv_tmap_rows(&tq, q, ld_q, nseq, Sq, n_heads * head_dim, 64))) return rc;
+  if ((rc = make_qkv_tmap_rows(&tdo, d_out, ld_dout, nseq, Sq, n_heads * head_dim, 64))) return rc;
+  if ((rc = make_qkv_tmap_rows(&tk, k, ld_kv, nseq, Skv, n_kv_heads * head_dim, 128))) return rc;
+  if ((rc = make_qkv_tmap_rows(&tv, v, ld_kv, nseq, Skv, n_kv_heads * head_dim, 128))) return rc;
+  B200_CHECK_CUDA(configure_smem_once((const void*)attention_bwd_dkv_kernel, (int)AttBwd2Cfg::SMEM_BYTES));
+  B200_CHECK_CUDA(configure_smem_once((const void*)attention_bwd_dq_kernel, (int)AttBwd2Cfg::SMEM_BYTES));
+  {
+    dim3 grid((Skv + 127) / 128, n_kv_heads, nseq);
+    attention_bwd_dkv_kernel<<<grid, 384, AttBwd2Cfg::SMEM_BYTES, st>>>(tq, tk, tv, tdo, lse, delta_ws, (bf16*)dk,
+                                                                        (bf16*)dv, ld_dkv, Sq, Skv, n_heads, g, causal,
+                                                                        scale);
+    B200_CHECK_CUDA(cudaGetLastError());
+  }
+  // dQ: Q, dO resident, K / V streamed in 64-row chunks
+  if ((rc = make_qkv_tmap_rows(&tq, q, ld_q, nseq, Sq, n_heads * head_dim, 128))) return rc;
+  if ((rc = make_qkv_tmap_rows(&tdo, d_out, ld_dout, nseq, Sq, n_heads * head_dim, 128))) return rc;
+  if ((rc = make_qkv_tmap_rows(&tk, k, ld_kv, nseq, Skv, n_kv_heads * head_dim, 64))) return rc;
+  if ((rc = make_qkv_tmap_rows(&tv, v, ld_kv, nseq, Skv, n_kv_heads * head_dim, 64))) return rc;
+  {
+    dim3 grid((Sq + 127) / 128, n_heads, nseq);
+    attention_bwd_dq_kernel<<<grid, 384, AttBwd2Cfg::SMEM_BYTES, st>>>(tq, tk, tv, tdo, lse, delta_ws, (bf16*)dq, ld_dq,
+                                                                       Sq, Skv, n_heads, g, causal, scale);
+    B200_CHECK_CUDA(cudaGetLastError());
+  }
   return 0;
 }
 

@@ -30,6 +30,7 @@ struct GemmEpilogue {
   int debug;       // profiling only: bit0 skip global stores, bit1 skip the TMEM loads as well
   int dynamic;     // 1: tiles drawn from the global counter; 0: static round-robin (tile = cta + i*grid)
   float alpha;     // != 1: result = bf16(bf16(acc) * alpha) first (LoRA scaling, peft: lora_B(...) * scaling)
+  int tma_store;   // 1: C leaves through swizzled shared memory + cp.async.bulk.tensor stores (full 128-byte rows)
 };
 
 // Optional second operand pair accumulated into the same TMEM tile after the first K loop:
@@ -45,6 +46,10 @@ struct GemmSecondSource {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 192;
+// Epilogue staging for the TMA store of C: each of the 4 epilogue warps owns two [32 rows x 64 bf16] SWIZZLE_128B
+// buffers (4 KB each, double-buffered against the asynchronous store) = 32 KB per CTA.
+constexpr uint32_t EPI_BUF_BYTES = 32 * 128;
+constexpr uint32_t EPI_STAGE_BYTES = 4 * 2 * EPI_BUF_BYTES;
 
 // Dynamic tile scheduler: CTAs pull tile indices from a global counter, so a CTA that becomes
 // resident late (an NCCL kernel of the overlapped ZeRO-2 reduce-scatter is holding its SM) simply
@@ -66,7 +71,7 @@ struct GemmCfg {
   static constexpr uint32_t B_BYTES = BN * GEMM_BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t TMEM_COLS = 2 * BN;
-  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 512 + 1024;  // + barriers/queue + align
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 512 + 1024;  // + barriers/queue + align
 };
 
 __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int GROUP_M, int& m_blk, int& n_blk) {
@@ -135,17 +140,105 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int col0
   }
 }
 
+// Same math as epilogue_chunk, but the 32 columns go to this lane's row of the warp's swizzled staging buffer
+// (`half` = which 64-byte half of the 128-byte row) instead of straight to global memory.
+__device__ __forceinline__ void epilogue_chunk_staged(const uint32_t (&r)[32], int col0, int N, const bf16* c_row,
+                                                      const bf16* r_row, const GemmEpilogue& epi, bool accumulate,
+                                                      uint8_t* stage_row, int half, int lane) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int col = col0 + g * 8;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+    if (col < N) {
+      if (epi.alpha != 1.0f) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = bf16_round(bf16_round(v[j]) * epi.alpha);
+      }
+      if (epi.bias) {
+        uint4 b4 = __ldg(reinterpret_cast<const uint4*>(epi.bias + col));
+        float2 b0 = unpack_bf16(b4.x), b1 = unpack_bf16(b4.y), b2 = unpack_bf16(b4.z), b3 = unpack_bf16(b4.w);
+        v[0] += b0.x; v[1] += b0.y; v[2] += b1.x; v[3] += b1.y;
+        v[4] += b2.x; v[5] += b2.y; v[6] += b3.x; v[7] += b3.y;
+      }
+      if (epi.act) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = apply_act(bf16_round(v[j]), epi.act);
+      }
+      if (r_row) {
+        uint4 q4 = *reinterpret_cast<const uint4*>(r_row + col);
+        float2 q0 = unpack_bf16(q4.x), q1 = unpack_bf16(q4.y), q2 = unpack_bf16(q4.z), q3 = unpack_bf16(q4.w);
+        v[0] = bf16_round(v[0]) + q0.x; v[1] = bf16_round(v[1]) + q0.y;
+        v[2] = bf16_round(v[2]) + q1.x; v[3] = bf16_round(v[3]) + q1.y;
+        v[4] = bf16_round(v[4]) + q2.x; v[5] = bf16_round(v[5]) + q2.y;
+        v[6] = bf16_round(v[6]) + q3.x; v[7] = bf16_round(v[7]) + q3.y;
+      }
+      if (accumulate) {
+        uint4 o4 = *reinterpret_cast<const uint4*>(c_row + col);
+        float2 o0 = unpack_bf16(o4.x), o1 = unpack_bf16(o4.y), o2 = unpack_bf16(o4.z), o3 = unpack_bf16(o4.w);
+        v[0] += o0.x; v[1] += o0.y; v[2] += o1.x; v[3] += o1.y;
+        v[4] += o2.x; v[5] += o2.y; v[6] += o3.x; v[7] += o3.y;
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16(v[0], v[1]);
+    o.y = pack_bf16(v[2], v[3]);
+    o.z = pack_bf16(v[4], v[5]);
+    o.w = pack_bf16(v[6], v[7]);
+    const int chunk = (half * 4 + g) ^ (lane & 7);              // SWIZZLE_128B: 16-byte chunk index XOR (row % 8)
+    *reinterpret_cast<uint4*>(stage_row + chunk * 16) = o;
+  }
+}
+
+// Epilogue of one tile for one warp (32 rows): TMEM -> registers -> (math) -> swizzled smem -> TMA store, 64 columns at
+// a time, double-buffered against the asynchronous store. row0 = first row of this warp's 32-row slab.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile_tma(uint32_t t_addr, long long row0, long long row, bool row_ok, int n0,
+                                                  int N, const GemmEpilogue& epi, const CUtensorMap* tmC,
+                                                  uint8_t* warp_stage, int lane, int& buf_sel) {
+  bf16* c_row = epi.C + row * epi.ldc;
+  const bf16* r_row = epi.residual ? epi.residual + row * epi.ldr : nullptr;
+#pragma unroll 1
+  for (int c64 = 0; c64 < BN / 64; ++c64) {
+    const int col0 = n0 + c64 * 64;
+    if (col0 >= N) break;
+    uint8_t* buf = warp_stage + buf_sel * EPI_BUF_BYTES;
+    if (lane == 0) tma_store_wait_read<1>();     // the store that last read `buf` (two issues ago) is done with it
+    __syncwarp();
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(t_addr + c64 * 64 + half * 32, r);
+      tmem_wait_ld();
+      // rows beyond M come from zero-filled OOB operand rows and are clipped by the tensor map on the way out; they
+      // must not touch the residual / C rows (addresses past the tensor)
+      epilogue_chunk_staged(r, col0 + half * 32, N, c_row, row_ok ? r_row : nullptr, epi,
+                            row_ok && epi.accumulate != 0, buf + lane * 128, half, lane);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(tmC, buf, col0, (int)row0);
+      tma_store_commit();
+    }
+    buf_sel ^= 1;
+  }
+}
+
 template <bool A_MN, bool B_MN, int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+                 const __grid_constant__ CUtensorMap tmC,
                  int M, int N, int K, GemmSecondSource src2, GemmEpilogue epi, TileCounter* ctr) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* epi_stage = smem + STAGES * Cfg::STAGE_BYTES;          // 1024-byte aligned (stage sizes are multiples)
+  uint64_t* full = reinterpret_cast<uint64_t*>(epi_stage + EPI_STAGE_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
@@ -280,8 +373,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ------------------------------ epilogue ------------------------------
     const int quad = warp & 3;
     const int row_in_tile = quad * 32 + lane;
+    uint8_t* warp_stage = epi_stage + quad * 2 * EPI_BUF_BYTES;
+    int buf_sel = 0;
     int qs = 0;
     uint32_t qph = 0;
+    if (lane == 0 && epi.tma_store) tma_prefetch_desc(&tmC);
     for (int it = 0;; ++it) {
       mbar_wait(&tq_full[qs], qph);
       const int t = tile_q[qs];
@@ -298,21 +394,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const long long row = (long long)m_blk * GEMM_BM + row_in_tile;
       const bool row_ok = row < M;
       const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
-      bf16* c_row = epi.C + row * epi.ldc;
-      const bf16* r_row = epi.residual ? epi.residual + row * epi.ldr : nullptr;
+      if (epi.tma_store && !(epi.debug & 3)) {
+        epilogue_tile_tma<BN>(t_addr, (long long)m_blk * GEMM_BM + quad * 32, row, row_ok, n_blk * BN, N, epi, &tmC,
+                              warp_stage, lane, buf_sel);
+      } else {
+        bf16* c_row = epi.C + row * epi.ldc;
+        const bf16* r_row = epi.residual ? epi.residual + row * epi.ldr : nullptr;
 #pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        if (epi.debug & 2) break;
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_addr + ch * 32, r);
-        tmem_wait_ld();
-        const int col0 = n_blk * BN + ch * 32;
-        if (row_ok && col0 < N && !(epi.debug & 1)) epilogue_chunk(r, col0, N, c_row, r_row, epi);
+        for (int ch = 0; ch < BN / 32; ++ch) {
+          if (epi.debug & 2) break;
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_addr + ch * 32, r);
+          tmem_wait_ld();
+          const int col0 = n_blk * BN + ch * 32;
+          if (row_ok && col0 < N && !(epi.debug & 1)) epilogue_chunk(r, col0, N, c_row, r_row, epi);
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
     }
+    if (lane == 0 && epi.tma_store) tma_store_wait_all<0>();     // staging smem must outlive the last bulk stores
   }
 
   tc_fence_before();
@@ -342,7 +444,7 @@ constexpr int GEMM2_STAGES = 6;
 constexpr uint32_t GEMM2_A_BYTES = 128 * GEMM_BK * 2;
 constexpr uint32_t GEMM2_B_BYTES = 128 * GEMM_BK * 2;
 constexpr uint32_t GEMM2_STAGE_BYTES = GEMM2_A_BYTES + GEMM2_B_BYTES;
-constexpr uint32_t GEMM2_SMEM_BYTES = GEMM2_STAGES * GEMM2_STAGE_BYTES + 512 + 1024;
+constexpr uint32_t GEMM2_SMEM_BYTES = GEMM2_STAGES * GEMM2_STAGE_BYTES + EPI_STAGE_BYTES + 512 + 1024;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -363,13 +465,15 @@ template <bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+                  const __grid_constant__ CUtensorMap tmC,
                   int M, int N, int K, GemmSecondSource src2, GemmEpilogue epi, TileCounter* ctr) {
   constexpr int STAGES = GEMM2_STAGES;
   constexpr int BN = 256;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * GEMM2_STAGE_BYTES);
+  uint8_t* epi_stage = smem + STAGES * GEMM2_STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(epi_stage + EPI_STAGE_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
@@ -514,8 +618,11 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ------------------------------ epilogue (both CTAs) ------------------------------
     const int quad = warp & 3;
     const int row_in_tile = (int)cta_rank * 128 + quad * 32 + lane;
+    uint8_t* warp_stage = epi_stage + quad * 2 * EPI_BUF_BYTES;
+    int buf_sel = 0;
     int qs = 0;
     uint32_t qph = 0;
+    if (lane == 0 && epi.tma_store) tma_prefetch_desc(&tmC);
     for (int it = 0;; ++it) {
       if (cta_rank == 0) mbar_wait(&tq_full[qs], qph);
       else mbar_wait_cluster(&tq_full[qs], qph);
@@ -536,16 +643,21 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const long long row = (long long)m_blk * 256 + row_in_tile;
       const bool row_ok = row < M;
       const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
-      bf16* c_row = epi.C + row * epi.ldc;
-      const bf16* r_row = epi.residual ? epi.residual + row * epi.ldr : nullptr;
+      if (epi.tma_store && !(epi.debug & 3)) {
+        epilogue_tile_tma<BN>(t_addr, (long long)m_blk * 256 + (int)cta_rank * 128 + quad * 32, row, row_ok, n_blk * BN,
+                              N, epi, &tmC, warp_stage, lane, buf_sel);
+      } else {
+        bf16* c_row = epi.C + row * epi.ldc;
+        const bf16* r_row = epi.residual ? epi.residual + row * epi.ldr : nullptr;
 #pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        if (epi.debug & 2) break;
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_addr + ch * 32, r);
-        tmem_wait_ld();
-        const int col0 = n_blk * BN + ch * 32;
-        if (row_ok && col0 < N && !(epi.debug & 1)) epilogue_chunk(r, col0, N, c_row, r_row, epi);
+        for (int ch = 0; ch < BN / 32; ++ch) {
+          if (epi.debug & 2) break;
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_addr + ch * 32, r);
+          tmem_wait_ld();
+          const int col0 = n_blk * BN + ch * 32;
+          if (row_ok && col0 < N && !(epi.debug & 1)) epilogue_chunk(r, col0, N, c_row, r_row, epi);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -554,6 +666,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         else mbar_arrive_cluster(&tempty[acc], 0);
       }
     }
+    if (lane == 0 && epi.tma_store) tma_store_wait_all<0>();     // staging smem must outlive the last bulk stores
   }
 
   tc_fence_before();
@@ -574,8 +687,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
 template <bool A_MN, bool B_MN>
 static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA2,
-                        const CUtensorMap& tmB2, int M, int N, int K, const GemmSecondSource& src2,
-                        const GemmEpilogue& epi, cudaStream_t stream) {
+                        const CUtensorMap& tmB2, const CUtensorMap& tmC, int M, int N, int K,
+                        const GemmSecondSource& src2, const GemmEpilogue& epi, cudaStream_t stream) {
   auto kern = gemm2_bf16_kernel<A_MN, B_MN>;
   B200_CHECK_CUDA(configure_smem_once((const void*)kern, (int)GEMM2_SMEM_BYTES));
   const int num_tiles = ((M + 255) / 256) * ((N + 255) / 256);
@@ -583,15 +696,15 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
   if (num_tiles < clusters) clusters = num_tiles;
   if (!g_counter_pool) B200_CHECK_CUDA(cudaGetSymbolAddress((void**)&g_counter_pool, g_tile_counters));
   TileCounter* ctr = g_counter_pool + (g_launch_seq++ & 63);
-  kern<<<clusters * 2, GEMM_THREADS, GEMM2_SMEM_BYTES, stream>>>(tmA, tmB, tmA2, tmB2, M, N, K, src2, epi, ctr);
+  kern<<<clusters * 2, GEMM_THREADS, GEMM2_SMEM_BYTES, stream>>>(tmA, tmB, tmA2, tmB2, tmC, M, N, K, src2, epi, ctr);
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 template <bool A_MN, bool B_MN, int BN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA2,
-                       const CUtensorMap& tmB2, int M, int N, int K, const GemmSecondSource& src2,
-                       const GemmEpilogue& epi, cudaStream_t stream) {
+                       const CUtensorMap& tmB2, const CUtensorMap& tmC, int M, int N, int K,
+                       const GemmSecondSource& src2, const GemmEpilogue& epi, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_bf16_kernel<A_MN, B_MN, BN>;
   B200_CHECK_CUDA(configure_smem_once((const void*)kern, (int)Cfg::SMEM_BYTES));
@@ -599,7 +712,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
   if (!g_counter_pool) B200_CHECK_CUDA(cudaGetSymbolAddress((void**)&g_counter_pool, g_tile_counters));
   TileCounter* ctr = g_counter_pool + (g_launch_seq++ & 63);
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmA2, tmB2, M, N, K, src2, epi, ctr);
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmA2, tmB2, tmC, M, N, K, src2, epi, ctr);
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -627,9 +740,11 @@ using namespace b200;
 
 static int g_group_m = 16;
 static int g_debug = 0;
+static int g_tma_store = 1;   // C through swizzled smem + cp.async.bulk.tensor stores (rlaifv_gemm_set_tuning debug bit 8 = off)
 extern "C" int rlaifv_gemm_set_tuning(int group_m, int debug) {
   if (group_m > 0) g_group_m = group_m;
-  g_debug = debug;
+  g_debug = debug & 7;
+  g_tma_store = (debug & 8) ? 0 : 1;
   return 0;
 }
 // auto-selection policy for tile_n = 0: 0 never, 1 whenever the problem is large, 2 (default) where measured faster
@@ -712,7 +827,18 @@ static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B
     rc = operand_tmap(&tmB2, B2, ldb2, b_mn_major != 0, N, K2, bn == 512 ? 128 : bn);
     if (rc) return rc;
   }
+  // C tensor map for the TMA-store epilogue: [M rows][N cols], row stride ldc, box = 64 columns x 32 rows (one
+  // epilogue warp's slab), SWIZZLE_128B like the operand tiles
+  CUtensorMap tmC = tmA;
+  int use_tma_store = g_tma_store;
+  if (use_tma_store) {
+    uint64_t cdims[2] = {(uint64_t)N, (uint64_t)M};
+    uint64_t cstr[1] = {(uint64_t)ldc * 2};
+    uint32_t cbox[2] = {64, 32};
+    if (make_tmap_bf16(&tmC, C, 2, cdims, cstr, cbox) != 0) use_tma_store = 0;    // odd view: direct stores instead
+  }
   GemmEpilogue epi;
+  epi.tma_store = use_tma_store;
   epi.C = (bf16*)C;
   epi.ldc = ldc;
   epi.bias = (const bf16*)bias;
@@ -726,18 +852,18 @@ static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B
   epi.dynamic = (g_debug & 4) ? 0 : 1;
   cudaStream_t st = (cudaStream_t)stream;
   if (bn == 512) {
-    if (!a_mn_major && !b_mn_major) return launch_gemm2<false, false>(tmA, tmB, tmA2, tmB2, M, N, K, src2, epi, st);
-    if (!a_mn_major && b_mn_major) return launch_gemm2<false, true>(tmA, tmB, tmA2, tmB2, M, N, K, src2, epi, st);
-    return launch_gemm2<true, true>(tmA, tmB, tmA2, tmB2, M, N, K, src2, epi, st);
+    if (!a_mn_major && !b_mn_major) return launch_gemm2<false, false>(tmA, tmB, tmA2, tmB2, tmC, M, N, K, src2, epi, st);
+    if (!a_mn_major && b_mn_major) return launch_gemm2<false, true>(tmA, tmB, tmA2, tmB2, tmC, M, N, K, src2, epi, st);
+    return launch_gemm2<true, true>(tmA, tmB, tmA2, tmB2, tmC, M, N, K, src2, epi, st);
   }
   if (!a_mn_major && !b_mn_major)
-    return bn == 256 ? launch_gemm<false, false, 256>(tmA, tmB, tmA2, tmB2, M, N, K, src2, epi, st)
-                     : launch_gemm<false, false, 128>(tmA, tmB, tmA2, tmB2, M, N, K, src2, epi, st);
+    return bn == 256 ? launch_gemm<false, false, 256>(tmA, tmB, tmA2, tmB2, tmC, M, N, K, src2, epi, st)
+                     : launch_gemm<false, false, 128>(tmA, tmB, tmA2, tmB2, tmC, M, N, K, src2, epi, st);
   if (!a_mn_major && b_mn_major)
-    return bn == 256 ? launch_gemm<false, true, 256>(tmA, tmB, tmA2, tmB2, M, N, K, src2, epi, st)
-                     : launch_gemm<false, true, 128>(tmA, tmB, tmA2, tmB2, M, N, K, src2, epi, st);
-  return bn == 256 ? launch_gemm<true, true, 256>(tmA, tmB, tmA2, tmB2, M, N, K, src2, epi, st)
-                   : launch_gemm<true, true, 128>(tmA, tmB, tmA2, tmB2, M, N, K, src2, epi, st);
+    return bn == 256 ? launch_gemm<false, true, 256>(tmA, tmB, tmA2, tmB2, tmC, M, N, K, src2, epi, st)
+                     : launch_gemm<false, true, 128>(tmA, tmB, tmA2, tmB2, tmC, M, N, K, src2, epi, st);
+  return bn == 256 ? launch_gemm<true, true, 256>(tmA, tmB, tmA2, tmB2, tmC, M, N, K, src2, epi, st)
+                   : launch_gemm<true, true, 128>(tmA, tmB, tmA2, tmB2, tmC, M, N, K, src2, epi, st);
 }
 
 extern "C" int rlaifv_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb,

@@ -382,7 +382,7 @@ __global__ void rope_bwd_kernel(bf16* __restrict__ dqkv, const float* __restrict
     const int pos = (int)(row % T);
     bf16* p = dqkv + row * ld + (long long)head * D + c8 * 8;
     float y1[8], y2[8], c1[8], s1[8], c2[8], s2[8];
-    if (head < nh) {
+    if (head < nh && dq_f32) {     // dq_f32 == nullptr: dQ already sits in the q block as bf16 (split backward)
       const float* q = dq_f32 + row * (long long)nh * D + head * D + c8 * 8;
       float4 a = *reinterpret_cast<const float4*>(q), b = *reinterpret_cast<const float4*>(q + 4);
       float4 c = *reinterpret_cast<const float4*>(q + half), d = *reinterpret_cast<const float4*>(q + half + 4);

@@ -328,13 +328,10 @@ class EvaTower:
             ops.colsum(da, G[f"b{i}.proj_b"], accumulate=acc)
             datt = ops.gemm(da, P[f"b{i}.proj_w"], self.buf("datt", (M, HP)), b_mn=True)
             qkv = bs["qkv"]
-            dq32 = self.buf("dq32", (M, HP), _F32)
-            dq32.zero_()
             dqkv = self.buf("dqkv", (M, 3 * HP))
-            ops.cross_attention_bwd(qkv[:, :HP], qkv[:, HP:2 * HP], qkv[:, 2 * HP:], bs["att"], datt, bs["lse"], B, S, S,
-                                    nh, PADDED_HEAD, scale, dq32, dqkv[:, HP:2 * HP], dqkv[:, 2 * HP:], q_shared=False,
+            ops.attention_bwd_split(qkv[:, :HP], qkv[:, HP:2 * HP], qkv[:, 2 * HP:], bs["att"], datt, bs["lse"], B, S, S,
+                                    nh, PADDED_HEAD, False, scale, dqkv[:, :HP], dqkv[:, HP:2 * HP], dqkv[:, 2 * HP:],
                                     delta_ws=self.buf("delta", (B, nh, S), _F32))
-            ops.f32_to_bf16_2d(dq32, dqkv[:, :HP])
             ops.gemm(dqkv, bs["x"], G[f"b{i}.qkv_w"], a_mn=True, b_mn=True, accumulate=acc)
             if acc:
                 kb_old = G[f"b{i}.qkv_b"][HP:2 * HP].clone()

@@ -28,6 +28,9 @@ _SIGNATURES = {
                               c_void_p],
     "rlaifv_gemm_set_2cta": [c_int],
     "rlaifv_attention_set_variant": [c_int],
+    "rlaifv_attention_bwd_split": [c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_void_p,
+                                   c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                   c_int, c_int, c_float, c_void_p],
     "rlaifv_gemm_set_tuning": [c_int, c_int],
     "rlaifv_gemm_set_split_k": [c_int, c_int],
     "rlaifv_rmsnorm_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p],

@@ -361,6 +361,8 @@ class LlavaDPOPolicy:
         # (forward_logps); inference / the reference log-prob pre-pass keep the full head (per-token values of every
         # position are part of the parquet contract)
         self.compact_head = True
+        # attention backward as two kernels (dK/dV, dQ) without fp32 atomics; False = the fused round-1 kernel
+        self.split_attention_bwd = True
         self.embed_grad_f32 = None   # fp32 scatter target for embedding rows (allocated lazily)
         self._stash = None
         self.lora = None             # LoraStore: base weights frozen, adapters + mm_projector trainable
@@ -721,13 +723,20 @@ class LlavaDPOPolicy:
             # ---- attention ----
             datt = self._lin_bwd(i, "o", dx2, ls["att"], self.buf("datt", (M, H)), ls, acc)
             qkv = ls["qkv"]
-            dq32 = self.buf("dq32", (M, H), _F32)
-            dq32.zero_()
             dqkv = self.buf("dqkv", (M, H + 2 * KV))
-            ops.attention_bwd(qkv[:, :H], qkv[:, H:H + KV], qkv[:, H + KV:], ls["att"], datt, ls["lse"], nseq, T, nh, hd,
-                              scale, dq32, dqkv[:, H:H + KV], dqkv[:, H + KV:], self.buf("delta", (nseq, nh, T), _F32),
-                              n_kv_heads=nkv)
-            ops.rope_bwd(dqkv, dq32, cos, sin, T, nh, hd, n_kv_heads=nkv)
+            if self.split_attention_bwd:
+                # dK/dV kernel + dQ kernel: dQ lands in the q block of dqkv as bf16, rotated back in place
+                ops.attention_bwd_split(qkv[:, :H], qkv[:, H:H + KV], qkv[:, H + KV:], ls["att"], datt, ls["lse"], nseq,
+                                        T, T, nh, hd, True, scale, dqkv[:, :H], dqkv[:, H:H + KV], dqkv[:, H + KV:],
+                                        n_kv_heads=nkv, delta_ws=self.buf("delta", (nseq, nh, T), _F32))
+                ops.rope_bwd(dqkv, None, cos, sin, T, nh, hd, n_kv_heads=nkv)
+            else:
+                dq32 = self.buf("dq32", (M, H), _F32)
+                dq32.zero_()
+                ops.attention_bwd(qkv[:, :H], qkv[:, H:H + KV], qkv[:, H + KV:], ls["att"], datt, ls["lse"], nseq, T, nh,
+                                  hd, scale, dq32, dqkv[:, H:H + KV], dqkv[:, H + KV:],
+                                  self.buf("delta", (nseq, nh, T), _F32), n_kv_heads=nkv)
+                ops.rope_bwd(dqkv, dq32, cos, sin, T, nh, hd, n_kv_heads=nkv)
             n1 = ls["n1"] if "n1" in ls else ops.rmsnorm_fwd(ls["x"], P[f"l{i}.ln1"], d.rms_eps,
                                                              out=self.buf("n", (M, H)))             # recompute
             dn1 = self._lin_bwd(i, "qkv", dqkv, n1, self.buf("dn", (M, H)), ls, acc)

@@ -97,6 +97,21 @@ def attention_bwd(q, k, v, out, d_out, lse, nseq, S, n_heads, head_dim, scale, d
     return dq_f32, dk, dv
 
 
+def attention_bwd_split(q, k, v, out, d_out, lse, nseq, Sq, Skv, n_heads, head_dim, causal, scale, dq, dk, dv,
+                        n_kv_heads=None, delta_ws=None):
+    """Split backward (dK/dV kernel + dQ kernel, no atomics): dq bf16 [nseq*Sq, n_heads*head_dim] (may be the q column
+    block of a fused dqkv buffer), dk/dv bf16 views sharing a row stride. Nothing needs zero-filling."""
+    _chk(q), _chk(k), _chk(v), _chk(out), _chk(d_out), _chk(dq), _chk(dk), _chk(dv), _chk(lse, torch.float32)
+    assert dk.stride(0) == dv.stride(0) and k.stride(0) == v.stride(0) and q.stride(1) == 1 and dq.stride(1) == 1
+    if delta_ws is None:
+        delta_ws = torch.empty((nseq, n_heads, Sq), dtype=torch.float32, device=q.device)
+    _l.call("rlaifv_attention_bwd_split", _l.ptr(q), q.stride(0), _l.ptr(k), _l.ptr(v), k.stride(0), _l.ptr(out),
+            out.stride(0), _l.ptr(d_out), d_out.stride(0), _l.ptr(lse), _l.ptr(dq), dq.stride(0), _l.ptr(dk), _l.ptr(dv),
+            dk.stride(0), _l.ptr(delta_ws), nseq, Sq, Skv, n_heads, n_heads if n_kv_heads is None else n_kv_heads,
+            head_dim, int(causal), float(scale), _l.stream_ptr())
+    return dq, dk, dv
+
+
 def cross_attention_fwd(q, k, v, nseq, Sq, Skv, n_heads, head_dim, scale, q_shared=True, out=None, lse=None):
     """Non-causal cross-attention: q [(1 if q_shared else nseq)*Sq, ld_q], k/v [nseq*Skv, ld_kv] (column blocks of
     one buffer allowed) -> out [nseq*Sq, n_heads*head_dim], lse [nseq, n_heads, Sq]."""
@@ -204,7 +219,10 @@ def rope_fwd(qkv, cos, sin, T, n_heads, head_dim, n_kv_heads=None):
 
 
 def rope_bwd(dqkv, dq_f32, cos, sin, T, n_heads, head_dim, n_kv_heads=None):
-    _chk(dqkv), _chk(dq_f32, _f32)
+    """dq_f32 None: the q block of dqkv already holds dQ (bf16, split attention backward) and is rotated in place."""
+    _chk(dqkv)
+    if dq_f32 is not None:
+        _chk(dq_f32, _f32)
     _l.call("rlaifv_rope_bwd_gqa", _l.ptr(dqkv), _l.ptr(dq_f32), _l.ptr(cos), _l.ptr(sin), dqkv.shape[0], T,
             n_heads, n_heads if n_kv_heads is None else n_kv_heads, head_dim, dqkv.stride(0), _l.stream_ptr())
     return dqkv

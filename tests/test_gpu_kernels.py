@@ -130,6 +130,39 @@ def test_attention_backward():
     assert rel(split(dqkv[:, 2 * H:]), v.grad) <= 3e-2
 
 
+@pytest.mark.parametrize("nseq,S,nh,nkv,causal", [(2, 687, 2, 2, True), (2, 300, 4, 2, True), (2, 1025, 2, 2, False),
+                                                  (3, 70, 2, 2, False), (1, 64, 1, 1, True)])
+def test_attention_backward_split_kernels(nseq, S, nh, nkv, causal):
+    """dK/dV kernel + dQ kernel (no atomics): dq written as bf16 into the q block of a NaN-poisoned fused buffer."""
+    from rlaifv_b200 import ops
+    D = 128
+    H, KV = nh * D, nkv * D
+    qkv = torch.randn(nseq * S, H + 2 * KV, device=DEV).to(BF)
+    scale = D ** -0.5
+    q_, k_, v_ = qkv[:, :H], qkv[:, H:H + KV], qkv[:, H + KV:]
+    if causal:
+        out, lse = ops.attention_fwd(q_, k_, v_, nseq, S, nh, D, True, scale, n_kv_heads=nkv)
+    else:
+        out, lse = ops.cross_attention_fwd(q_, k_, v_, nseq, S, S, nh, D, scale, q_shared=False)
+    d_out = torch.randn(nseq * S, H, device=DEV).to(BF)
+    dqkv = torch.full((nseq * S, H + 2 * KV), float("nan"), device=DEV, dtype=BF)
+    ops.attention_bwd_split(q_, k_, v_, out, d_out, lse, nseq, S, S, nh, D, causal, scale, dqkv[:, :H], dqkv[:, H:H + KV],
+                            dqkv[:, H + KV:], n_kv_heads=nkv)
+
+    def split(t, n):
+        return t.float().reshape(nseq, S, n, D).permute(0, 2, 1, 3).contiguous()
+    q, k, v = split(q_, nh).requires_grad_(), split(k_, nkv).requires_grad_(), split(v_, nkv).requires_grad_()
+    g = nh // nkv
+    s = q @ k.repeat_interleave(g, 1).transpose(-1, -2) * scale
+    if causal:
+        s = s.masked_fill(~torch.ones(S, S, device=DEV, dtype=torch.bool).tril(), float("-inf"))
+    (torch.softmax(s, -1) @ v.repeat_interleave(g, 1)).backward(split(d_out, nh))
+    assert torch.isfinite(dqkv.float()).all()
+    assert rel(split(dqkv[:, :H], nh), q.grad) <= 3e-2
+    assert rel(split(dqkv[:, H:H + KV], nkv), k.grad) <= 3e-2
+    assert rel(split(dqkv[:, H + KV:], nkv), v.grad) <= 3e-2
+
+
 # ------------------------------------------------------------------------------------------------ row kernels
 def test_rmsnorm_forward_backward():
     from rlaifv_b200 import ops

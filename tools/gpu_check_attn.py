@@ -47,14 +47,23 @@ def run(nseq, S, nh, D, causal, bwd=False, qscale=1.0):
     check("attn_fwd lse " + tag, lse, rl, 2e-3)
     if bwd:
         d_out = torch.randn(nseq * S, H, device=dev).bfloat16()
-        dq32 = torch.zeros(nseq * S, H, device=dev, dtype=torch.float32)
-        dqkv = torch.zeros(nseq * S, 3 * H, device=dev, dtype=torch.bfloat16)
-        ops.attention_bwd(q, k, v, out, d_out, lse, nseq, S, nh, D, scale, dq32, dqkv[:, H:2 * H], dqkv[:, 2 * H:])
-        torch.cuda.synchronize()
         ro.backward(split(d_out))
-        check("attn_bwd dq " + tag, split(dq32), qf.grad, 3e-2)
-        check("attn_bwd dk " + tag, split(dqkv[:, H:2 * H]), kf.grad, 3e-2)
-        check("attn_bwd dv " + tag, split(dqkv[:, 2 * H:]), vf.grad, 3e-2)
+        if causal:                                    # the fused round-1 kernel's entry point is causal-only
+            dq32 = torch.zeros(nseq * S, H, device=dev, dtype=torch.float32)
+            dqkv = torch.zeros(nseq * S, 3 * H, device=dev, dtype=torch.bfloat16)
+            ops.attention_bwd(q, k, v, out, d_out, lse, nseq, S, nh, D, scale, dq32, dqkv[:, H:2 * H], dqkv[:, 2 * H:])
+            torch.cuda.synchronize()
+            check("attn_bwd dq " + tag, split(dq32), qf.grad, 3e-2)
+            check("attn_bwd dk " + tag, split(dqkv[:, H:2 * H]), kf.grad, 3e-2)
+            check("attn_bwd dv " + tag, split(dqkv[:, 2 * H:]), vf.grad, 3e-2)
+        # split backward (dK/dV kernel + dQ kernel), dq as bf16 in the q block of a fused buffer (poisoned first)
+        d2 = torch.full((nseq * S, 3 * H), float("nan"), device=dev, dtype=torch.bfloat16)
+        ops.attention_bwd_split(q, k, v, out, d_out, lse, nseq, S, S, nh, D, causal, scale, d2[:, :H], d2[:, H:2 * H],
+                                d2[:, 2 * H:])
+        torch.cuda.synchronize()
+        check("attn_bwd_split dq " + tag, split(d2[:, :H]), qf.grad, 3e-2)
+        check("attn_bwd_split dk " + tag, split(d2[:, H:2 * H]), kf.grad, 3e-2)
+        check("attn_bwd_split dv " + tag, split(d2[:, 2 * H:]), vf.grad, 3e-2)
 
 cases = [
     (1, 128, 1, 128, True, False, 1.0), (1, 128, 1, 128, False, False, 1.0), (1, 256, 2, 128, True, False, 1.0),
@@ -62,7 +71,8 @@ cases = [
     (1, 128, 1, 64, False, False, 1.0), (2, 577, 4, 64, False, False, 1.0), (3, 5, 2, 64, False, False, 1.0),
     (2, 1025, 2, 128, False, False, 1.0), (1, 1135, 2, 128, True, False, 8.0), (2, 384, 2, 128, True, False, 1.0),
     (1, 128, 1, 128, True, True, 1.0), (1, 256, 2, 128, True, True, 1.0), (2, 300, 2, 128, True, True, 1.0),
-    (2, 1135, 4, 128, True, True, 1.0), (2, 687, 4, 128, True, True, 3.0),
+    (2, 1135, 4, 128, True, True, 1.0), (2, 687, 4, 128, True, True, 3.0), (2, 1025, 2, 128, False, True, 1.0),
+    (3, 70, 2, 128, False, True, 1.0), (1, 64, 1, 128, True, True, 1.0),
 ]
 for cse in cases:
     try:
@@ -72,7 +82,7 @@ for cse in cases:
         fails += 1
         break
 
-def bench(nseq, S, nh, D, causal, bwd):
+def bench(nseq, S, nh, D, causal, bwd, split=False):
     H = nh * D
     qkv = torch.randn(nseq * S, 3 * H, device=dev).bfloat16()
     q, k, v = qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:]
@@ -82,7 +92,10 @@ def bench(nseq, S, nh, D, causal, bwd):
     dq32 = torch.zeros(nseq * S, H, device=dev, dtype=torch.float32)
     dqkv = torch.zeros(nseq * S, 3 * H, device=dev, dtype=torch.bfloat16)
     def f():
-        if bwd:
+        if bwd and split:
+            ops.attention_bwd_split(q, k, v, out, d_out, lse, nseq, S, S, nh, D, causal, scale, dqkv[:, :H],
+                                    dqkv[:, H:2 * H], dqkv[:, 2 * H:])
+        elif bwd:
             ops.attention_bwd(q, k, v, out, d_out, lse, nseq, S, nh, D, scale, dq32, dqkv[:, H:2 * H], dqkv[:, 2 * H:])
         else:
             ops.attention_fwd(q, k, v, nseq, S, nh, D, causal, scale, out, lse)
@@ -94,12 +107,13 @@ def bench(nseq, S, nh, D, causal, bwd):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
     fl = 4.0 * nseq * nh * S * S * D * (0.5 if causal else 1.0) * (2.5 if bwd else 1.0)
-    print(f"perf attn {'bwd' if bwd else 'fwd'} nseq={nseq} S={S} nh={nh} D={D} causal={causal}: {ms:.3f} ms {fl/ms/1e9:.0f} TFLOP/s (algorithmic)", flush=True)
+    print(f"perf attn {('bwd_split' if split else 'bwd') if bwd else 'fwd'} nseq={nseq} S={S} nh={nh} D={D} causal={causal}: {ms:.3f} ms {fl/ms/1e9:.0f} TFLOP/s (algorithmic)", flush=True)
 
 if fails == 0:
     try:
         bench(16, 1135, 32, 128, True, False)
         bench(16, 1135, 32, 128, True, True)
+        bench(16, 1135, 32, 128, True, True, split=True)
         bench(16, 577, 16, 64, False, False)
     except Exception as e:
         print("EXCEPTION", repr(e), flush=True); fails += 1

@@ -1,0 +1,61 @@
+"""In-process A/B of step-level switches on the config-(b) DPO step (same process, same box, alternating settings —
+the only comparison that is reliable on the power-capped part):
+  tma_store  : GEMM epilogue through swizzled smem + cp.async.bulk.tensor stores (1) vs direct 16-byte stores (0)
+  split_bwd  : attention backward as dK/dV + dQ kernels (1) vs the fused kernel with fp32 dQ atomics (0)
+  fwd_variant: attention forward ping-pong kernel (1) vs single-tile kernel (0)
+
+    python tools/gpu_step_ab.py
+"""
+import itertools
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import bench
+from rlaifv_b200 import lib
+from rlaifv_b200.engine import DPOStepEngine
+from rlaifv_b200.model import LlavaDims, LlavaDPOPolicy
+
+L = lib.load()
+B = bench.PAIRS_PER_GPU
+pol = LlavaDPOPolicy(LlavaDims(), torch.device("cuda", 0), seed=0)
+eng = DPOStepEngine(pol, lr=5e-7, total_steps=2672, micro_pairs=B)
+hb = bench.synthetic_batch(0, 0, B)
+out = pol.forward_logps(hb["concatenated_input_ids"], hb["concatenated_labels"], hb["images"], keep_stash=False)
+hb["ref_win_logp"], hb["ref_rej_logp"] = out["logp"][:B].float().cpu(), out["logp"][B:].float().cpu()
+batch = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in hb.items()}
+
+
+def setting(tma, split, fwd):
+    L.rlaifv_gemm_set_tuning(0, 0 if tma else 8)
+    pol.split_attention_bwd = bool(split)
+    L.rlaifv_attention_set_variant(fwd)
+
+
+def measure(n=4):
+    eng.train_step(batch)
+    eng.opt.wait_all()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        eng.train_step(batch)
+    eng.opt.wait_all()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+for _ in range(2):
+    eng.train_step(batch)
+configs = [(1, 1, 1), (0, 1, 1), (1, 0, 1), (0, 0, 1), (0, 0, 0)]
+res = {c: [] for c in configs}
+for rnd in range(3):
+    for c in configs:
+        setting(*c)
+        res[c].append(measure())
+for c in configs:
+    print("tma_store=%d split_bwd=%d fwd_variant=%d : %s ms/step" % (c + (["%.1f" % t for t in res[c]],)))
+setting(1, 1, 1)

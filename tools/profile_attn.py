@@ -27,5 +27,9 @@ for _ in range(2):
 if "--bwd" in sys.argv:
     for _ in range(2):
         ops.attention_bwd(q, k, v, out, d_out, lse, nseq, S, nh, D, scale, dq32, dqkv[:, H:2 * H], dqkv[:, 2 * H:])
+if "--bwd-split" in sys.argv:
+    for _ in range(2):
+        ops.attention_bwd_split(q, k, v, out, d_out, lse, nseq, S, S, nh, D, True, scale, dqkv[:, :H], dqkv[:, H:2 * H],
+                                dqkv[:, 2 * H:])
 torch.cuda.synchronize()
 print("done")
