@@ -27,6 +27,17 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+// same, also returning the elected lane's id (to broadcast a value the leader produced)
+__device__ __forceinline__ bool elect_one_lane(uint32_t& leader_lane) {
+  uint32_t pred, ll;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync %1|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(pred), "=r"(ll));
+  leader_lane = ll;
+  return pred != 0;
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

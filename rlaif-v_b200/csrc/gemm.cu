@@ -289,17 +289,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
-    if (lane == 0) {
+    // The whole warp runs the loop (uniform control flow: coordinates / addresses stay in uniform registers); one
+    // elected lane issues the barrier operations and the bulk-tensor copies (elect.sync is what lets ptxas keep the
+    // single-thread region on the uniform datapath instead of R2UR-converting every operand).
+    {
+      uint32_t leader_lane;
+      const bool leader = elect_one_lane(leader_lane);
       int s = 0;
       uint32_t ph = 0;
       int qs = 0;
       uint32_t qph = 0;
       for (int iter = 0;; ++iter) {
-        int t = epi.dynamic ? (int)atomicAdd(&ctr->next, 1u) : (int)(blockIdx.x + iter * gridDim.x);
+        int t = 0;
+        if (leader) t = epi.dynamic ? (int)atomicAdd(&ctr->next, 1u) : (int)(blockIdx.x + iter * gridDim.x);
+        t = __shfl_sync(0xffffffffu, t, leader_lane);
         if (t >= num_tiles) t = -1;
         mbar_wait(&tq_empty[qs], qph ^ 1);
-        tile_q[qs] = t;
-        mbar_arrive(&tq_full[qs]);
+        if (leader) {
+          tile_q[qs] = t;
+          mbar_arrive(&tq_full[qs]);
+        }
         if (++qs == GEMM_TQ) { qs = 0; qph ^= 1; }
         if (t < 0) break;
         int m_blk, n_blk;
@@ -309,34 +318,37 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
           uint8_t* b_dst = a_dst + Cfg::A_BYTES;
-          mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
           const bool second = kb >= num_k1;
           const CUtensorMap* mA = second ? &tmA2 : &tmA;
           const CUtensorMap* mB = second ? &tmB2 : &tmB;
           const int kB = (second ? kb - num_k1 : kb) * GEMM_BK;                      // k index into B
           const int kA = second ? kB + (src2.n_sub > 0 ? (n0 / src2.n_sub) * src2.r : 0) : kB;   // into A
-          if (A_MN) {
+          if (leader) {
+            mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
+            if (A_MN) {
 #pragma unroll
-            for (int a = 0; a < GEMM_BM / 64; ++a)
-              tma_load_2d(a_dst + a * (GEMM_BK * 128), mA, &full[s], m0 + a * 64, kA);
-          } else {
-            tma_load_2d(a_dst, mA, &full[s], kA, m0);
-          }
-          if (B_MN) {
+              for (int a = 0; a < GEMM_BM / 64; ++a)
+                tma_load_2d(a_dst + a * (GEMM_BK * 128), mA, &full[s], m0 + a * 64, kA);
+            } else {
+              tma_load_2d(a_dst, mA, &full[s], kA, m0);
+            }
+            if (B_MN) {
 #pragma unroll
-            for (int a = 0; a < BN / 64; ++a)
-              tma_load_2d(b_dst + a * (GEMM_BK * 128), mB, &full[s], n0 + a * 64, kB);
-          } else {
-            tma_load_2d(b_dst, mB, &full[s], kB, n0);
+              for (int a = 0; a < BN / 64; ++a)
+                tma_load_2d(b_dst + a * (GEMM_BK * 128), mB, &full[s], n0 + a * 64, kB);
+            } else {
+              tma_load_2d(b_dst, mB, &full[s], kB, n0);
+            }
           }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------ MMA issuer ------------------------------
-    if (lane == 0) {
+    // ------------------------------ MMA issuer (whole warp loops, lane 0 issues) ------------------------------
+    {
       constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, A_MN, B_MN);
+      const bool leader = elect_one();
       int s = 0;
       uint32_t ph = 0;
       int qs = 0;
@@ -344,7 +356,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int it = 0;; ++it) {
         mbar_wait(&tq_full[qs], qph);
         const int t = tile_q[qs];
-        mbar_arrive(&tq_empty[qs]);
+        __syncwarp();
+        if (leader) mbar_arrive(&tq_empty[qs]);
         if (++qs == GEMM_TQ) { qs = 0; qph ^= 1; }
         if (t < 0) break;
         const int acc = it & 1;
@@ -357,14 +370,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
           const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+          // descriptors of the stage once; per UMMA_K step the start-address field (16-byte units) advances by 2
+          // (K-major: 32 bytes) or 128 (MN-major: 16 rows of 128 bytes)
+          const uint64_t ad0 = A_MN ? desc_mnmajor(a_addr, 0, GEMM_BK) : desc_kmajor(a_addr, 0);
+          const uint64_t bd0 = B_MN ? desc_mnmajor(b_addr, 0, GEMM_BK) : desc_kmajor(b_addr, 0);
+          if (leader) {
 #pragma unroll
-          for (int k16 = 0; k16 < GEMM_BK / 16; ++k16) {
-            const uint64_t adesc = A_MN ? desc_mnmajor(a_addr, k16, GEMM_BK) : desc_kmajor(a_addr, k16);
-            const uint64_t bdesc = B_MN ? desc_mnmajor(b_addr, k16, GEMM_BK) : desc_kmajor(b_addr, k16);
-            umma_ss(d_tmem, adesc, bdesc, idesc, (kb > 0 || k16 > 0) ? 1u : 0u);
+            for (int k16 = 0; k16 < GEMM_BK / 16; ++k16)
+              umma_ss(d_tmem, ad0 + (uint64_t)(k16 * (A_MN ? 128 : 2)), bd0 + (uint64_t)(k16 * (B_MN ? 128 : 2)), idesc,
+                      (kb > 0 || k16 > 0) ? 1u : 0u);
+            umma_commit(&empty[s]);  // smem slot is free once these MMAs have read it
+            if (kb == num_k - 1) umma_commit(&tfull[acc]);
           }
-          umma_commit(&empty[s]);  // smem slot is free once these MMAs have read it
-          if (kb == num_k - 1) umma_commit(&tfull[acc]);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -521,26 +538,33 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------ TMA producer (both CTAs); the leader's also schedules tiles ------------------
-    if (lane == 0) {
+    // ------------------------------ TMA producer (both CTAs); the leader CTA's also schedules tiles ------------------
+    // whole warp loops, one elected lane issues (see gemm_bf16_kernel)
+    {
+      uint32_t leader_lane;
+      const bool leader = elect_one_lane(leader_lane);
       int s = 0;
       uint32_t ph = 0;
       int qs = 0;
       uint32_t qph = 0;
       for (int iter = 0;; ++iter) {
-        int t;
+        int t = 0;
         if (cta_rank == 0) {
-          t = epi.dynamic ? (int)atomicAdd(&ctr->next, 1u) : (int)((blockIdx.x >> 1) + iter * num_clusters);
+          if (leader) t = epi.dynamic ? (int)atomicAdd(&ctr->next, 1u) : (int)((blockIdx.x >> 1) + iter * num_clusters);
+          t = __shfl_sync(0xffffffffu, t, leader_lane);
           if (t >= num_tiles) t = -1;
           mbar_wait_cluster(&tq_empty[qs], qph ^ 1);
-          tile_q[qs] = t;
-          st_shared_cluster_u32(const_cast<int*>(&tile_q[qs]), 1, (uint32_t)t);
-          mbar_arrive(&tq_full[qs]);
-          mbar_arrive_cluster_release(&tq_full[qs], 1);
+          if (leader) {
+            tile_q[qs] = t;
+            st_shared_cluster_u32(const_cast<int*>(&tile_q[qs]), 1, (uint32_t)t);
+            mbar_arrive(&tq_full[qs]);
+            mbar_arrive_cluster_release(&tq_full[qs], 1);
+          }
         } else {
           mbar_wait_cluster(&tq_full[qs], qph);
           t = tile_q[qs];
-          mbar_arrive_cluster_release(&tq_empty[qs], 0);
+          __syncwarp();
+          if (leader) mbar_arrive_cluster_release(&tq_empty[qs], 0);
         }
         if (++qs == GEMM_TQ) { qs = 0; qph ^= 1; }
         if (t < 0) break;
@@ -553,35 +577,38 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           uint8_t* a_dst = smem + s * GEMM2_STAGE_BYTES;
           uint8_t* b_dst = a_dst + GEMM2_A_BYTES;
           const uint32_t leader_full = mapa_u32(smem_u32(&full[s]), 0);
-          if (cta_rank == 0) mbar_arrive_expect_tx(&full[s], 2 * GEMM2_STAGE_BYTES);
-          else mbar_arrive_cluster(&full[s], 0);
           const bool second = kb >= num_k1;
           const CUtensorMap* mA = second ? &tmA2 : &tmA;
           const CUtensorMap* mB = second ? &tmB2 : &tmB;
           const int kB = (second ? kb - num_k1 : kb) * GEMM_BK;
           const int kA = second ? kB + (src2.n_sub > 0 ? ((n_blk * BN) / src2.n_sub) * src2.r : 0) : kB;
-          if (A_MN) {
+          if (leader) {
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full[s], 2 * GEMM2_STAGE_BYTES);
+            else mbar_arrive_cluster(&full[s], 0);
+            if (A_MN) {
 #pragma unroll
-            for (int a = 0; a < 2; ++a)
-              tma_load_2d_2sm(a_dst + a * (GEMM_BK * 128), mA, leader_full, m0 + a * 64, kA);
-          } else {
-            tma_load_2d_2sm(a_dst, mA, leader_full, kA, m0);
-          }
-          if (B_MN) {
+              for (int a = 0; a < 2; ++a)
+                tma_load_2d_2sm(a_dst + a * (GEMM_BK * 128), mA, leader_full, m0 + a * 64, kA);
+            } else {
+              tma_load_2d_2sm(a_dst, mA, leader_full, kA, m0);
+            }
+            if (B_MN) {
 #pragma unroll
-            for (int a = 0; a < 2; ++a)
-              tma_load_2d_2sm(b_dst + a * (GEMM_BK * 128), mB, leader_full, n0 + a * 64, kB);
-          } else {
-            tma_load_2d_2sm(b_dst, mB, leader_full, kB, n0);
+              for (int a = 0; a < 2; ++a)
+                tma_load_2d_2sm(b_dst + a * (GEMM_BK * 128), mB, leader_full, n0 + a * 64, kB);
+            } else {
+              tma_load_2d_2sm(b_dst, mB, leader_full, kB, n0);
+            }
           }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------ MMA issuer (leader CTA only) ------------------------------
-    if (lane == 0 && cta_rank == 0) {
+    // ------------------------------ MMA issuer (leader CTA only; whole warp loops, elected lane issues) ------------
+    if (cta_rank == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(256, BN, A_MN, B_MN);
+      const bool leader = elect_one();
       int s = 0;
       uint32_t ph = 0;
       int qs = 0;
@@ -589,7 +616,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int it = 0;; ++it) {
         mbar_wait(&tq_full[qs], qph);
         const int t = tile_q[qs];
-        mbar_arrive(&tq_empty[qs]);
+        __syncwarp();
+        if (leader) mbar_arrive(&tq_empty[qs]);
         if (++qs == GEMM_TQ) { qs = 0; qph ^= 1; }
         if (t < 0) break;
         const int acc = it & 1;
@@ -602,14 +630,16 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * GEMM2_STAGE_BYTES);
           const uint32_t b_addr = a_addr + GEMM2_A_BYTES;
+          const uint64_t ad0 = A_MN ? desc_mnmajor(a_addr, 0, GEMM_BK) : desc_kmajor(a_addr, 0);
+          const uint64_t bd0 = B_MN ? desc_mnmajor(b_addr, 0, GEMM_BK) : desc_kmajor(b_addr, 0);
+          if (leader) {
 #pragma unroll
-          for (int k16 = 0; k16 < GEMM_BK / 16; ++k16) {
-            const uint64_t adesc = A_MN ? desc_mnmajor(a_addr, k16, GEMM_BK) : desc_kmajor(a_addr, k16);
-            const uint64_t bdesc = B_MN ? desc_mnmajor(b_addr, k16, GEMM_BK) : desc_kmajor(b_addr, k16);
-            umma_ss_2sm(d_tmem, adesc, bdesc, idesc, (kb > 0 || k16 > 0) ? 1u : 0u);
+            for (int k16 = 0; k16 < GEMM_BK / 16; ++k16)
+              umma_ss_2sm(d_tmem, ad0 + (uint64_t)(k16 * (A_MN ? 128 : 2)), bd0 + (uint64_t)(k16 * (B_MN ? 128 : 2)),
+                          idesc, (kb > 0 || k16 > 0) ? 1u : 0u);
+            umma_commit_2sm(&empty[s], 0x3);
+            if (kb == num_k - 1) umma_commit_2sm(&tfull[acc], 0x3);
           }
-          umma_commit_2sm(&empty[s], 0x3);
-          if (kb == num_k - 1) umma_commit_2sm(&tfull[acc], 0x3);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
