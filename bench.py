@@ -462,6 +462,8 @@ def run_workload(args, rank, local_rank, world, lora=False, omnilmm=False, steps
     # HBM plan: with the optimizer state sharded over >= 2 GPUs there is room to stash the normalised inputs
     # and the SwiGLU product (no recompute in the backward); one GPU holds the unsharded 81 GB state.
     policy.stash_extra = world > 1 and not args.no_stash_extra and not (omnilmm and eva is not None)
+    # one GPU, full fine-tuning: room for the SwiGLU product only (peak ~172 of 180 GB); OOM falls back below
+    policy.stash_act = world == 1 and not lora and not omnilmm and not args.no_stash_extra
     T = PROMPT_LEN + RESP_LEN - 1 + (dims.num_query + 2 if omnilmm else dims.num_patches)
 
     def make_host_batch(s):
@@ -510,10 +512,13 @@ def run_workload(args, rank, local_rank, world, lora=False, omnilmm=False, steps
         # whole-batch activations did not fit next to the optimizer state: fall back to smaller micro-batches
         policy._stash = None
         policy._bufs.clear()
-        policy.stash_extra = False
         torch.cuda.empty_cache()
-        micro = max(1, micro // 2)
-        engine.micro_pairs = micro
+        if policy.stash_act:
+            policy.stash_act = False            # first give back the optional stash, keep the whole-batch pass
+        else:
+            policy.stash_extra = False
+            micro = max(1, micro // 2)
+            engine.micro_pairs = micro
         step0 = engine.train_step(dev_batches[0], optimizer_step=False)
         loss0 = float(step0[0].item())
 
@@ -645,7 +650,8 @@ def run_workload(args, rank, local_rank, world, lora=False, omnilmm=False, steps
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": wl,
                    "layers": args.layers, "pairs_per_gpu": B, "micro_pairs": micro, "parallelism": "dp%d" % world,
-                   "stash_extra": bool(policy.stash_extra), "compact_head": bool(policy.compact_head),
+                   "stash_extra": bool(policy.stash_extra), "stash_act": bool(policy.stash_act),
+                   "compact_head": bool(policy.compact_head),
                    "l2": "per-step working set (>100 GB of weights/activations) is far larger than the 126 MB L2",
                    "step0_loss": loss0, "step0_loss_expected": math.log(2.0)},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 36,

@@ -206,6 +206,10 @@ int rlaifv_f32_to_bf16_2d(const float* in, long long ld_in, void* out, long long
  * rows_gather: out[r] = x[row_pos[r]] (zeros for -1); rows_scatter: dx[row_pos[r]] = dy[r] (dx pre-zeroed).
  * logp_fwd_rows / logp_bwd_rows: the log-prob gather and its in-place backward on logits [n_rows][ld] of the gathered
  * rows; per_tok [nseq][T-1] pre-zeroed, lse [n_rows]; token_weight / norm nullable (token-weighted and average modes). */
+/* Token weights [nseq][Lw] in TEXT positions (collator: weight i belongs to token i+1) -> [nseq][T-1] in SPLICED
+ * positions via the splice map src [nseq][T] (image rows / padding -> 1). Extension beyond the reference, which refuses
+ * --dpo_token_weighted for LLaVA-1.5 (muffin/train/trainers.py:246-248). */
+int rlaifv_splice_token_weight(const int* src, const float* token_weight, float* out, int nseq, int Lw, int T, void* stream);
 int rlaifv_supervised_rows(const long long* labels, int nseq, int T, int cap, int* row_pos, void* stream);
 int rlaifv_rows_gather(const int* row_pos, const void* x, void* out, long long n_rows, int H, void* stream);
 int rlaifv_rows_scatter(const int* row_pos, const void* dy, void* dx, long long n_rows, int H, void* stream);

@@ -95,6 +95,10 @@ class DataCollatorForDPODataset:
     tokenizer: Any
     beta: float
     mod_token_weight: float
+    # Extension (off = the reference's 20 keys, bit-exact): also emit the UN-truncated reference per-token log-probs.
+    # For LLaVA-1.5 the cached lists are in spliced positions (length n - 1 + 575) and the reference's cut at L - 1
+    # (train_muffin.py:78-81) drops their tail — one of the two reasons it refuses --dpo_token_weighted for LLaVA.
+    keep_spliced_per_token: bool = False
 
     def __call__(self, instances: Sequence[Dict]) -> Dict[str, torch.Tensor]:
         batch = preference_collator_fn(instances, self.tokenizer.pad_token_id)
@@ -110,6 +114,8 @@ class DataCollatorForDPODataset:
             need = batch[f"{kind}_input_ids"].size(1) - 1     # logits of the last token are unused
             assert padded.size(1) >= need, f"{padded.size(1)} >= {need}"
             batch[f"ref_{kind}_per_token_logp"] = padded[:, :need]
+            if self.keep_spliced_per_token:
+                batch[f"ref_{kind}_per_token_logp_spliced"] = padded
             per_tok[kind] = torch.ones_like(batch[f"ref_{kind}_per_token_logp"])
         for i, (w, r) in enumerate(zip(batch["win_input_ids"], batch["rej_input_ids"])):
             r_mod, w_mod = get_diff_ids(r[1:].tolist(), w[1:].tolist(), min_match_size=3)

@@ -963,6 +963,21 @@ logp_bwd_weighted_kernel(bf16* __restrict__ logits, long long ld, const long lon
   }
 }
 
+// Token weights through the image splice (extension: --dpo_token_weighted for LLaVA-1.5, which the reference refuses
+// because its collator's weights are in TEXT positions while the log-probs are in SPLICED positions,
+// muffin/train/train_muffin.py:78-81 / trainers.py:246-248). out[s][t] = weight of spliced token t+1: the text weight
+// tw[s][j-1] when that token is text token j >= 1 (src >= 0), 1 for image rows / padding (masked by the labels anyway).
+__global__ void splice_token_weight_kernel(const int* __restrict__ src, const float* __restrict__ tw, float* __restrict__ out,
+                                           int nseq, int Lw, int T) {
+  const long long total = (long long)nseq * (T - 1);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int s = (int)(idx / (T - 1)), t = (int)(idx % (T - 1));
+    const int j = src[(long long)s * T + t + 1];
+    out[idx] = (j >= 1 && j - 1 < Lw) ? tw[(long long)s * Lw + j - 1] : 1.0f;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Compact lm_head: only positions whose NEXT token carries a label contribute to get_batch_logps
 // (muffin/eval/muffin_inference_logp.py:93-104: loss_mask = labels[:, 1:] != -100), i.e. 512 of the 1135 positions
@@ -1387,6 +1402,13 @@ extern "C" int rlaifv_logp_fwd(const void* logits, long long ld, const long long
   logp_fwd_kernel<<<grid, LOGP_THREADS, 0, ST>>>((const bf16*)logits, ld, labels, nseq, T, V, per_tok, lse, nullptr, 0);
   B200_CHECK_CUDA(cudaGetLastError());
   logp_reduce_kernel<<<nseq, 256, 0, ST>>>(per_tok, labels, nseq, T, logp_sum, logp_avg, count);
+  B200_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int rlaifv_splice_token_weight(const int* src, const float* token_weight, float* out, int nseq, int Lw, int T,
+                                          void* stream) {
+  B200_REQUIRE(nseq > 0 && Lw > 0 && T >= 2, "splice_token_weight: bad shape");
+  splice_token_weight_kernel<<<grid_for((long long)nseq * (T - 1), 256), 256, 0, ST>>>(src, token_weight, out, nseq, Lw, T);
   B200_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -217,7 +217,8 @@ def make_dpo_data_module(tokenizer, data_args, reference_model, source_rows=None
     train = DPODataset(tokenizer, data_args.data_dir, cfg, reference_model, source_rows)
     print(f"Train data size is {len(train)}", flush=True)
     collator = DataCollatorForDPODataset(tokenizer=tokenizer, beta=data_args.dpo_beta,
-                                         mod_token_weight=data_args.dpo_token_weight)
+                                         mod_token_weight=data_args.dpo_token_weight,
+                                         keep_spliced_per_token=bool(getattr(data_args, "keep_spliced_per_token", False)))
     return dict(train_dataset=train, eval_dataset=None, data_collator=collator)
 
 

@@ -35,11 +35,12 @@ class DPOStepEngine:
         self.base_lr, self.total_steps, self.warmup_ratio = lr, total_steps, warmup_ratio
         self.constant_lr = constant_lr
         self.dpo_use_average = dpo_use_average
-        # --dpo_token_weighted (muffin/train/trainers.py:246-261): log-probs become token-weighted sums; the reference
-        # refuses it for LLaVA-1.5 (:246-248), so it is only accepted for the OmniLMM policy
+        # --dpo_token_weighted (muffin/train/trainers.py:246-261): log-probs become token-weighted sums. The reference
+        # refuses it for LLaVA-1.5 (:246-248: weights live in text positions, log-probs in spliced positions). Here the
+        # LLaVA policy maps the weights through the splice (ops.splice_token_weight) and reduces the cached reference
+        # per-token log-probs with the same spliced weights; it needs the collator's keep_spliced_per_token=True keys.
         self.dpo_token_weighted = dpo_token_weighted
-        if dpo_token_weighted and policy.dims.frontend == "clip_mlp":
-            raise NotImplementedError("dpo_token_weighted with LLaVA-1.5 (the reference raises too, trainers.py:246-248)")
+        self._spliced_weights = dpo_token_weighted and policy.dims.frontend == "clip_mlp"
         self.micro_pairs = micro_pairs
         # HF Trainer._prepare_inputs casts every floating input to bf16 under DeepSpeed-bf16, which
         # rounds the reference log-probs (|logp| ~ 5e3 -> granularity 32) before dpo_loss. The drop-in
@@ -98,8 +99,20 @@ class DPOStepEngine:
         ids = self._h2d(batch["concatenated_input_ids"])
         labels = self._h2d(batch["concatenated_labels"])
         images = self._h2d(batch["images"])
-        tw = None
-        if self.dpo_token_weighted:
+        tw = ref_pt = None
+        if self._spliced_weights:
+            if "ref_win_per_token_logp_spliced" not in batch:
+                raise KeyError("dpo_token_weighted on the LLaVA policy needs the un-truncated reference per-token "
+                               "log-probs: DataCollatorForDPODataset(keep_spliced_per_token=True)")
+            tw = self._h2d(batch["concatenated_token_weight"]).to(_F32).contiguous()       # [2B, L-1], text positions
+            pw_, pr_ = batch["ref_win_per_token_logp_spliced"], batch["ref_rej_per_token_logp_spliced"]
+            n = max(pw_.shape[1], pr_.shape[1])
+            ref_pt = torch.zeros((2 * pw_.shape[0], n), dtype=_F32, device=pw_.device)
+            ref_pt[: pw_.shape[0], : pw_.shape[1]] = pw_
+            ref_pt[pw_.shape[0]:, : pr_.shape[1]] = pr_
+            ref_pt = self._h2d(ref_pt)
+            rw = rr = None
+        elif self.dpo_token_weighted:
             from .trainers import compute_weighted_logp     # host tensors from the collator, [B, L-1] each
             rw = self._h2d(compute_weighted_logp(batch["ref_win_per_token_logp"], batch["win_labels"],
                                                  batch["win_token_weight"], self.dpo_use_average)).to(_F32)
@@ -110,7 +123,7 @@ class DPOStepEngine:
             key = "avg_logp" if self.dpo_use_average else "logp"
             rw = self._h2d(batch["ref_win_" + key]).to(_F32)
             rr = self._h2d(batch["ref_rej_" + key]).to(_F32)
-        if self.hf_deepspeed_input_cast:
+        if self.hf_deepspeed_input_cast and rw is not None:
             rw = rw.to(torch.bfloat16).to(_F32)
             rr = rr.to(torch.bfloat16).to(_F32)
         beta = float(batch["beta"])
@@ -134,12 +147,24 @@ class DPOStepEngine:
             out = pol.forward_logps(mids, mlab, images[lo:hi], keep_stash=True)
             lp = out["avg_logp"] if self.dpo_use_average else out["logp"]
             mtw = wsum = None
+            mrw, mrr = (rw[lo:hi].contiguous(), rr[lo:hi].contiguous()) if rw is not None else (None, None)
             if tw is not None:
                 mtw = torch.cat([tw[lo:hi], tw[B + lo:B + hi]], 0).contiguous()
+                if self._spliced_weights:
+                    T = out["T"]
+                    mtw = ops.splice_token_weight(pol._stash["src"], mtw, T)              # text -> spliced positions
+                    mref = torch.zeros((2 * b, T - 1), dtype=_F32, device=mtw.device)
+                    n = min(T - 1, ref_pt.shape[1])
+                    mref[:b, :n] = ref_pt[lo:hi, :n]
+                    mref[b:, :n] = ref_pt[B + lo:B + hi, :n]
+                    rlw, raw_, _ = ops.logp_weighted_reduce(mref, out["labels"], mtw)       # reference side, same weights
+                    rsel = raw_ if self.dpo_use_average else rlw
+                    mrw, mrr = rsel[:b].contiguous(), rsel[b:].contiguous()
+                    if self.hf_deepspeed_input_cast:
+                        mrw, mrr = mrw.to(torch.bfloat16).to(_F32), mrr.to(torch.bfloat16).to(_F32)
                 lw, aw, wsum = ops.logp_weighted_reduce(out["per_token_logps"], out["labels"], mtw)
                 lp = aw if self.dpo_use_average else lw
-            _, _, _, dpw, dpr, out9 = ops.dpo_loss(lp[:b].contiguous(), lp[b:].contiguous(), rw[lo:hi].contiguous(),
-                                                   rr[lo:hi].contiguous(), beta, dpo_w, sft_w,
+            _, _, _, dpw, dpr, out9 = ops.dpo_loss(lp[:b].contiguous(), lp[b:].contiguous(), mrw, mrr, beta, dpo_w, sft_w,
                                                    grad_scale=(b / B) / self.world)
             self._metrics.add_(out9, alpha=b / B)
             pol.backward_logps(torch.cat([dpw, dpr]).contiguous(), use_average=self.dpo_use_average,

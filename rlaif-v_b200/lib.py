@@ -58,6 +58,7 @@ _SIGNATURES = {
                               c_void_p],
     "rlaifv_f32_to_bf16": [c_void_p, c_void_p, c_ll, c_int, c_void_p],
     "rlaifv_f32_to_bf16_2d": [c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_int, c_void_p],
+    "rlaifv_splice_token_weight": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "rlaifv_supervised_rows": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "rlaifv_rows_gather": [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p],
     "rlaifv_rows_scatter": [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p],

@@ -357,6 +357,9 @@ class LlavaDPOPolicy:
         # True: also stash the normalised inputs and the SwiGLU product (22 KB/token/layer more memory,
         # 3 fewer row passes per layer in the backward). The engine turns it on when HBM allows.
         self.stash_extra = False
+        # middle ground for one GPU (unsharded 81 GB optimizer state): stash only the SwiGLU product (22 KB/token/layer,
+        # 12.8 GB at config b) — saves the largest of the three recompute passes
+        self.stash_act = False
         # training forward sends only the supervised positions through final norm / lm_head / log-softmax
         # (forward_logps); inference / the reference log-prob pre-pass keep the full head (per-token values of every
         # position are part of the parquet contract)
@@ -590,12 +593,15 @@ class LlavaDPOPolicy:
                                  out=torch.empty((M, H), dtype=_BF, device=dev) if extra else self.buf("n", (M, H)),
                                  rstd=rstd2)
             self._lin_fwd(i, "gu", n2, gu, ls=ls if keep_stash else None)
-            act = ops.swiglu_fwd(gu, torch.empty((M, F), dtype=_BF, device=dev) if extra else self.buf("act", (M, F)))
+            keep_act = extra or (keep_stash and self.stash_act)
+            act = ops.swiglu_fwd(gu, torch.empty((M, F), dtype=_BF, device=dev) if keep_act else self.buf("act", (M, F)))
             self._lin_fwd(i, "down", act, x3, residual=x2, ls=ls if keep_stash else None)
             if keep_stash:
                 ls.update(qkv=qkv, att=att, x2=x2, gu=gu, rstd1=rstd1, rstd2=rstd2, lse=lse)
                 if extra:
                     ls.update(n1=n1, n2=n2, act=act)
+                elif keep_act:
+                    ls.update(act=act)
                 st["layers"].append(ls)
             x = x3
         return x

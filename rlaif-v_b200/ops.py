@@ -379,6 +379,16 @@ def logp_fwd(logits, labels, nseq, T):
     return per_tok, lse, s, a, c
 
 
+def splice_token_weight(src, token_weight, T):
+    """token_weight fp32 [nseq, Lw] (text positions) -> fp32 [nseq, T-1] in spliced positions (src int32 [nseq, T])."""
+    _chk(token_weight, _f32)
+    assert src.dtype == torch.int32 and src.is_contiguous() and token_weight.is_contiguous() and src.shape[1] == T
+    nseq, Lw = token_weight.shape
+    out = torch.empty((nseq, T - 1), dtype=_f32, device=src.device)
+    _l.call("rlaifv_splice_token_weight", _l.ptr(src), _l.ptr(token_weight), _l.ptr(out), nseq, Lw, T, _l.stream_ptr())
+    return out
+
+
 def supervised_rows(labels, cap):
     """labels [nseq, T] int64 (spliced) -> row_pos int32 [nseq*cap]: flat positions s*T+t whose NEXT token is
     supervised (the rows get_batch_logps keeps), -1 in the unused slots of each sequence's cap-sized segment."""

@@ -222,6 +222,8 @@ def init_model(model_args, data_args, training_args, attn_implementation=None, s
     tokenizer = load_tokenizer(model_args.model_name_or_path, training_args.model_max_length)
     data_args.is_multimodal = True
     data_args.image_token_len = dims.num_patches
+    # extension: --dpo_token_weighted on LLaVA-1.5 needs the un-truncated (spliced-position) reference per-token lists
+    data_args.keep_spliced_per_token = bool(training_args.dpo_token_weighted)
     # muffin/train/train_llava15.py:244: `lambda x: vision_tower.image_processor(x)['pixel_values'][0]`
     data_args.image_processor = PixelValues(ClipImageProcessor.from_pretrained(model_args.vision_tower,
                                                                                dims.image_size))

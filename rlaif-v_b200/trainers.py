@@ -207,6 +207,7 @@ class LLaVA15DPOTrainer:
                                     betas=(getattr(a, "adam_beta1", 0.9), getattr(a, "adam_beta2", 0.999)),
                                     eps=getattr(a, "adam_epsilon", 1e-8), total_steps=max(1, a.max_steps),
                                     warmup_ratio=a.warmup_ratio, dpo_use_average=a.dpo_use_average,
+                                    dpo_token_weighted=bool(getattr(a, "dpo_token_weighted", False)),
                                     micro_pairs=getattr(a, "micro_pairs", None), rank=self.rank, world=self.world,
                                     hf_deepspeed_input_cast=bool(getattr(a, "bf16", True) and getattr(a, "deepspeed", None)),
                                     constant_lr=getattr(a, "lr_scheduler_type", "cosine") == "constant")

@@ -194,8 +194,18 @@ def test_engine_token_weighted_step_and_llava_refusal():
                                      num_heads=c.num_heads, clip_hidden=c.clip_hidden,
                                      clip_intermediate=c.clip_intermediate, clip_layers=c.clip_layers,
                                      clip_heads=c.clip_heads, image_size=c.image_size, patch_size=c.patch_size), "cuda")
-    with pytest.raises(NotImplementedError):                # the reference refuses it for LLaVA-1.5 too
-        DPOStepEngine(llava, dpo_token_weighted=True)
+    # LLaVA-1.5: the drop-in seam keeps the reference's refusal (trainers.py:246-248); the ENGINE accepts it as an
+    # extension but only with the collator's un-truncated (spliced-position) reference per-token log-probs
+    from types import SimpleNamespace
+    from rlaifv_b200 import trainers as TR
+    with pytest.raises(NotImplementedError):
+        TR.get_beta_and_logps({}, SimpleNamespace(policy=llava), SimpleNamespace(dpo_token_weighted=True, dpo_use_average=False,
+                                                                                 task="DPO"), is_llava15=True)
+    eng_l = DPOStepEngine(llava, dpo_token_weighted=True)
+    with pytest.raises(KeyError):
+        eng_l.train_step({"concatenated_input_ids": torch.zeros(2, 8, dtype=torch.long),
+                          "concatenated_labels": torch.zeros(2, 8, dtype=torch.long),
+                          "images": torch.zeros(1, 3, c.image_size, c.image_size), "beta": 0.1})
 
 
 @pytest.mark.parametrize("case", ["omni_ragged_b2", "omni_weighted_b2"])

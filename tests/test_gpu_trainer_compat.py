@@ -230,3 +230,78 @@ def test_reference_compute_loss_text_on_rebound_seam(tmp_path):
         assert abs(names[k] - md[k]) <= 1e-5 * max(1.0, abs(md[k])), k
     g_engine = model2.policy.store.grad.float()
     assert float((g_bridge - g_engine).norm() / g_engine.norm()) <= 1e-3
+
+
+def test_llava_token_weighted_extension_matches_spliced_oracle():
+    """--dpo_token_weighted on the LLaVA policy (an EXTENSION: the reference raises NotImplementedError for it,
+    trainers.py:246-248, because its collator's weights are in text positions and the per-token log-probs in spliced
+    positions). The engine maps the collator's weights through the splice and applies compute_weighted_logp
+    (trainers.py:128-137) to policy AND cached reference per-token log-probs in spliced positions; checked against the
+    same arithmetic done with the oracle's tensors, and against the unweighted path when every weight is 1."""
+    from rlaifv_b200.collator import DataCollatorForDPODataset
+    from rlaifv_b200.engine import DPOStepEngine
+    from rlaifv_b200.llava_model import LlavaLlamaForCausalLM
+    c = O.TINY
+    params = O.make_params(c, seed=0, scale=0.4)
+    B = 2
+    inst = instances(B, seed=7)
+    # make the pair share most tokens, so the diff-based weights are non-trivial (3.0 on modified spans)
+    for rej, win in inst:
+        n = min(len(rej["input_ids"]), len(win["input_ids"]))
+        rej["input_ids"][6:n - 6] = win["input_ids"][6:n - 6]
+        rej["labels"] = torch.where(rej["labels"] != -100, rej["input_ids"], rej["labels"])
+    # cached reference per-token log-probs in SPLICED positions, as the pre-pass stores them
+    g = torch.Generator().manual_seed(3)
+    for rej, win in inst:
+        for d, kind in ((rej, "rej"), (win, "win")):
+            n_sp = len(d["input_ids"]) - 1 + c.num_patches
+            d[f"ref_{kind}_per_token_logp"] = (-2.0 + 0.5 * torch.randn(n_sp - 1, generator=g)).tolist()
+    coll = DataCollatorForDPODataset(tokenizer=Tok(), beta=0.1, mod_token_weight=3.0, keep_spliced_per_token=True)
+    batch = coll(inst)
+    assert len(batch) == 22 and float(batch["concatenated_token_weight"].max()) == 3.0
+    model = LlavaLlamaForCausalLM(dims(), "cuda", hf_state=params)
+    eng = DPOStepEngine(model.policy, lr=1e-3, total_steps=4, constant_lr=True, dpo_token_weighted=True)
+    m = eng.train_step(dict(batch), optimizer_step=False)
+    md = eng.metrics_dict(m)
+    torch.cuda.synchronize()
+    # --- the same arithmetic with the oracle's (bf16-order) per-token log-probs ---
+    pb = {k: v.to(torch.bfloat16) for k, v in params.items()}
+    ids, labels = batch["concatenated_input_ids"], batch["concatenated_labels"]
+    with torch.no_grad():
+        ob = O.policy_logps(pb, c, ids, labels, batch["images"].to(torch.bfloat16))
+    src, T = ob["src"], ob["labels"].shape[1]
+    tw = batch["concatenated_token_weight"].float()
+    w_sp = torch.ones(2 * B, T - 1)
+    for s_ in range(2 * B):
+        for t in range(T - 1):
+            j = int(src[s_, t + 1])
+            if 1 <= j <= tw.shape[1]:
+                w_sp[s_, t] = tw[s_, j - 1]
+    mask = (ob["labels"][:, 1:] != -100).float()
+    pol_w = (ob["per_token_logps"].float() * w_sp * mask).sum(-1)
+    ref_pt = torch.zeros(2 * B, T - 1)
+    for kind, off in (("win", 0), ("rej", B)):
+        t_ = batch[f"ref_{kind}_per_token_logp_spliced"]
+        n = min(T - 1, t_.shape[1])
+        ref_pt[off:off + B, :n] = t_[:, :n]
+    ref_w = (ref_pt * w_sp * mask).sum(-1)
+    losses, cr, rj = O.dpo_loss(pol_w[:B], pol_w[B:], ref_w[:B], ref_w[B:], 0.1)
+    assert abs(md["loss"] - float(losses.mean())) <= 2e-3 * max(1.0, abs(float(losses.mean())))
+    assert abs(md["logps_train/chosen"] - float(pol_w[:B].mean())) <= 1e-3 * abs(float(pol_w[:B].mean()))
+    assert abs(md["logps_train/ref_rejected"] - float(ref_w[B:].mean())) <= 1e-5 * abs(float(ref_w[B:].mean()))
+    # --- all weights 1 == the unweighted engine (gradients too) ---
+    coll1 = DataCollatorForDPODataset(tokenizer=Tok(), beta=0.1, mod_token_weight=1.0, keep_spliced_per_token=True)
+    b1 = coll1(inst)
+    mask_rows = (ob["labels"][:, 1:] != -100).float()
+    b1["ref_win_logp"] = (ref_pt[:B] * mask_rows[:B]).sum(-1)
+    b1["ref_rej_logp"] = (ref_pt[B:] * mask_rows[B:]).sum(-1)
+    model.policy.store.grad.zero_()
+    mw = eng.train_step(dict(b1), optimizer_step=False).clone()
+    gw = model.policy.store.grad.float().clone()
+    eng_plain = DPOStepEngine(model.policy, lr=1e-3, total_steps=4, constant_lr=True)
+    model.policy.store.grad.zero_()
+    mp = eng_plain.train_step(dict(b1), optimizer_step=False).clone()
+    gp = model.policy.store.grad.float()
+    torch.cuda.synchronize()
+    assert abs(float(mw[0]) - float(mp[0])) <= 1e-5 * max(1.0, abs(float(mp[0])))
+    assert float((gw - gp).norm() / gp.norm()) <= 1e-3

@@ -26,6 +26,7 @@ dq32 = torch.zeros(nseq * S, H, device=dev, dtype=torch.float32)
 dqkv = torch.zeros(nseq * S, 3 * H, device=dev, dtype=torch.bfloat16)
 for _ in range(2):
     ops.attention_fwd(q, k, v, nseq, S, nh, D, True, scale, out, lse)
-    ops.attention_bwd(q, k, v, out, do, lse, nseq, S, nh, D, scale, dq32, dqkv[:, H:2 * H], dqkv[:, 2 * H:])
+    ops.attention_bwd_split(q, k, v, out, do, lse, nseq, S, S, nh, D, True, scale, dqkv[:, :H], dqkv[:, H:2 * H],
+                            dqkv[:, 2 * H:])
 torch.cuda.synchronize()
 print("done")
