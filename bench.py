@@ -16,7 +16,7 @@ fused fp32 AdamW, on BASELINE.json configs[1]: 8 synthetic pairs per GPU, 336x33
            every GEMM launch of one instrumented step, against MEASURED_PEAKS.json.
 `cpu_baseline` / `--impl reference`: the UNMODIFIED reference staged under oracle/_ref (oracle/stage_ref.py; the
            oracle port only if that staging is absent) on the host cores, on a bounded sample: full-width config-(a)
-           steps at 2 and 4 decoder layers after a warm-up, min of 3, extrapolated to 32 layers, raw timings in the
+           steps at 2 and 8 decoder layers after a warm-up, min of 3, extrapolated to 32 layers, raw timings in the
            line (see cpu_reference_pairs_per_sec); thread count calibrated against the container's real CPU quota.
 `parity_full_width`: checker leg — the CUDA path vs the oracle on the same full-width 1-layer model (log-probs,
            loss, gradients), with the reference's own bf16-vs-fp32 gap beside it.
@@ -279,7 +279,8 @@ def pick_cpu_threads():
     return best
 
 
-REF_ARM_LAYERS = (2, 4)     # full-width decoder depths that are timed; the 32-layer step is extrapolated linearly
+REF_ARM_LAYERS = (2, 8)     # full-width decoder depths that are timed; the 32-layer step is extrapolated linearly
+                            # (a 6-layer lever arm: with (2, 4) the x14 extrapolation turned 3 % timing noise into 15 %)
 
 
 def _time_cpu_steps(step_fn, warmup, reps):
@@ -360,8 +361,8 @@ def _port_step_fn(nl):
 
 def cpu_reference_pairs_per_sec(reps=3, warmup=1):
     """The reference arm / cpu_baseline leg: full-width (h=4096, ffn=11008, vocab=32000, CLIP-L 23 layers, 336 px)
-    config-(a) step (1 pair, 64-token responses, T=687), fp32, timed at 2 and 4 decoder layers after a warm-up pass
-    each (min of `reps`), extrapolated linearly to the 32-layer model: t32 = t4 + 28 * (t4 - t2) / 2.
+    config-(a) step (1 pair, 64-token responses, T=687), fp32, timed at 2 and 8 decoder layers after a warm-up pass
+    each (min of `reps`), extrapolated linearly to the 32-layer model: t32 = t8 + 24 * (t8 - t2) / 6.
     Returns (pairs/s, threads, kind, sample description, raw timings)."""
     from oracle import stage_ref
     threads = pick_cpu_threads()
@@ -402,7 +403,7 @@ def run_reference_arm(args, rank):
             "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "LLaVA-1.5-7B DPO step, reference CPU path (config (a) shape: 1 pair, 336px, 64-tok "
-                                   "responses; full width, 2- and 4-layer steps extrapolated to 32 layers)",
+                                   "responses; full width, 2- and 8-layer steps extrapolated to 32 layers)",
                        "timed_steps_per_depth": reps, "warmup_steps_per_depth": warm, "same_config_as_b200_arm": False,
                        "note": "BASELINE.json configs[0] is the reference's CPU-runnable case; configs[1] (8 pairs, "
                                "512-tok) would take ~15 min per CPU step"},
