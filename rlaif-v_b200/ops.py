@@ -392,7 +392,8 @@ def splice_token_weight(src, token_weight, T):
 def supervised_rows(labels, cap):
     """labels [nseq, T] int64 (spliced) -> row_pos int32 [nseq*cap]: flat positions s*T+t whose NEXT token is
     supervised (the rows get_batch_logps keeps), -1 in the unused slots of each sequence's cap-sized segment."""
-    assert labels.dtype == torch.int64 and labels.is_cuda and labels.is_contiguous()
+    _chk(labels, torch.int64)
+    assert labels.is_contiguous()
     nseq, T = labels.shape
     row_pos = torch.empty(nseq * cap, dtype=torch.int32, device=labels.device)
     _l.call("rlaifv_supervised_rows", _l.ptr(labels), nseq, T, int(cap), _l.ptr(row_pos), _l.stream_ptr())

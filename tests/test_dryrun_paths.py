@@ -57,7 +57,10 @@ def test_launch_sequence_dry_run(monkeypatch, use_lora, cfg_name):
     assert calls.count("rlaifv_attention_fwd") + calls.count("rlaifv_attention_fwd_gqa") == \
         dims.num_layers + dims.clip_layers_used
     assert calls.count("rlaifv_attention_fwd_gqa") == (dims.num_layers if gqa else 0)
-    assert calls.count("rlaifv_attention_bwd_gqa" if gqa else "rlaifv_attention_bwd") == dims.num_layers
+    # decoder backward: the split dK/dV + dQ kernels (one C-ABI entry for MHA and GQA), compact-head log-prob rows
+    assert calls.count("rlaifv_attention_bwd_split") == dims.num_layers
+    assert calls.count("rlaifv_supervised_rows") == 1 and calls.count("rlaifv_logp_fwd_rows") == 1
+    assert calls.count("rlaifv_logp_bwd_rows") == 1 and calls.count("rlaifv_rows_scatter") == 1
     names = {b.name for b in pol.trainable_buckets()}
     assert ("projector" in names) and (("lora0" in names) == use_lora) and (("embed" in names) != use_lora)
 
@@ -134,9 +137,10 @@ def test_omnilmm_policy_launch_sequence_dry_run(monkeypatch):
     out = pol.forward_logps(batch["concatenated_input_ids"], batch["concatenated_labels"], batch["vision_tokens"])
     tw = torch.ones(4, L - 1)
     lw, aw, ws = ops.logp_weighted_reduce(out["per_token_logps"], out["labels"], tw)
-    n_plain = calls.count("rlaifv_logp_bwd")
+    n_rows = calls.count("rlaifv_logp_bwd_rows")
     pol.backward_logps(torch.zeros(4), use_average=True, token_weight=tw, weight_sum=ws)
-    assert calls.count("rlaifv_logp_bwd_weighted") == 1 and calls.count("rlaifv_logp_bwd") == n_plain
+    # compact head: the weighted and the plain backward share the rows entry point (token_weight / norm arguments)
+    assert calls.count("rlaifv_logp_bwd_rows") == n_rows + 1 and calls.count("rlaifv_logp_bwd") == 0
     # generic get_beta_and_logps branch (forward_DPO) incl. --dpo_token_weighted, autograd bridge end to end
     from types import SimpleNamespace
     from rlaifv_b200 import trainers
@@ -149,12 +153,12 @@ def test_omnilmm_policy_launch_sequence_dry_run(monkeypatch):
               "ref_rej_logp": torch.zeros(2), "beta": 0.1, "images": batch["vision_tokens"],
               "concatenated_input_ids": ids, "concatenated_labels": labels, "concatenated_attention_mask": None}
         args = SimpleNamespace(dpo_use_average=False, dpo_token_weighted=weighted, task="DPO")
-        n_w = calls.count("rlaifv_logp_bwd_weighted")
+        n_w = calls.count("rlaifv_logp_bwd_rows")
         pw, pr, rw, rr, beta = trainers.get_beta_and_logps(dd, pol, args, is_llava15=False)
         assert pw.shape == (2,) and pr.shape == (2,) and pw.requires_grad and not dd
         losses, cr, rj = trainers.dpo_loss(pw, pr, rw, rr, beta)
         losses.mean().backward()
-        assert calls.count("rlaifv_logp_bwd_weighted") == n_w + (1 if weighted else 0)
+        assert calls.count("rlaifv_logp_bwd_rows") == n_w + 1
     with pytest.raises(ValueError):
         trainers.get_beta_and_logps({**{k: None for k in ("win_input_ids", "rej_input_ids", "ref_win_avg_logp",
                                                           "ref_rej_avg_logp", "ref_win_logp", "ref_rej_logp", "beta",
