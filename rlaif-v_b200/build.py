@@ -17,9 +17,8 @@ LIB = os.path.join(HERE, "librlaifv_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "--use_fast_math_off_placeholder",
+    "-Xcompiler", "-fPIC",
 ]
-FLAGS = [f for f in FLAGS if f != "--use_fast_math_off_placeholder"]
 
 
 def _sources():

@@ -73,6 +73,8 @@ cases = [
     (1, 128, 1, 128, True, True, 1.0), (1, 256, 2, 128, True, True, 1.0), (2, 300, 2, 128, True, True, 1.0),
     (2, 1135, 4, 128, True, True, 1.0), (2, 687, 4, 128, True, True, 3.0), (2, 1025, 2, 128, False, True, 1.0),
     (3, 70, 2, 128, False, True, 1.0), (1, 64, 1, 128, True, True, 1.0),
+    # large logits (lazy-rescale path taken on most tiles) and a long non-causal row
+    (1, 1135, 2, 128, True, False, 16.0), (2, 2049, 2, 128, False, False, 6.0), (2, 1100, 2, 64, False, False, 10.0),
 ]
 for cse in cases:
     try:
@@ -111,7 +113,13 @@ def bench(nseq, S, nh, D, causal, bwd, split=False):
 
 if fails == 0:
     try:
-        bench(16, 1135, 32, 128, True, False)
+        for var in (0, 1, 0, 1):                        # in-process A/B: single-tile kernel vs two-tile ping-pong
+            _lib.load().rlaifv_attention_set_variant(var)
+            print("forward variant", var, flush=True)
+            bench(16, 1135, 32, 128, True, False)
+            bench(4, 1025, 16, 128, False, False)
+            bench(16, 577, 16, 64, False, False)
+        _lib.load().rlaifv_attention_set_variant(_variant)
         bench(16, 1135, 32, 128, True, True)
         bench(16, 1135, 32, 128, True, True, split=True)
         bench(16, 577, 16, 64, False, False)

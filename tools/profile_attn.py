@@ -24,6 +24,10 @@ dq32 = torch.zeros(nseq * S, H, device="cuda", dtype=torch.float32)
 dqkv = torch.zeros(nseq * S, 3 * H, device="cuda", dtype=torch.bfloat16)
 for _ in range(2):
     ops.attention_fwd(q, k, v, nseq, S, nh, D, True, scale, out, lse)
+if "--fwd-ab" in sys.argv:                  # one launch of each forward variant, for a side-by-side capture
+    for var in (0, 1):
+        lib.load().rlaifv_attention_set_variant(var)
+        ops.attention_fwd(q, k, v, nseq, S, nh, D, True, scale, out, lse)
 if "--bwd" in sys.argv:
     for _ in range(2):
         ops.attention_bwd(q, k, v, out, d_out, lse, nseq, S, nh, D, scale, dq32, dqkv[:, H:2 * H], dqkv[:, 2 * H:])
