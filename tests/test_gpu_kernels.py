@@ -259,10 +259,10 @@ def test_splice_index_map_and_rows_bit_exact(max_len):
 
 
 EDGE_FX = os.path.join(os.path.dirname(__file__), "golden_host", "splice_edge_cases.npz")
-# two image tokens in one sequence do not occur on the DPO path (one image per sample); the case is pinned for the
-# oracle and kept here as a non-strict expectation until it has run on hardware
+# two image tokens in one sequence do not occur on the DPO path (one image per sample); the case is pinned anyway
+# (it passed on B200 in rounds 1 and 2, so it is a plain expectation now)
 EDGE_CASES = ["truncate_max_len_20", "truncate_inside_image", "no_image_sequence", "image_first_and_last", "very_ragged",
-              pytest.param("two_images_one_sequence", marks=pytest.mark.xfail(strict=False, reason="not yet run on a GPU"))]
+              "two_images_one_sequence"]
 
 
 @pytest.mark.parametrize("name", EDGE_CASES)
