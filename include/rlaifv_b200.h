@@ -58,6 +58,12 @@ int rlaifv_gemm_set_2cta(int enable);
 /* raster group size (row-blocks per group, default 16) and profiling switches (debug: bit0 skip stores,
  * bit1 skip TMEM loads too — results are then garbage; for roofline experiments only). */
 int rlaifv_gemm_set_tuning(int group_m, int debug);
+/* L2 policy of the CTA-pair kernel's TMA traffic: bits 0-1 A loads, 2-3 B loads, 4-5 C stores (0 normal, 1 evict
+ * first, 2 evict last); bit 6: raster walks n-fastest inside groups of group_m column blocks instead of m-fastest
+ * inside groups of row blocks. l2 < 0 (default): raster, group size and hints are chosen per launch from the shape
+ * (long-K launches keep the smaller operand's panels resident in the L2); l2 >= 0 forces the given bits together
+ * with rlaifv_gemm_set_tuning's group size. Process-wide; results are unaffected. */
+int rlaifv_gemm_set_l2(int l2);
 /* EXPERIMENTAL (default off): run GEMMs with K >= min_k and no bias / activation / residual as n K-slice passes
  * (passes 2.. with C +=) so each pass's operand slabs fit the L2. n <= 1 switches it off. */
 int rlaifv_gemm_set_split_k(int n, int min_k);

@@ -31,6 +31,8 @@ struct GemmEpilogue {
   int dynamic;     // 1: tiles drawn from the global counter; 0: static round-robin (tile = cta + i*grid)
   float alpha;     // != 1: result = bf16(bf16(acc) * alpha) first (LoRA scaling, peft: lora_B(...) * scaling)
   int tma_store;   // 1: C leaves through swizzled shared memory + cp.async.bulk.tensor stores (full 128-byte rows)
+  int l2;          // L2 policy of the CTA-pair kernel: bits 0-1 A loads, 2-3 B loads, 4-5 C stores (0 normal, 1 evict
+                   // first, 2 evict last); bit 6: raster groups column blocks (n-fastest inside groups of group_m)
 };
 
 // Optional second operand pair accumulated into the same TMEM tile after the first K loop:
@@ -74,7 +76,12 @@ struct GemmCfg {
   static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 512 + 1024;  // + barriers/queue + align
 };
 
-__device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int GROUP_M, int& m_blk, int& n_blk) {
+__device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int GROUP_M, int& m_blk, int& n_blk,
+                                            bool n_grouped = false) {
+  if (n_grouped) {            // same walk with the roles of m and n exchanged: groups of GROUP_M column blocks
+    tile_coords(t, num_n, num_m, GROUP_M, n_blk, m_blk, false);
+    return;
+  }
   int per_group = GROUP_M * num_n;
   int g = t / per_group;
   int first_m = g * GROUP_M;
@@ -219,7 +226,8 @@ __device__ __forceinline__ void epilogue_tile_tma(uint32_t t_addr, long long row
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
-      tma_store_2d(tmC, buf, col0, (int)row0);
+      if (epi.l2 & 0x30) tma_store_2d_hint(tmC, buf, col0, (int)row0, l2_policy((epi.l2 >> 4) & 3));
+      else tma_store_2d(tmC, buf, col0, (int)row0);
       tma_store_commit();
     }
     buf_sel ^= 1;
@@ -569,9 +577,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (++qs == GEMM_TQ) { qs = 0; qph ^= 1; }
         if (t < 0) break;
         int m_blk, n_blk;
-        tile_coords(t, num_m, num_n, epi.group_m, m_blk, n_blk);
+        tile_coords(t, num_m, num_n, epi.group_m, m_blk, n_blk, (epi.l2 & 0x40) != 0);
         const int m0 = m_blk * 256 + (int)cta_rank * 128;
         const int n0 = n_blk * BN + (int)cta_rank * 128;
+        const uint64_t pol_a = l2_policy(epi.l2 & 3), pol_b = l2_policy((epi.l2 >> 2) & 3);
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* a_dst = smem + s * GEMM2_STAGE_BYTES;
@@ -588,16 +597,16 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (A_MN) {
 #pragma unroll
               for (int a = 0; a < 2; ++a)
-                tma_load_2d_2sm(a_dst + a * (GEMM_BK * 128), mA, leader_full, m0 + a * 64, kA);
+                tma_load_2d_2sm_hint(a_dst + a * (GEMM_BK * 128), mA, leader_full, m0 + a * 64, kA, pol_a);
             } else {
-              tma_load_2d_2sm(a_dst, mA, leader_full, kA, m0);
+              tma_load_2d_2sm_hint(a_dst, mA, leader_full, kA, m0, pol_a);
             }
             if (B_MN) {
 #pragma unroll
               for (int a = 0; a < 2; ++a)
-                tma_load_2d_2sm(b_dst + a * (GEMM_BK * 128), mB, leader_full, n0 + a * 64, kB);
+                tma_load_2d_2sm_hint(b_dst + a * (GEMM_BK * 128), mB, leader_full, n0 + a * 64, kB, pol_b);
             } else {
-              tma_load_2d_2sm(b_dst, mB, leader_full, kB, n0);
+              tma_load_2d_2sm_hint(b_dst, mB, leader_full, kB, n0, pol_b);
             }
           }
           if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -665,7 +674,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (++qs == GEMM_TQ) { qs = 0; qph ^= 1; }
       if (t < 0) break;
       int m_blk, n_blk;
-      tile_coords(t, num_m, num_n, epi.group_m, m_blk, n_blk);
+      tile_coords(t, num_m, num_n, epi.group_m, m_blk, n_blk, (epi.l2 & 0x40) != 0);
       const int acc = it & 1;
       const uint32_t acc_ph = (it >> 1) & 1;
       mbar_wait(&tfull[acc], acc_ph);
@@ -777,6 +786,28 @@ extern "C" int rlaifv_gemm_set_tuning(int group_m, int debug) {
   g_tma_store = (debug & 8) ? 0 : 1;
   return 0;
 }
+// L2 policy of the CTA-pair kernel (GemmEpilogue::l2); the 1-CTA kernel ignores the load policies and the raster bit.
+// l2 < 0 (default): chosen per launch by l2_auto_policy() below; l2 >= 0: the given bits for every launch.
+static int g_l2 = -1;
+extern "C" int rlaifv_gemm_set_l2(int l2) {
+  g_l2 = l2 < 0 ? -1 : (l2 & 0x7f);
+  return 0;
+}
+// Long-K launches (dgrad / wgrad / down projection: K = 11008 .. 22016) have 256-row operand panels of 6-11 MB; with
+// the default raster (16 row blocks per group) the panels one wave of 74 CTA pairs touches (130+ MB) fall out of the
+// L2 before the next wave needs them again and the launch reads 4-5x its operands from DRAM (ncu: dgrad qkv 3.2 GB vs
+// 0.55 GB of operands). Grouping along the SHORTER tile dimension keeps the smaller operand's panels resident while the
+// larger one streams: DRAM reads = (streamed operand) x ceil(blocks / group) + (resident operand), and the resident set
+// (group x panel) has to stay well under the L2: 8 panels up to K = 16384, 4 beyond. The resident operand's TMA loads
+// carry evict_last, the streamed one's evict_first. Measured (tools/gpu_gemm_l2_sweep.py, profiles/r02u_*): dgrad qkv
+// 3.20 -> 1.65 GB, wgrad qkv 4.32 -> 2.27 GB, dgrad gate|up 8.28 -> 4.8-5.1 GB per launch. Results are bit-identical.
+static void l2_auto_policy(int M, int N, int K, int* l2, int* group) {
+  if (K < 8192) return;                                    // short K: panels are small, the default raster is the best
+  const bool n_grouped = N < M;
+  *group = K <= 16384 ? 8 : 4;
+  *l2 = n_grouped ? (0x40 | 1 | (2 << 2))                  // column blocks grouped: B resident, A streams
+                  : (2 | (1 << 2));                        // row blocks grouped: A resident, B streams
+}
 // auto-selection policy for tile_n = 0: 0 never, 1 whenever the problem is large, 2 (default) where measured faster
 static int g_enable_2cta = 2;
 extern "C" int rlaifv_gemm_set_2cta(int enable) {
@@ -880,6 +911,13 @@ static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B
   epi.group_m = g_group_m;
   epi.debug = g_debug & 3;
   epi.dynamic = (g_debug & 4) ? 0 : 1;
+  epi.l2 = 0;
+  if (bn == 512) {
+    if (g_l2 < 0) l2_auto_policy(M, N, K, &epi.l2, &epi.group_m);
+    else epi.l2 = g_l2;
+  } else if (g_l2 > 0) {
+    epi.l2 = g_l2 & 0x30;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   if (bn == 512) {
     if (!a_mn_major && !b_mn_major) return launch_gemm2<false, false>(tmA, tmB, tmA2, tmB2, tmC, M, N, K, src2, epi, st);

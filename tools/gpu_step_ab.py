@@ -5,6 +5,7 @@ the only comparison that is reliable on the power-capped part):
   fwd_variant: attention forward ping-pong kernel (1) vs single-tile kernel (0)
 
     python tools/gpu_step_ab.py
+    python tools/gpu_step_ab.py --l2      # GEMM L2 raster / eviction-hint policy: per-shape (auto) vs the fixed raster
 """
 import itertools
 import os
@@ -50,6 +51,16 @@ def measure(n=4):
 
 for _ in range(2):
     eng.train_step(batch)
+if "--l2" in sys.argv:
+    res = {-1: [], 0: []}
+    for rnd in range(5):
+        for l2 in (0, -1):
+            L.rlaifv_gemm_set_l2(l2)
+            res[l2].append(measure())
+    L.rlaifv_gemm_set_l2(-1)
+    for l2, name in ((0, "fixed raster (16 row blocks per group, no hints)"), (-1, "per-shape policy (default)")):
+        print("%-50s: %s ms/step  mean %.1f" % (name, ["%.1f" % t for t in res[l2]], sum(res[l2]) / len(res[l2])))
+    sys.exit(0)
 configs = [(1, 1, 1), (0, 1, 1), (1, 0, 1), (0, 0, 1), (0, 0, 0)]
 res = {c: [] for c in configs}
 for rnd in range(3):
