@@ -800,7 +800,9 @@ extern "C" int rlaifv_gemm_set_l2(int l2) {
 // larger one streams: DRAM reads = (streamed operand) x ceil(blocks / group) + (resident operand), and the resident set
 // (group x panel) has to stay well under the L2: 8 panels up to K = 16384, 4 beyond. The resident operand's TMA loads
 // carry evict_last, the streamed one's evict_first. Measured (tools/gpu_gemm_l2_sweep.py, profiles/r02u_*): dgrad qkv
-// 3.20 -> 1.65 GB, wgrad qkv 4.32 -> 2.27 GB, dgrad gate|up 8.28 -> 4.8-5.1 GB per launch. Results are bit-identical.
+// 3.20 -> 1.65 GB, wgrad qkv 4.32 -> 2.27 GB, dgrad gate|up 8.28 -> 4.8-5.1 GB per launch; the config-(b) step 665.5 ->
+// 654.1 ms in-process (profiles/r02u_step_ab_l2_policy.log). The raster is what pays: hints off, group 4 / 6 / 8 all
+// land within 0.1 % of each other at step level (profiles/r02u_step_ab_l2_variants.log). Results are bit-identical.
 static void l2_auto_policy(int M, int N, int K, int* l2, int* group) {
   if (K < 8192) return;                                    // short K: panels are small, the default raster is the best
   const bool n_grouped = N < M;
