@@ -51,6 +51,17 @@ def measure(n=4):
 
 for _ in range(2):
     eng.train_step(batch)
+if "--splitk" in sys.argv:     # K-sliced passes for the longest-K launches only (dgrad of gate|up, K = 22016)
+    variants = ((0, 0), (2, 20000), (2, 16384))
+    res = {v: [] for v in variants}
+    for rnd in range(4):
+        for v in variants:
+            L.rlaifv_gemm_set_split_k(*v)
+            res[v].append(measure(3))
+    L.rlaifv_gemm_set_split_k(0, 0)
+    for v in variants:
+        print("split_k n=%d min_k=%d: %s ms/step  mean %.1f" % (v + (["%.1f" % t for t in res[v]], sum(res[v]) / len(res[v]))))
+    sys.exit(0)
 if "--l2" in sys.argv:
     res = {-1: [], 0: []}
     for rnd in range(5):
