@@ -26,6 +26,45 @@ __device__ __forceinline__ float fast_exp2(float x) {   // MUFU.EX2, flush-to-ze
   return y;
 }
 
+// One warp writes its 32 rows x (NCH*32) bf16 columns — held in TMEM as fp32, one row per lane — to global memory with
+// coalesced stores. The row-per-lane form (each lane writes 16-byte pieces of its own row) makes every store
+// instruction touch 32 different rows; with one CTA per SM nothing overlaps the epilogue and ncu showed the compute
+// warps of the backward kernels spending 18-26 % of their time there. Each row is staged as NCH*64 bytes in a per-warp
+// shared buffer (16-byte chunks XOR-swizzled by the row so that neither the row-per-lane writes nor the row-major
+// reads conflict), then every instruction writes whole rows: 2 rows x 256 bytes (D = 128) or 4 x 128 bytes.
+// `mul` scales the row (1/l in the forward), `rows_valid` clips the rows beyond the sequence end.
+template <int NCH>
+__device__ __forceinline__ void store_tile_rows(uint32_t taddr, float mul, uint8_t* stage, int lane, bf16* g_row0,
+                                                long long ld, int rows_valid) {
+  constexpr int ROW_B = NCH * 64;            // bytes per staged row
+  constexpr int CPR = ROW_B / 16;            // 16-byte chunks per row
+  constexpr int RPI = 32 / CPR;              // rows per store instruction
+#pragma unroll 1
+  for (int ch = 0; ch < NCH; ++ch) {
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(taddr + ch * 32, v);
+    tmem_wait_ld();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint4 u;
+      u.x = pack_bf16(__uint_as_float(v[g * 8 + 0]) * mul, __uint_as_float(v[g * 8 + 1]) * mul);
+      u.y = pack_bf16(__uint_as_float(v[g * 8 + 2]) * mul, __uint_as_float(v[g * 8 + 3]) * mul);
+      u.z = pack_bf16(__uint_as_float(v[g * 8 + 4]) * mul, __uint_as_float(v[g * 8 + 5]) * mul);
+      u.w = pack_bf16(__uint_as_float(v[g * 8 + 6]) * mul, __uint_as_float(v[g * 8 + 7]) * mul);
+      const int c = ch * 4 + g;
+      *reinterpret_cast<uint4*>(stage + lane * ROW_B + ((c ^ (lane & (CPR - 1))) << 4)) = u;
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 32 / RPI; ++it) {
+    const int r = it * RPI + lane / CPR, c = lane % CPR;
+    const uint4 u = *reinterpret_cast<const uint4*>(stage + r * ROW_B + ((c ^ (r & (CPR - 1))) << 4));
+    if (r < rows_valid) *reinterpret_cast<uint4*>(g_row0 + (long long)r * ld + c * 8) = u;
+  }
+  __syncwarp();
+}
+
 // ================================================================================================
 // forward
 // ================================================================================================
@@ -525,28 +564,17 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         tc_fence_before();
         mbar_arrive(&p_full[x]);
       }
-      // epilogue
+      // epilogue: O / l -> bf16, staged through this tile's Q buffer (its last S MMA is complete once o_final fires)
       mbar_wait(&o_final[x], 0);
       tc_fence_after();
       const float inv = 1.f / l;
       const bool row_ok = q_idx < Sq;
-      bf16* o_row = out + ((long long)seq * Sq + q_idx) * ld_out + head * D;
-#pragma unroll 1
-      for (int ch = 0; ch < D / 32; ++ch) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tO + ch * 32, v);
-        tmem_wait_ld();
-        if (row_ok) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4 u;
-            u.x = pack_bf16(__uint_as_float(v[g * 8 + 0]) * inv, __uint_as_float(v[g * 8 + 1]) * inv);
-            u.y = pack_bf16(__uint_as_float(v[g * 8 + 2]) * inv, __uint_as_float(v[g * 8 + 3]) * inv);
-            u.z = pack_bf16(__uint_as_float(v[g * 8 + 4]) * inv, __uint_as_float(v[g * 8 + 5]) * inv);
-            u.w = pack_bf16(__uint_as_float(v[g * 8 + 6]) * inv, __uint_as_float(v[g * 8 + 7]) * inv);
-            *reinterpret_cast<uint4*>(o_row + ch * 32 + g * 8) = u;
-          }
-        }
+      {
+        const int wq = warp & 3;
+        const int row0 = qt[x] * ATT_BQ + wq * 32;                        // first query row of this warp
+        uint8_t* stage = smem + Cfg::OFF_Q + x * Cfg::Q_BYTES + wq * (32 * D * 2);
+        store_tile_rows<D / 32>(tO, inv, stage, lane, out + ((long long)seq * Sq + row0) * ld_out + head * D, ld_out,
+                                Sq - row0);
       }
       if (row_ok && lse_out)
         lse_out[((long long)seq * n_heads + head) * Sq + q_idx] = (m_used + log2f(l)) * LN2;
@@ -895,8 +923,8 @@ struct AttBwd2Cfg {
   static constexpr uint32_t OFF_RES0 = 0;                         // dkv: K   | dq: Q
   static constexpr uint32_t OFF_RES1 = TILE_BYTES;                // dkv: V   | dq: dO
   static constexpr uint32_t OFF_RING = 2 * TILE_BYTES;            // [STAGES][2 chunks]: dkv Q,dO | dq K,V
-  static constexpr uint32_t OFF_STAT = OFF_RING + STAGES * 2 * CHUNK_BYTES;   // dkv: [2 groups][lse 64 | delta 64] fp32
-  static constexpr uint32_t OFF_BAR = OFF_STAT + 2 * 2 * CH * 4;
+  static constexpr uint32_t OFF_STAT = OFF_RING + STAGES * 2 * CHUNK_BYTES;   // dkv: [2 groups][2 buffers][lse 64 | delta 64] fp32
+  static constexpr uint32_t OFF_BAR = OFF_STAT + 2 * 2 * 2 * CH * 4;
   static constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;
   static constexpr uint32_t TMEM_COLS = 512;
 };
@@ -1036,23 +1064,28 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     const int kv_idx = kv0 + r;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t tST = tmem_base + g * CH + lane_off, tDPT = tmem_base + 128 + g * CH + lane_off;
-    float* s_lse = reinterpret_cast<float*>(smem + Cfg::OFF_STAT) + g * 2 * CH;
-    float* s_delta = s_lse + CH;
+    float* s_stat = reinterpret_cast<float*>(smem + Cfg::OFF_STAT) + g * 4 * CH;   // [2 buffers][lse 64 | delta 64]
     const float c = scale * LOG2E;
     const int tid_g = threadIdx.x & 127;
-    for (int it = g; it < n_it; it += 2) {
+    // lse (threads 0-63) / delta (64-127) of the 64 query rows of chunk `it`: loaded one chunk ahead into a register
+    // and parked in the other half of a double buffer at the end of the iteration, so the global-load latency is off
+    // the S^T -> P^T chain (it used to sit between two named barriers at the top of every iteration)
+    auto load_stat = [&](int it) -> float {
       const int head = kv_head * kv_group + it / n_ch;
+      const int q = q_begin + (it % n_ch) * CH + (tid_g & 63);
+      const long long base = ((long long)seq * n_heads + head) * Sq;
+      if (q >= Sq) return tid_g < 64 ? INFINITY : 0.f;                      // exp2(x - inf) = 0 for padded rows
+      return tid_g < 64 ? lse[base + q] * LOG2E : delta[base + q];
+    };
+    if (g < n_it) s_stat[tid_g] = load_stat(g);
+    int k = 0;                                      // this group's iteration count: buffer k & 1
+    for (int it = g; it < n_it; it += 2, ++k) {
       const int q0 = q_begin + (it % n_ch) * CH;
-      // stage lse / delta of the 64 query rows of this chunk (named barrier per group: ids 1, 2)
+      // one named barrier per iteration (ids 1, 2): publishes buffer k&1, and everyone is done reading buffer (k+1)&1
       asm volatile("bar.sync %0, 128;" ::"r"(g + 1));
-      {
-        const int j = tid_g & 63;
-        const int q = q0 + j;
-        const long long base = ((long long)seq * n_heads + head) * Sq;
-        if (tid_g < 64) s_lse[j] = q < Sq ? lse[base + q] * LOG2E : INFINITY;     // exp2(x - inf) = 0 for padded rows
-        else s_delta[j] = q < Sq ? delta[base + q] : 0.f;
-      }
-      asm volatile("bar.sync %0, 128;" ::"r"(g + 1));
+      const float* s_lse = s_stat + (k & 1) * 2 * CH;
+      const float* s_delta = s_lse + CH;
+      const float next_stat = (it + 2 < n_it) ? load_stat(it + 2) : 0.f;
       mbar_wait(&st_full[g], (it >> 1) & 1);
       tc_fence_after();
       uint32_t sv[64], dpv[64];
@@ -1088,31 +1121,18 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(&pt_full[g]);
+      s_stat[((k + 1) & 1) * 2 * CH + tid_g] = next_stat;
     }
     // epilogue: group 0 stores dV, group 1 stores dK (kv row r)
     mbar_wait(acc_done, 0);
     tc_fence_after();
     {
-      const bool row_ok = kv_idx < Skv;
-      bf16* o_row = (g == 0 ? dv : dk) + ((long long)seq * Skv + kv_idx) * ld_dkv + kv_head * D;
-      const uint32_t tA = tmem_base + 256 + g * 128 + lane_off;
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t a[32];
-        tmem_ld_32x32b_x32(tA + ch * 32, a);
-        tmem_wait_ld();
-        if (row_ok) {
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            uint4 u;
-            u.x = pack_bf16(__uint_as_float(a[q4 * 8 + 0]), __uint_as_float(a[q4 * 8 + 1]));
-            u.y = pack_bf16(__uint_as_float(a[q4 * 8 + 2]), __uint_as_float(a[q4 * 8 + 3]));
-            u.z = pack_bf16(__uint_as_float(a[q4 * 8 + 4]), __uint_as_float(a[q4 * 8 + 5]));
-            u.w = pack_bf16(__uint_as_float(a[q4 * 8 + 6]), __uint_as_float(a[q4 * 8 + 7]));
-            *reinterpret_cast<uint4*>(o_row + ch * 32 + q4 * 8) = u;
-          }
-        }
-      }
+      // every MMA is complete (acc_done), so the Q/dO ring is free: 8 KB of it per warp stages the coalesced stores
+      const int row0 = kv0 + (warp & 3) * 32;
+      uint8_t* stage = smem + Cfg::OFF_RING + warp * (32 * D * 2);
+      store_tile_rows<D / 32>(tmem_base + 256 + g * 128 + lane_off, 1.f, stage, lane,
+                              (g == 0 ? dv : dk) + ((long long)seq * Skv + row0) * ld_dkv + kv_head * D, ld_dkv,
+                              Skv - row0);
     }
   }
   tc_fence_before();
@@ -1137,9 +1157,9 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   uint64_t* q_full = bars + 0;
   uint64_t* ring_full = bars + 1;
   uint64_t* ring_empty = bars + 1 + STAGES;
-  uint64_t* s_full = bars + 1 + 2 * STAGES;       // [2]
-  uint64_t* ds_full = s_full + 2;                 // [2]  (128 arrivals)
-  uint64_t* acc_done = ds_full + 2;
+  uint64_t* s_full = bars + 1 + 2 * STAGES;       // [3]
+  uint64_t* ds_full = s_full + 3;                 // [3]  (128 arrivals)
+  uint64_t* acc_done = ds_full + 3;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1156,7 +1176,7 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
       mbar_init(q_full, 1);
       for (int i = 0; i < STAGES; ++i) { mbar_init(&ring_full[i], 1); mbar_init(&ring_empty[i], 1); }
-      for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&ds_full[i], 128); }
+      for (int i = 0; i < 3; ++i) { mbar_init(&s_full[i], 1); mbar_init(&ds_full[i], 128); }
       mbar_init(acc_done, 1);
       fence_barrier_init();
     }
@@ -1167,7 +1187,12 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // columns: S[b] = b*64, dP[b] = 128 + b*64, dQ = 256
+  // columns: dQ = 256..383; THREE S / dP buffers (b = chunk % 3): S[b] = b*64, dP[b] = 128 + b*64 for b < 2 and
+  // S[2] = 384, dP[2] = 448. With two buffers S(it+2) could only be issued after dS(it) had been consumed, so each compute
+  // group waited for "dQ MMA + next S/dP MMAs + commit latency" after every chunk (44 % of its time in the ncu sampling);
+  // with three, S/dP run two chunks ahead and never wait on the chunk being processed.
+  auto s_col = [&](int b) -> uint32_t { return b < 2 ? (uint32_t)(b * CH) : 384u; };
+  auto dp_col = [&](int b) -> uint32_t { return b < 2 ? (uint32_t)(128 + b * CH) : 448u; };
 
   if (warp >= 8) {
    setmaxnreg_dec<56>();
@@ -1196,7 +1221,7 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       const bool leader = elect_one();
       const uint64_t qd = desc_kmajor(smem_u32(smem + Cfg::OFF_RES0), 0), dod = desc_kmajor(smem_u32(smem + Cfg::OFF_RES1), 0);
       auto issue_s = [&](int it) {
-        const int s = it % STAGES, b = it & 1;
+        const int s = it % STAGES, b = it % 3;
         mbar_wait(&ring_full[s], (it / STAGES) & 1);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(smem + Cfg::OFF_RING + s * 2 * Cfg::CHUNK_BYTES);
@@ -1205,12 +1230,12 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 #pragma unroll
           for (int k16 = 0; k16 < D / 16; ++k16) {    // S = Q K^T
             const uint64_t oa = (uint64_t)((k16 >> 2) * (128 * 8) + (k16 & 3) * 2), ob = (uint64_t)((k16 >> 2) * (CH * 8) + (k16 & 3) * 2);
-            umma_ss(tmem_base + b * CH, qd + oa, kd + ob, idesc_s, k16 > 0);
+            umma_ss(tmem_base + s_col(b), qd + oa, kd + ob, idesc_s, k16 > 0);
           }
 #pragma unroll
           for (int k16 = 0; k16 < D / 16; ++k16) {    // dP = dO V^T
             const uint64_t oa = (uint64_t)((k16 >> 2) * (128 * 8) + (k16 & 3) * 2), ob = (uint64_t)((k16 >> 2) * (CH * 8) + (k16 & 3) * 2);
-            umma_ss(tmem_base + 128 + b * CH, dod + oa, vd + ob, idesc_s, k16 > 0);
+            umma_ss(tmem_base + dp_col(b), dod + oa, vd + ob, idesc_s, k16 > 0);
           }
           umma_commit(&s_full[b]);
         }
@@ -1218,16 +1243,18 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       };
       mbar_wait(q_full, 0);
       issue_s(0);
+      if (n_it > 1) issue_s(1);
       for (int it = 0; it < n_it; ++it) {
-        if (it + 1 < n_it) issue_s(it + 1);
-        const int s = it % STAGES, b = it & 1;
-        mbar_wait(&ds_full[b], (it >> 1) & 1);
+        // buffer (it+2) % 3 == (it-1) % 3 was released by the dQ MMA of chunk it-1, issued by this thread just before
+        if (it + 2 < n_it) issue_s(it + 2);
+        const int s = it % STAGES, b = it % 3;
+        mbar_wait(&ds_full[b], (it / 3) & 1);
         tc_fence_after();
         const uint64_t km = desc_mnmajor(smem_u32(smem + Cfg::OFF_RING + s * 2 * Cfg::CHUNK_BYTES), 0, CH);
         if (leader) {
 #pragma unroll
           for (int k16 = 0; k16 < CH / 16; ++k16)     // dQ += dS K   (A = dS in TMEM, B = K chunk read MN-major)
-            umma_ts(tmem_base + 256, tmem_base + 128 + b * CH + k16 * 8, km + (uint64_t)(k16 * 128), idesc_acc,
+            umma_ts(tmem_base + 256, tmem_base + dp_col(b) + k16 * 8, km + (uint64_t)(k16 * 128), idesc_acc,
                     (it > 0 || k16 > 0));
           umma_commit(&ring_empty[s]);
         }
@@ -1244,14 +1271,15 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     const int r = (warp & 3) * 32 + lane;
     const int q_idx = q0 + r;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t tS = tmem_base + g * CH + lane_off, tDP = tmem_base + 128 + g * CH + lane_off;
     const float c = scale * LOG2E;
     const long long sbase = ((long long)seq * n_heads + head) * Sq;
     const float my_lse = q_idx < Sq ? lse[sbase + q_idx] * LOG2E : INFINITY;
     const float my_delta = q_idx < Sq ? delta[sbase + q_idx] : 0.f;
     for (int it = g; it < n_it; it += 2) {
       const int kvc = it * CH;
-      mbar_wait(&s_full[g], (it >> 1) & 1);
+      const int b = it % 3;
+      const uint32_t tS = tmem_base + s_col(b) + lane_off, tDP = tmem_base + dp_col(b) + lane_off;
+      mbar_wait(&s_full[b], (it / 3) & 1);
       tc_fence_after();
       uint32_t sv[64], dpv[64];
       tmem_ld_32x32b_x64(tS, sv);
@@ -1280,32 +1308,17 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       }
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(&ds_full[g]);
+      mbar_arrive(&ds_full[b]);
     }
     // epilogue: group g stores dQ columns [g*64, g*64+64) of its row
     mbar_wait(acc_done, 0);
     tc_fence_after();
     {
-      const bool row_ok = q_idx < Sq;
-      bf16* o_row = dq + ((long long)seq * Sq + q_idx) * ld_dq + head * D + g * 64;
-      const uint32_t tA = tmem_base + 256 + g * 64 + lane_off;
-#pragma unroll 1
-      for (int ch = 0; ch < 2; ++ch) {
-        uint32_t a[32];
-        tmem_ld_32x32b_x32(tA + ch * 32, a);
-        tmem_wait_ld();
-        if (row_ok) {
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            uint4 u;
-            u.x = pack_bf16(__uint_as_float(a[q4 * 8 + 0]), __uint_as_float(a[q4 * 8 + 1]));
-            u.y = pack_bf16(__uint_as_float(a[q4 * 8 + 2]), __uint_as_float(a[q4 * 8 + 3]));
-            u.z = pack_bf16(__uint_as_float(a[q4 * 8 + 4]), __uint_as_float(a[q4 * 8 + 5]));
-            u.w = pack_bf16(__uint_as_float(a[q4 * 8 + 6]), __uint_as_float(a[q4 * 8 + 7]));
-            *reinterpret_cast<uint4*>(o_row + ch * 32 + q4 * 8) = u;
-          }
-        }
-      }
+      // every MMA is complete (acc_done): the K/V ring is free, 4 KB of it per warp stages the coalesced stores
+      const int row0 = q0 + (warp & 3) * 32;
+      uint8_t* stage = smem + Cfg::OFF_RING + warp * (32 * 128);
+      store_tile_rows<2>(tmem_base + 256 + g * 64 + lane_off, 1.f, stage, lane,
+                         dq + ((long long)seq * Sq + row0) * ld_dq + head * D + g * 64, ld_dq, Sq - row0);
     }
   }
   tc_fence_before();
