@@ -52,6 +52,16 @@ int rlaifv_gemm_bf16_dual(const void* A, long long lda, int a_mn_major, const vo
                           void* C, long long ldc, int M, int N, int K, const void* bias, const void* residual,
                           long long ldr, int act, int accumulate, void* stream);
 
+/* Fused SwiGLU backward (replaces the autograd of `down_proj(act_fn(gate_proj(x)) * up_proj(x))`, HF
+ * llama/modeling_llama.py:182-184, between the down-projection dgrad and the gate|up dgrad): with
+ * d = bf16(A[M,K] @ op(B)^T) = d(act) [M, F] held in the accumulator,
+ *   dgu[:, n] = d * up * silu'(gate),   dgu[:, F + n] = d * silu(gate)      (gu = [gate | up], [M, 2F], bf16)
+ * are written by the GEMM epilogue; d(act) never reaches memory. F % 64 == 0. Optional second operand pair
+ * (A2 [M, K2], B2, K2 > 0) accumulated into the same tile as in rlaifv_gemm_bf16_dual with n_sub = 0. */
+int rlaifv_gemm_bf16_swiglu_bwd(const void* A, long long lda, const void* B, long long ldb, int b_mn_major,
+                                const void* A2, long long lda2, const void* B2, long long ldb2, int K2, const void* gu,
+                                long long ld_gu, void* dgu, long long ld_dgu, int M, int F, int K, void* stream);
+
 /* tile_n = 512 selects the 2-CTA kernel (cta_group::2, 256x256 tile per CTA pair). rlaifv_gemm_set_2cta(1)
  * lets tile_n = 0 (auto) pick it for large problems. */
 int rlaifv_gemm_set_2cta(int enable);

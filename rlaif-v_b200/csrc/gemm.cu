@@ -31,6 +31,8 @@ struct GemmEpilogue {
   int dynamic;     // 1: tiles drawn from the global counter; 0: static round-robin (tile = cta + i*grid)
   float alpha;     // != 1: result = bf16(bf16(acc) * alpha) first (LoRA scaling, peft: lora_B(...) * scaling)
   int tma_store;   // 1: C leaves through swizzled shared memory + cp.async.bulk.tensor stores (full 128-byte rows)
+  const bf16* glu; // non-null: fused SwiGLU backward. The accumulator tile is d(act) [M, N = F]; glu = [gate | up] rows
+  long long ld_glu;//   [M, 2F]; C = d[gate | up] [M, 2F]: C[:, n] = d*u*silu'(g), C[:, F + n] = d*silu(g)  (d = bf16(acc))
   int l2;          // L2 policy of the CTA-pair kernel: bits 0-1 A loads, 2-3 B loads, 4-5 C stores (0 normal, 1 evict
                    // first, 2 evict last); bit 6: raster groups column blocks (n-fastest inside groups of group_m)
 };
@@ -234,6 +236,84 @@ __device__ __forceinline__ void epilogue_tile_tma(uint32_t t_addr, long long row
   }
 }
 
+// Fused SwiGLU backward (HF llama/modeling_llama.py:182-184 under autograd): the GEMM computes d(act) = dy @ W_down for
+// a 256-column slice of F; instead of writing it out for a separate elementwise pass (0.4 GB written + read back per
+// layer, one more launch) the epilogue reads the matching gate / up values and writes d(gate) and d(up) straight into
+// the [M, 2F] gradient of the fused gate|up projection. d is rounded to bf16 first (the reference materialises it), the
+// arithmetic is swiglu_bwd_kernel's (rowops.cu). Uses both staging buffers of the warp per 64-column step (one for each
+// output half), so it waits for the previous step's two stores before restaging.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile_glu(uint32_t t_addr, long long row0, long long row, bool row_ok, int n0,
+                                                  int N, const GemmEpilogue& epi, const CUtensorMap* tmC,
+                                                  uint8_t* warp_stage, int lane) {
+  const bf16* g_row = epi.glu + row * epi.ld_glu;
+  uint8_t* buf_g = warp_stage;
+  uint8_t* buf_u = warp_stage + EPI_BUF_BYTES;
+  // gate / up values of one 64-column step: 8 + 8 16-byte loads per lane (this lane's row), fetched one step ahead of
+  // the arithmetic (the first version loaded inside the step and waited ~1.5 us eight times per tile — longer than the
+  // main loop of the next tile, which made the GEMM epilogue-bound)
+  uint4 cur[16], nxt[16];
+  auto load_step = [&](int c64, uint4 (&dst)[16]) {
+    const int col0 = n0 + c64 * 64;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int col = col0 + i * 8;
+      const bool ok = row_ok && col < N;
+      dst[i] = ok ? *reinterpret_cast<const uint4*>(g_row + col) : make_uint4(0u, 0u, 0u, 0u);
+      dst[8 + i] = ok ? *reinterpret_cast<const uint4*>(g_row + N + col) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  };
+  load_step(0, cur);
+#pragma unroll 1
+  for (int c64 = 0; c64 < BN / 64; ++c64) {
+    const int col0 = n0 + c64 * 64;
+    if (col0 >= N) break;
+    if (c64 + 1 < BN / 64) load_step(c64 + 1, nxt);
+    if (lane == 0) tma_store_wait_read<0>();
+    __syncwarp();
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(t_addr + c64 * 64 + half * 32, r);
+      tmem_wait_ld();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const uint4 gq = cur[half * 4 + g], uq = cur[8 + half * 4 + g];
+        float gv[8], uv[8], dg[8], du[8];
+        const float2 g0 = unpack_bf16(gq.x), g1 = unpack_bf16(gq.y), g2 = unpack_bf16(gq.z), g3 = unpack_bf16(gq.w);
+        const float2 u0 = unpack_bf16(uq.x), u1 = unpack_bf16(uq.y), u2 = unpack_bf16(uq.z), u3 = unpack_bf16(uq.w);
+        gv[0] = g0.x; gv[1] = g0.y; gv[2] = g1.x; gv[3] = g1.y; gv[4] = g2.x; gv[5] = g2.y; gv[6] = g3.x; gv[7] = g3.y;
+        uv[0] = u0.x; uv[1] = u0.y; uv[2] = u1.x; uv[3] = u1.y; uv[4] = u2.x; uv[5] = u2.y; uv[6] = u3.x; uv[7] = u3.y;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          // 128 threads per SM do this arithmetic (the separate pass has 2048): approximate reciprocal (2 ulp, far
+          // below the bf16 rounding of the result) instead of the IEEE division sequence
+          const float d = bf16_round(__uint_as_float(r[g * 8 + j]));
+          const float sg = __fdividef(1.f, 1.f + __expf(-gv[j]));
+          const float silu = gv[j] * sg;
+          du[j] = d * silu;
+          dg[j] = d * uv[j] * (sg * (1.f + gv[j] * (1.f - sg)));
+        }
+        uint4 og, ou;
+        og.x = pack_bf16(dg[0], dg[1]); og.y = pack_bf16(dg[2], dg[3]); og.z = pack_bf16(dg[4], dg[5]); og.w = pack_bf16(dg[6], dg[7]);
+        ou.x = pack_bf16(du[0], du[1]); ou.y = pack_bf16(du[2], du[3]); ou.z = pack_bf16(du[4], du[5]); ou.w = pack_bf16(du[6], du[7]);
+        const int chunk = (half * 4 + g) ^ (lane & 7);            // SWIZZLE_128B, as in epilogue_chunk_staged
+        *reinterpret_cast<uint4*>(buf_g + lane * 128 + chunk * 16) = og;
+        *reinterpret_cast<uint4*>(buf_u + lane * 128 + chunk * 16) = ou;
+      }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(tmC, buf_g, col0, (int)row0);
+      tma_store_2d(tmC, buf_u, N + col0, (int)row0);
+      tma_store_commit();
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
+  }
+}
+
 template <bool A_MN, bool B_MN, int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -420,6 +500,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool row_ok = row < M;
       const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
       if (epi.tma_store && !(epi.debug & 3)) {
+        if (epi.glu)
+          epilogue_tile_glu<BN>(t_addr, (long long)m_blk * GEMM_BM + quad * 32, row, row_ok, n_blk * BN, N, epi, &tmC,
+                                warp_stage, lane);
+        else
         epilogue_tile_tma<BN>(t_addr, (long long)m_blk * GEMM_BM + quad * 32, row, row_ok, n_blk * BN, N, epi, &tmC,
                               warp_stage, lane, buf_sel);
       } else {
@@ -683,6 +767,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const bool row_ok = row < M;
       const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
       if (epi.tma_store && !(epi.debug & 3)) {
+        if (epi.glu)
+          epilogue_tile_glu<BN>(t_addr, (long long)m_blk * 256 + (int)cta_rank * 128 + quad * 32, row, row_ok, n_blk * BN,
+                                N, epi, &tmC, warp_stage, lane);
+        else
         epilogue_tile_tma<BN>(t_addr, (long long)m_blk * 256 + (int)cta_rank * 128 + quad * 32, row, row_ok, n_blk * BN,
                               N, epi, &tmC, warp_stage, lane, buf_sel);
       } else {
@@ -833,9 +921,16 @@ static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B
                      void* C, long long ldc, int M, int N, int K, const void* bias, const void* residual,
                      long long ldr, int act, int accumulate, int tile_n, float alpha, void* stream,
                      const void* A2 = nullptr, long long lda2 = 0, const void* B2 = nullptr, long long ldb2 = 0,
-                     int K2 = 0, int r2 = 0, int n_sub = 0) {
+                     int K2 = 0, int r2 = 0, int n_sub = 0, const void* glu = nullptr, long long ld_glu = 0) {
   B200_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
-  if (g_split_k > 1 && K2 == 0 && !bias && !residual && act == 0 && K >= g_split_k_min_k) {
+  if (glu) {
+    B200_REQUIRE(!bias && !residual && act == 0 && !accumulate && alpha == 1.0f,
+                 "gemm (swiglu_bwd epilogue): no bias / residual / activation / accumulate / alpha");
+    B200_REQUIRE(N % 64 == 0 && ld_glu % 8 == 0 && ld_glu >= 2LL * N && ldc >= 2LL * N,
+                 "gemm (swiglu_bwd epilogue): F = %d must be a multiple of 64, gate|up rows at least 2F wide", N);
+    B200_REQUIRE(((uintptr_t)glu & 15) == 0, "gemm (swiglu_bwd epilogue): gate|up not 16-byte aligned");
+  }
+  if (g_split_k > 1 && K2 == 0 && !bias && !residual && act == 0 && !glu && K >= g_split_k_min_k) {
     const int n = g_split_k;
     const int ks = ((K + n - 1) / n + GEMM_BK - 1) / GEMM_BK * GEMM_BK;   // slice = whole 64-wide k blocks
     g_split_k = 0;                                   // the passes themselves are ordinary launches
@@ -895,11 +990,12 @@ static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B
   CUtensorMap tmC = tmA;
   int use_tma_store = g_tma_store;
   if (use_tma_store) {
-    uint64_t cdims[2] = {(uint64_t)N, (uint64_t)M};
+    uint64_t cdims[2] = {(uint64_t)(glu ? 2 * N : N), (uint64_t)M};      // swiglu_bwd epilogue: C is [M, 2F]
     uint64_t cstr[1] = {(uint64_t)ldc * 2};
     uint32_t cbox[2] = {64, 32};
     if (make_tmap_bf16(&tmC, C, 2, cdims, cstr, cbox) != 0) use_tma_store = 0;    // odd view: direct stores instead
   }
+  B200_REQUIRE(!glu || use_tma_store, "gemm (swiglu_bwd epilogue): needs the TMA-store epilogue (C view not mappable)");
   GemmEpilogue epi;
   epi.tma_store = use_tma_store;
   epi.C = (bf16*)C;
@@ -910,6 +1006,8 @@ static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B
   epi.act = act;
   epi.accumulate = accumulate;
   epi.alpha = alpha;
+  epi.glu = (const bf16*)glu;
+  epi.ld_glu = ld_glu;
   epi.group_m = g_group_m;
   epi.debug = g_debug & 3;
   epi.dynamic = (g_debug & 4) ? 0 : 1;
@@ -954,6 +1052,16 @@ extern "C" int rlaifv_gemm_bf16_scaled(const void* A, long long lda, int a_mn_ma
 
 // C (+)= A*B^T + A2[:, koff:koff+K2] * B2^T (shared fp32 accumulator, one rounding), then bias/act/residual.
 // koff = (n0 / n_sub) * r when n_sub > 0 (forward over fused sub-linears), else 0. Same operand majors as A/B.
+// d[gate | up] = swiglu_bwd([gate | up], dy @ op(W)^T) in one launch — see epilogue_tile_glu. Optional second operand
+// pair (K2 > 0) as in rlaifv_gemm_bf16_dual (LoRA: d(act) = dy W + (s dy B) A).
+extern "C" int rlaifv_gemm_bf16_swiglu_bwd(const void* A, long long lda, const void* B, long long ldb, int b_mn_major,
+                                           const void* A2, long long lda2, const void* B2, long long ldb2, int K2,
+                                           const void* gu, long long ld_gu, void* dgu, long long ld_dgu, int M, int F,
+                                           int K, void* stream) {
+  B200_REQUIRE(gu && dgu, "gemm_swiglu_bwd: gate|up / output missing");
+  return gemm_impl(A, lda, 0, B, ldb, b_mn_major, dgu, ld_dgu, M, F, K, nullptr, nullptr, 0, 0, 0, 0, 1.0f, stream, A2,
+                   lda2, B2, ldb2, K2, K2, 0, gu, ld_gu);
+}
 extern "C" int rlaifv_gemm_bf16_dual(const void* A, long long lda, int a_mn_major, const void* B, long long ldb,
                                      int b_mn_major, const void* A2, long long lda2, const void* B2, long long ldb2,
                                      int K2, int r, int n_sub, void* C, long long ldc, int M, int N, int K,

@@ -366,6 +366,9 @@ class LlavaDPOPolicy:
         self.compact_head = True
         # attention backward as two kernels (dK/dV, dQ) without fp32 atomics; False = the fused round-1 kernel
         self.split_attention_bwd = True
+        # SwiGLU backward inside the epilogue of the down-projection dgrad (no d(act) round trip, one launch less per
+        # layer); False = separate swiglu_bwd pass
+        self.fuse_swiglu_bwd = True
         self.embed_grad_f32 = None   # fp32 scatter target for embedding rows (allocated lazily)
         self._stash = None
         self.lora = None             # LoraStore: base weights frozen, adapters + mm_projector trainable
@@ -436,11 +439,15 @@ class LlavaDPOPolicy:
             ls["t_" + group] = t
         return out
 
-    def _lin_bwd(self, i, group, dy, x, dx_out, ls, acc):
-        """dx = dy @ W (+ adapter path); weight gradients: base (full FT) or adapters (LoRA)."""
+    def _lin_bwd(self, i, group, dy, x, dx_out, ls, acc, glu=None):
+        """dx = dy @ W (+ adapter path); weight gradients: base (full FT) or adapters (LoRA).
+        glu (down projection only): the layer's gate|up pre-activations [M, 2F]; dx_out is then [M, 2F] and receives
+        swiglu_bwd(glu, dy @ W) from the GEMM epilogue — d(act) stays in the accumulator (ops.gemm_swiglu_bwd)."""
         W = self.store.p[f"l{i}.{group}"]
         if self.lora is None:
             ops.gemm(dy, x, self.store.g[f"l{i}.{group}"], a_mn=True, b_mn=True, accumulate=acc)
+            if glu is not None:
+                return ops.gemm_swiglu_bwd(dy, W, glu, dx_out)
             return ops.gemm(dy, W, dx_out, b_mn=True)
         L = self.lora
         a_name, b_names, _ = self._GROUPS[group]
@@ -458,11 +465,15 @@ class LlavaDPOPolicy:
             # dropout on the adapter input: dA sees the dropped input, and the adapter's dx passes through the mask
             xd = ops.dropout_fwd(x, L.dropout, seed, out=self.buf("lora_xd_%d" % x.shape[1], tuple(x.shape)))
             ops.gemm(dt, xd, L.g[f"l{i}.{a_name}"], a_mn=True, b_mn=True, accumulate=acc)             # dA = dt^T drop(x)
-            ops.gemm(dy, W, dx_out, b_mn=True)
+            dx_plain = dx_out if glu is None else self.buf("dact", tuple(x.shape))
+            ops.gemm(dy, W, dx_plain, b_mn=True)
             pa = ops.gemm(dt, A, self.buf("lora_xd_%d" % x.shape[1], tuple(x.shape)), b_mn=True)                       # dt @ A
-            return ops.dropout_bwd_add(dx_out, pa, L.dropout, seed)
+            ops.dropout_bwd_add(dx_plain, pa, L.dropout, seed)
+            return dx_plain if glu is None else ops.swiglu_bwd(glu, dx_plain, dx_out)
         ops.gemm(dt, x, L.g[f"l{i}.{a_name}"], a_mn=True, b_mn=True, accumulate=acc)                  # dA = dt^T x
         # dx = dy @ W + dt @ A in one pass (second source = stacked lora_A, MN-major like W)
+        if glu is not None:
+            return ops.gemm_swiglu_bwd(dy, W, glu, dx_out, a2=dt, b2=A)
         return ops.gemm_dual(dy, W, dt, A, dx_out, k2=A.shape[0], r=r, n_sub=0, b_mn=True)
 
     # ------------------------------------------------------------------ init / buffers
@@ -719,8 +730,12 @@ class LlavaDPOPolicy:
             ls = st["layers"][i]
             # ---- MLP ----
             act = ls["act"] if "act" in ls else ops.swiglu_fwd(ls["gu"], self.buf("act", (M, F)))   # recompute
-            dact = self._lin_bwd(i, "down", dx, act, self.buf("dact", (M, F)), ls, acc)
-            dgu = ops.swiglu_bwd(ls["gu"], dact, self.buf("dgu", (M, 2 * F)))
+            if self.fuse_swiglu_bwd and F % 64 == 0:
+                # d(act) = dx @ W_down never leaves the GEMM: its epilogue applies the SwiGLU backward
+                dgu = self._lin_bwd(i, "down", dx, act, self.buf("dgu", (M, 2 * F)), ls, acc, glu=ls["gu"])
+            else:
+                dact = self._lin_bwd(i, "down", dx, act, self.buf("dact", (M, F)), ls, acc)
+                dgu = ops.swiglu_bwd(ls["gu"], dact, self.buf("dgu", (M, 2 * F)))
             n2 = ls["n2"] if "n2" in ls else ops.rmsnorm_fwd(ls["x2"], P[f"l{i}.ln2"], d.rms_eps,
                                                              out=self.buf("n", (M, H)))             # recompute
             dn2 = self._lin_bwd(i, "gu", dgu, n2, self.buf("dn", (M, H)), ls, acc)

@@ -517,6 +517,23 @@ def gemm_dual(a, b, a2, b2, out, *, k2, r, n_sub=0, b_mn=False, residual=None, a
     return out
 
 
+def gemm_swiglu_bwd(dy, w, gu, dgu, *, b_mn=True, a2=None, b2=None):
+    """dgu [M, 2F] = swiglu_bwd(gu, dy @ op(w)^T (+ a2 @ op(b2)^T)) with d(act) kept in the GEMM accumulator
+    (dy [M, K], w [K, F] when b_mn else [F, K], gu = [gate | up] [M, 2F])."""
+    _chk(dy), _chk(w), _chk(gu), _chk(dgu)
+    M, K = dy.shape
+    F = w.shape[1] if b_mn else w.shape[0]
+    assert gu.shape == (M, 2 * F) and dgu.shape == (M, 2 * F) and gu.stride(1) == 1 and dgu.stride(1) == 1
+    k2 = 0
+    if a2 is not None:
+        _chk(a2), _chk(b2)
+        k2 = a2.shape[1]
+    _l.call("rlaifv_gemm_bf16_swiglu_bwd", _l.ptr(dy), dy.stride(0), _l.ptr(w), w.stride(0), int(b_mn), _l.ptr(a2),
+            a2.stride(0) if a2 is not None else 0, _l.ptr(b2), b2.stride(0) if b2 is not None else 0, int(k2), _l.ptr(gu),
+            gu.stride(0), _l.ptr(dgu), dgu.stride(0), M, F, K, _l.stream_ptr())
+    return dgu
+
+
 def dropout_fwd(x, p, seed, out=None):
     _chk(x)
     assert x.is_contiguous()

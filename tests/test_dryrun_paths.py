@@ -48,8 +48,10 @@ def test_launch_sequence_dry_run(monkeypatch, use_lora, cfg_name):
     pol.finalize_embed_grad()
     assert len(calls) > 2 * n_fwd * 0.8
     per_layer_gemm = 4
+    # the down-projection dgrad carries the SwiGLU backward in its epilogue (no separate swiglu_bwd pass)
+    assert calls.count("rlaifv_gemm_bf16_swiglu_bwd") == dims.num_layers and calls.count("rlaifv_swiglu_bwd") == 0
     if use_lora:
-        assert calls.count("rlaifv_gemm_bf16_dual") == 2 * per_layer_gemm * dims.num_layers   # fwd + dgrad
+        assert calls.count("rlaifv_gemm_bf16_dual") == (2 * per_layer_gemm - 1) * dims.num_layers   # fwd + dgrad
         assert "rlaifv_f32_to_bf16" in calls                # projected-image-row gradients still flow
     else:
         assert calls.count("rlaifv_gemm_bf16_dual") == 0

@@ -66,6 +66,32 @@ def test_gemm_epilogues_and_views():
 
 
 
+@pytest.mark.parametrize("M,F,K,k2", [(300, 512, 256, 0), (1136, 1408, 520, 0), (520, 768, 384, 16)])
+def test_gemm_swiglu_bwd_epilogue_matches_two_step_path(M, F, K, k2):
+    """rlaifv_gemm_bf16_swiglu_bwd: d[gate|up] from the down-projection dgrad's epilogue vs (i) the unfused kernels
+    (GEMM -> bf16 d(act) -> swiglu_bwd) and (ii) fp32 torch autograd of silu(g) * u on the bf16-rounded d(act)."""
+    from rlaifv_b200 import ops
+    dy = (torch.randn(M, K, device=DEV) * 0.5).to(BF)
+    w = (torch.randn(K, F, device=DEV) * 0.1).to(BF)                     # W_down stored [H, F]: MN-major B operand
+    gu = torch.randn(M, 2 * F, device=DEV).to(BF)
+    a2 = b2 = None
+    if k2:
+        a2 = (torch.randn(M, k2, device=DEV) * 0.5).to(BF)
+        b2 = (torch.randn(k2, F, device=DEV) * 0.1).to(BF)
+    dact = ops.gemm(dy, w, b_mn=True) if not k2 else ops.gemm_dual(dy, w, a2, b2, torch.empty(M, F, device=DEV, dtype=BF),
+                                                                  k2=k2, r=k2, n_sub=0, b_mn=True)
+    two_step = ops.swiglu_bwd(gu, dact, torch.empty(M, 2 * F, device=DEV, dtype=BF))
+    fused = ops.gemm_swiglu_bwd(dy, w, gu, torch.full((M, 2 * F), float("nan"), device=DEV, dtype=BF), a2=a2, b2=b2)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(fused.float()).all())
+    assert rel(fused.float(), two_step.float()) <= 8e-3 and float((fused.float() - two_step.float()).abs().mean()) <= 1e-4
+    g = gu[:, :F].float().requires_grad_()
+    u = gu[:, F:].float().requires_grad_()
+    (torch.nn.functional.silu(g) * u).backward(dact.float())
+    ref = torch.cat([g.grad, u.grad], dim=1)
+    assert rel(fused.float(), ref) <= 8e-3
+
+
 @pytest.mark.parametrize("a_mn,b_mn,M,N,K", [(False, True, 2100, 1024, 8320), (True, True, 1024, 2104, 8320),
                                              (False, False, 1500, 1280, 16448)])
 def test_gemm_long_k_raster_and_l2_hints_do_not_change_results(a_mn, b_mn, M, N, K):

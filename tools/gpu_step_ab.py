@@ -6,6 +6,7 @@ the only comparison that is reliable on the power-capped part):
 
     python tools/gpu_step_ab.py
     python tools/gpu_step_ab.py --l2      # GEMM L2 raster / eviction-hint policy: per-shape (auto) vs the fixed raster
+    python tools/gpu_step_ab.py --swiglu  # SwiGLU backward fused into the down-projection dgrad epilogue vs separate
 """
 import itertools
 import os
@@ -51,6 +52,16 @@ def measure(n=4):
 
 for _ in range(2):
     eng.train_step(batch)
+if "--swiglu" in sys.argv:     # SwiGLU backward in the down-projection dgrad epilogue vs the separate pass
+    res = {True: [], False: []}
+    for rnd in range(5):
+        for v in (False, True):
+            pol.fuse_swiglu_bwd = v
+            res[v].append(measure())
+    pol.fuse_swiglu_bwd = True
+    for v, name in ((False, "separate swiglu_bwd pass"), (True, "fused into the dgrad epilogue (default)")):
+        print("%-42s: %s ms/step  mean %.1f" % (name, ["%.1f" % t for t in res[v]], sum(res[v]) / len(res[v])))
+    sys.exit(0)
 if "--splitk" in sys.argv:     # K-sliced passes for the longest-K launches only (dgrad of gate|up, K = 22016)
     variants = ((0, 0), (2, 20000), (2, 16384))
     res = {v: [] for v in variants}
