@@ -16,6 +16,18 @@ for _ in range(3):
     ops.gemm(x, w, y)                                   # forward  (K-major, K-major)
     ops.gemm(dy, w, dx, b_mn=True)                      # dgrad    (K-major, MN-major)
     ops.gemm(dy, x, dw, a_mn=True, b_mn=True)           # wgrad    (MN-major, MN-major)
+# the two largest launches of the backward: gate|up dgrad (K = 22016) and the down-projection dgrad with the SwiGLU
+# backward in its epilogue
+w_gu = torch.randn(2 * F, H, device=dev).bfloat16() * 0.02
+w_dn = torch.randn(H, F, device=dev).bfloat16() * 0.02
+dgu = torch.randn(M, 2 * F, device=dev).bfloat16()
+gu = torch.randn(M, 2 * F, device=dev).bfloat16()
+dx3 = torch.randn(M, H, device=dev).bfloat16()
+dgu_out = torch.empty(M, 2 * F, device=dev, dtype=torch.bfloat16)
+for _ in range(2):
+    ops.gemm(dgu, w_gu, dx, b_mn=True)                  # dgrad gate|up
+    ops.gemm_swiglu_bwd(dx3, w_dn, gu, dgu_out)         # dgrad down + SwiGLU backward epilogue
+del w_gu, w_dn, dgu, gu, dx3, dgu_out
 nseq, S, nh, D = 16, 1135, 32, 128
 qkv = torch.randn(nseq * S, 3 * H, device=dev).bfloat16()
 q, k, v = qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:]

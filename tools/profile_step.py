@@ -17,6 +17,7 @@ from rlaifv_b200.model import LlavaDims, LlavaDPOPolicy
 torch.cuda.set_device(0)
 B = bench.PAIRS_PER_GPU
 policy = LlavaDPOPolicy(LlavaDims(), torch.device("cuda", 0), seed=0)
+policy.stash_act = True            # bench.py's single-GPU policy (SwiGLU product stashed, norms recomputed)
 engine = DPOStepEngine(policy, lr=5e-7, weight_decay=0.01, total_steps=2672, micro_pairs=B)
 hb = bench.synthetic_batch(0, 0, B)
 out = policy.forward_logps(hb["concatenated_input_ids"], hb["concatenated_labels"], hb["images"], keep_stash=False)
