@@ -1,12 +1,18 @@
-// Fused attention for sm_100a on tcgen05: S = Q K^T and O += P V run on the 5th-gen tensor cores
-// with S / O accumulators in TMEM; softmax is done one-thread-per-query-row straight out of TMEM
-// (no shuffles), P goes back through SWIZZLE_128B shared memory as the A operand of the PV MMA.
+// Fused attention for sm_100a on tcgen05: S = Q K^T and O += P V run on the 5th-gen tensor cores with the S / O
+// accumulators in TMEM; softmax is done one-thread-per-query-row straight out of TMEM (no shuffles).
 //
-//   forward : causal, d=128 (Llama; HF llama/modeling_llama.py:199-222, attention_mask=None =>
-//             pure causal, pads attended — muffin/train/trainers.py:199) and non-causal, d=64
-//             (CLIP; HF clip/modeling_clip.py:261-279). Softmax in fp32, P rounded to bf16 before PV.
-//   backward: causal d=128; recomputes S^T / dP^T per (kv tile, q tile), five MMAs per pair;
-//             dK/dV accumulate in TMEM, dQ is reduced with fp32 red.global.add.
+//   forward  (attention_fwd2_kernel, default): two 128-row query tiles per CTA ping-pong against the tensor pipe; P is
+//             packed back into its own S columns and consumed as the TMEM A operand of the PV MMA. Causal d=128
+//             (Llama; HF llama/modeling_llama.py:199-222, attention_mask=None => pure causal, pads attended —
+//             muffin/train/trainers.py:199), non-causal d=64 (CLIP; HF clip/modeling_clip.py:261-279) and d=128
+//             (EVA tower, heads padded 112 -> 128). Softmax in fp32, P rounded to bf16 before PV.
+//             attention_fwd_kernel is the round-1 single-tile kernel (P through shared memory), still selectable.
+//   backward (attention_bwd_dkv_kernel + attention_bwd_dq_kernel, default): dK/dV per 128-row K/V tile, dQ per
+//             128-row Q tile, both streaming 64-row chunks of the other side; S^T / dP^T (S / dP) are recomputed per
+//             chunk, P^T / dS^T / dS go back into the TMEM columns they came from as A operands; no atomics, dQ is
+//             written once as bf16. attention_bwd_kernel is the fused round-1 kernel (five MMAs per tile pair, dQ
+//             reduced with fp32 red.global.add); it serves the resampler's shared-query cross-attention.
+//   Epilogues stage each warp's 32 rows in shared memory and write whole rows (store_tile_rows).
 //
 // Layouts: q/k/v/o are [nseq*S rows][ld] bf16 with head h at columns [h*D, h*D+D); q, k, v may be
 // column blocks of one fused qkv buffer. LSE is fp32 [nseq][n_heads][S] (natural log).
