@@ -372,18 +372,43 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   const int n_of[2] = {CAUSAL ? qt[0] + 1 : n_kv_all, has_b ? (CAUSAL ? qt[1] + 1 : n_kv_all) : 0};
   const int n_kv = n_of[0] > n_of[1] ? n_of[0] : n_of[1];
 
+  // The producer thread initialises the barriers its loads complete on and issues the Q tiles and the first K/V
+  // stages before the CTA-wide sync: TMEM allocation and the other barriers overlap the load latency.
+  auto load_kv = [&](int j) {
+    const int s = j % STAGES;
+    mbar_arrive_expect_tx(&kv_full[s], 2 * Cfg::KV_BYTES);
+#pragma unroll
+    for (int a = 0; a < D / 64; ++a) {
+      tma_load_3d(smem + Cfg::OFF_K + s * Cfg::KV_BYTES + a * (ATT_BKV * 128), &tmK, &kv_full[s], kv_head * D + a * 64,
+                  j * ATT_BKV, seq);
+      tma_load_3d(smem + Cfg::OFF_V + s * Cfg::KV_BYTES + a * (ATT_BKV * 128), &tmV, &kv_full[s], kv_head * D + a * 64,
+                  j * ATT_BKV, seq);
+    }
+  };
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    for (int i = 0; i < 2; ++i) mbar_init(&q_full[i], 1);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    fence_barrier_init();
+    for (int x = 0; x < 2; ++x) {
+      if (x == 1 && !has_b) break;
+      mbar_arrive_expect_tx(&q_full[x], Cfg::Q_BYTES);
+#pragma unroll
+      for (int a = 0; a < D / 64; ++a)
+        tma_load_3d(smem + Cfg::OFF_Q + x * Cfg::Q_BYTES + a * (ATT_BQ * 128), &tmQ, &q_full[x], head * D + a * 64,
+                    qt[x] * ATT_BQ, q_seq);
+    }
+    for (int j = 0; j < n_kv && j < STAGES; ++j) load_kv(j);
+  }
   if (warp == 9) {
     if (lane == 0) {
-      tma_prefetch_desc(&tmQ);
-      tma_prefetch_desc(&tmK);
-      tma_prefetch_desc(&tmV);
       for (int i = 0; i < 2; ++i) {
-        mbar_init(&q_full[i], 1);
         mbar_init(&s_full[i], 1);
         mbar_init(&p_full[i], 128);
         mbar_init(&o_final[i], 1);
       }
-      for (int i = 0; i < STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -399,25 +424,9 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
    if (warp == 8) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
-      for (int x = 0; x < 2; ++x) {
-        if (x == 1 && !has_b) break;
-        mbar_arrive_expect_tx(&q_full[x], Cfg::Q_BYTES);
-#pragma unroll
-        for (int a = 0; a < D / 64; ++a)
-          tma_load_3d(smem + Cfg::OFF_Q + x * Cfg::Q_BYTES + a * (ATT_BQ * 128), &tmQ, &q_full[x], head * D + a * 64,
-                      qt[x] * ATT_BQ, q_seq);
-      }
-      for (int j = 0; j < n_kv; ++j) {
-        const int s = j % STAGES;
-        if (j >= STAGES) mbar_wait(&kv_empty[s], ((j / STAGES) - 1) & 1);
-        mbar_arrive_expect_tx(&kv_full[s], 2 * Cfg::KV_BYTES);
-#pragma unroll
-        for (int a = 0; a < D / 64; ++a) {
-          tma_load_3d(smem + Cfg::OFF_K + s * Cfg::KV_BYTES + a * (ATT_BKV * 128), &tmK, &kv_full[s],
-                      kv_head * D + a * 64, j * ATT_BKV, seq);
-          tma_load_3d(smem + Cfg::OFF_V + s * Cfg::KV_BYTES + a * (ATT_BKV * 128), &tmV, &kv_full[s],
-                      kv_head * D + a * 64, j * ATT_BKV, seq);
-        }
+      for (int j = STAGES; j < n_kv; ++j) {          // the first STAGES tiles were issued before the CTA sync
+        mbar_wait(&kv_empty[j % STAGES], ((j / STAGES) - 1) & 1);
+        load_kv(j);
       }
     }
   } else if (warp == 9) {
@@ -967,11 +976,33 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   const int n_ch = (Sq - q_begin + CH - 1) / CH;                   // chunks per query head
   const int n_it = n_ch * kv_group;
 
+  // producer thread: own barriers, resident K / V tile and the first ring stages before the CTA-wide sync (see the dQ
+  // kernel)
+  auto load_chunk = [&](int it) {
+    const int s = it % STAGES;
+    const int head = kv_head * kv_group + it / n_ch;
+    const int q0 = q_begin + (it % n_ch) * CH;
+    uint8_t* dst = smem + Cfg::OFF_RING + s * 2 * Cfg::CHUNK_BYTES;
+    mbar_arrive_expect_tx(&ring_full[s], 2 * Cfg::CHUNK_BYTES);
+    for (int a = 0; a < 2; ++a) {
+      tma_load_3d(dst + a * (CH * 128), &tmQ, &ring_full[s], head * D + a * 64, q0, seq);
+      tma_load_3d(dst + Cfg::CHUNK_BYTES + a * (CH * 128), &tmDO, &ring_full[s], head * D + a * 64, q0, seq);
+    }
+  };
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&ring_full[i], 1); mbar_init(&ring_empty[i], 1); }
+    fence_barrier_init();
+    mbar_arrive_expect_tx(kv_full, 2 * Cfg::TILE_BYTES);
+    for (int a = 0; a < 2; ++a) {
+      tma_load_3d(smem + Cfg::OFF_RES0 + a * 16384, &tmK, kv_full, kv_head * D + a * 64, kv0, seq);
+      tma_load_3d(smem + Cfg::OFF_RES1 + a * 16384, &tmV, kv_full, kv_head * D + a * 64, kv0, seq);
+    }
+    for (int it = 0; it < n_it && it < STAGES; ++it) load_chunk(it);
+  }
   if (warp == 9) {
     if (lane == 0) {
-      tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
-      mbar_init(kv_full, 1);
-      for (int i = 0; i < STAGES; ++i) { mbar_init(&ring_full[i], 1); mbar_init(&ring_empty[i], 1); }
       for (int i = 0; i < 2; ++i) { mbar_init(&st_full[i], 1); mbar_init(&pt_full[i], 128); }
       mbar_init(acc_done, 1);
       fence_barrier_init();
@@ -990,22 +1021,9 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
    if (warp == 8) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
-      mbar_arrive_expect_tx(kv_full, 2 * Cfg::TILE_BYTES);
-      for (int a = 0; a < 2; ++a) {
-        tma_load_3d(smem + Cfg::OFF_RES0 + a * 16384, &tmK, kv_full, kv_head * D + a * 64, kv0, seq);
-        tma_load_3d(smem + Cfg::OFF_RES1 + a * 16384, &tmV, kv_full, kv_head * D + a * 64, kv0, seq);
-      }
-      for (int it = 0; it < n_it; ++it) {
-        const int s = it % STAGES;
-        if (it >= STAGES) mbar_wait(&ring_empty[s], ((it / STAGES) - 1) & 1);
-        const int head = kv_head * kv_group + it / n_ch;
-        const int q0 = q_begin + (it % n_ch) * CH;
-        uint8_t* dst = smem + Cfg::OFF_RING + s * 2 * Cfg::CHUNK_BYTES;
-        mbar_arrive_expect_tx(&ring_full[s], 2 * Cfg::CHUNK_BYTES);
-        for (int a = 0; a < 2; ++a) {
-          tma_load_3d(dst + a * (CH * 128), &tmQ, &ring_full[s], head * D + a * 64, q0, seq);
-          tma_load_3d(dst + Cfg::CHUNK_BYTES + a * (CH * 128), &tmDO, &ring_full[s], head * D + a * 64, q0, seq);
-        }
+      for (int it = STAGES; it < n_it; ++it) {       // the first STAGES chunks were issued before the CTA sync
+        mbar_wait(&ring_empty[it % STAGES], ((it / STAGES) - 1) & 1);
+        load_chunk(it);
       }
     }
    } else if (warp == 9) {
@@ -1177,11 +1195,32 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   const int kv_end = causal ? min(Skv, q0 + 128) : Skv;            // keys [0, kv_end) are visible to this tile
   const int n_it = (kv_end + CH - 1) / CH;
 
+  // The producer thread initialises the barriers its loads complete on and starts the resident Q / dO tiles and the
+  // first ring stages right away; TMEM allocation, the other barriers and the CTA-wide sync overlap the load latency
+  // (with ~10 chunks per CTA the prologue is a visible share of the kernel).
+  auto load_chunk = [&](int it) {
+    const int s = it % STAGES;
+    uint8_t* dst = smem + Cfg::OFF_RING + s * 2 * Cfg::CHUNK_BYTES;
+    mbar_arrive_expect_tx(&ring_full[s], 2 * Cfg::CHUNK_BYTES);
+    for (int a = 0; a < 2; ++a) {
+      tma_load_3d(dst + a * (CH * 128), &tmK, &ring_full[s], kv_head * D + a * 64, it * CH, seq);
+      tma_load_3d(dst + Cfg::CHUNK_BYTES + a * (CH * 128), &tmV, &ring_full[s], kv_head * D + a * 64, it * CH, seq);
+    }
+  };
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&ring_full[i], 1); mbar_init(&ring_empty[i], 1); }
+    fence_barrier_init();
+    mbar_arrive_expect_tx(q_full, 2 * Cfg::TILE_BYTES);
+    for (int a = 0; a < 2; ++a) {
+      tma_load_3d(smem + Cfg::OFF_RES0 + a * 16384, &tmQ, q_full, head * D + a * 64, q0, seq);
+      tma_load_3d(smem + Cfg::OFF_RES1 + a * 16384, &tmDO, q_full, head * D + a * 64, q0, seq);
+    }
+    for (int it = 0; it < n_it && it < STAGES; ++it) load_chunk(it);
+  }
   if (warp == 9) {
     if (lane == 0) {
-      tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
-      mbar_init(q_full, 1);
-      for (int i = 0; i < STAGES; ++i) { mbar_init(&ring_full[i], 1); mbar_init(&ring_empty[i], 1); }
       for (int i = 0; i < 3; ++i) { mbar_init(&s_full[i], 1); mbar_init(&ds_full[i], 128); }
       mbar_init(acc_done, 1);
       fence_barrier_init();
@@ -1204,20 +1243,9 @@ attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
    setmaxnreg_dec<56>();
    if (warp == 8) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, 2 * Cfg::TILE_BYTES);
-      for (int a = 0; a < 2; ++a) {
-        tma_load_3d(smem + Cfg::OFF_RES0 + a * 16384, &tmQ, q_full, head * D + a * 64, q0, seq);
-        tma_load_3d(smem + Cfg::OFF_RES1 + a * 16384, &tmDO, q_full, head * D + a * 64, q0, seq);
-      }
-      for (int it = 0; it < n_it; ++it) {
-        const int s = it % STAGES;
-        if (it >= STAGES) mbar_wait(&ring_empty[s], ((it / STAGES) - 1) & 1);
-        uint8_t* dst = smem + Cfg::OFF_RING + s * 2 * Cfg::CHUNK_BYTES;
-        mbar_arrive_expect_tx(&ring_full[s], 2 * Cfg::CHUNK_BYTES);
-        for (int a = 0; a < 2; ++a) {
-          tma_load_3d(dst + a * (CH * 128), &tmK, &ring_full[s], kv_head * D + a * 64, it * CH, seq);
-          tma_load_3d(dst + Cfg::CHUNK_BYTES + a * (CH * 128), &tmV, &ring_full[s], kv_head * D + a * 64, it * CH, seq);
-        }
+      for (int it = STAGES; it < n_it; ++it) {       // the first STAGES chunks were issued before the CTA sync
+        mbar_wait(&ring_empty[it % STAGES], ((it / STAGES) - 1) & 1);
+        load_chunk(it);
       }
     }
    } else if (warp == 9) {
